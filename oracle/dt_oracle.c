@@ -1,0 +1,342 @@
+/*
+ * dt_oracle.c -- CPU restatement of h2oai/datatable's DT[i, j, by(), sort()] hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (datatable_b200/) may
+ * link, import or call this file; it is used by tests/, by
+ * __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference
+ * legs as the *checker*, never as the thing measured or shipped.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function
+ * here against fixtures under tests/golden/ that were produced by importing
+ * the reference itself (built from /root/reference, commit 3611640) with
+ * tests/golden/make_golden.py, which also restates the reference's own
+ * known-answer vectors (tests/ijby/test-sort.py, tests/test-groups.py,
+ * tests/test-reduce.py).
+ *
+ * Each function cites the reference file:line it restates
+ * (paths relative to /root/reference/src/core/).
+ *
+ * Plain C99, single-threaded, no dependencies.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+/* stype codes: src/datatable/include/datatable.h:32-42 */
+enum {
+  ST_BOOL = 1, ST_INT8 = 2, ST_INT16 = 3, ST_INT32 = 4, ST_INT64 = 5,
+  ST_FLOAT32 = 6, ST_FLOAT64 = 7, ST_DATE32 = 17, ST_TIME64 = 18
+};
+/* sort flags / NA position: sort.h:36-48 */
+enum { FLAG_DESCENDING = 2, FLAG_SORT_ONLY = 4 };
+enum { NA_FIRST = 1, NA_LAST = 2, NA_REMOVE = 3 };
+/* reducer codes (ours; one per reference ColumnImpl) */
+enum { OP_SUM = 1, OP_MEAN = 2, OP_MIN = 3, OP_MAX = 4, OP_COUNT = 5,
+       OP_COUNTNA = 6, OP_NROWS = 7 };
+
+static int stype_size(int st) {
+  switch (st) {
+    case ST_BOOL: case ST_INT8: return 1;
+    case ST_INT16: return 2;
+    case ST_INT32: case ST_FLOAT32: case ST_DATE32: return 4;
+    case ST_INT64: case ST_FLOAT64: case ST_TIME64: return 8;
+    default: return 0;
+  }
+}
+
+/* Read element i of an integer-like column as int64; *na set when it is the
+ * type's NA sentinel (stype.h:186-189: INT*_MIN; bool NA is int8 -128). */
+static int64_t read_int(const void* p, int st, int64_t i, int* na) {
+  switch (st) {
+    case ST_BOOL: case ST_INT8: {
+      int8_t v = ((const int8_t*)p)[i]; *na = (v == INT8_MIN); return v; }
+    case ST_INT16: {
+      int16_t v = ((const int16_t*)p)[i]; *na = (v == INT16_MIN); return v; }
+    case ST_INT32: case ST_DATE32: {
+      int32_t v = ((const int32_t*)p)[i]; *na = (v == INT32_MIN); return v; }
+    default: {
+      int64_t v = ((const int64_t*)p)[i]; *na = (v == INT64_MIN); return v; }
+  }
+}
+
+/*---------------------------------------------------------------------------
+ * Key normalisation: every key column becomes an array of uint64 radix keys
+ * whose unsigned order is the requested row order.
+ *   bool   : sort.cc:690-720  (_initB)
+ *   int*   : sort.cc:729-776  (_initI/_initI_impl): NA->0, x = t-min+1 (ASC),
+ *            max-t+1 (DESC); NA last: NA -> max-min+1 and the increment is 0.
+ *            min/max are the column's non-NA stats (stats.cc:601-634).
+ *   float* : sort.cc:809-845  (_initF): NaN -> 0 (all ones when NA last);
+ *            ASC  t ^ (SBT | -(t>>63)), DESC t ^ (~SBT & ((t>>63) - 1)).
+ * Returns the number of significant bits (sort.cc:735-736), or -1 for an
+ * unsupported stype (NotImplError at sort.cc:673).
+ *--------------------------------------------------------------------------*/
+static int normalise(const void* col, int st, int desc, int na_pos,
+                     int64_t n, uint64_t* x, int64_t* nacount)
+{
+  int64_t nna = 0;
+  if (st == ST_BOOL) {
+    const uint8_t* xi = (const uint8_t*)col;
+    uint8_t rep = (na_pos == NA_LAST) ? 3 : 0;
+    for (int64_t j = 0; j < n; j++) {
+      uint8_t t = xi[j];
+      if (t == 128) { x[j] = rep; nna++; }
+      else x[j] = desc ? (uint8_t)((uint8_t)(128 - t) >> 6) : (uint8_t)(t + 1);
+    }
+    *nacount = nna;
+    return 2;
+  }
+  if (st == ST_FLOAT32) {
+    const uint32_t* xi = (const uint32_t*)col;
+    const uint32_t EXP = 0x7F800000u, SIG = 0x007FFFFFu, SBT = 0x80000000u;
+    uint32_t rep = (na_pos == NA_LAST) ? 0xFFFFFFFFu : 0;
+    for (int64_t j = 0; j < n; j++) {
+      uint32_t t = xi[j];
+      if ((t & EXP) == EXP && (t & SIG) != 0) { x[j] = rep; nna++; }
+      else x[j] = desc ? (uint32_t)(t ^ (~SBT & ((t >> 31) - 1)))
+                       : (uint32_t)(t ^ (SBT | (0u - (t >> 31))));
+    }
+    *nacount = nna;
+    return 32;
+  }
+  if (st == ST_FLOAT64) {
+    const uint64_t* xi = (const uint64_t*)col;
+    const uint64_t EXP = 0x7FF0000000000000ull, SIG = 0x000FFFFFFFFFFFFFull,
+                   SBT = 0x8000000000000000ull;
+    uint64_t rep = (na_pos == NA_LAST) ? ~0ull : 0;
+    for (int64_t j = 0; j < n; j++) {
+      uint64_t t = xi[j];
+      if ((t & EXP) == EXP && (t & SIG) != 0) { x[j] = rep; nna++; }
+      else x[j] = desc ? (t ^ (~SBT & ((t >> 63) - 1)))
+                       : (t ^ (SBT | (0ull - (t >> 63))));
+    }
+    *nacount = nna;
+    return 64;
+  }
+  int sz = stype_size(st);
+  if (sz == 0) return -1;
+  /* integer family */
+  int64_t mn = 0, mx = 0; int have = 0;
+  for (int64_t j = 0; j < n; j++) {
+    int na; int64_t t = read_int(col, st, j, &na);
+    if (na) { nna++; continue; }
+    if (!have) { mn = mx = t; have = 1; }
+    else { if (t < mn) mn = t; if (t > mx) mx = t; }
+  }
+  uint64_t range1 = (uint64_t)mx - (uint64_t)mn + 1;   /* max - min + 1 */
+  uint64_t tmask = (sz == 8) ? ~0ull : ((1ull << (8 * sz)) - 1);
+  range1 &= tmask;
+  int nsig = 0; { uint64_t r = range1; while (r) { nsig++; r >>= 1; } }
+  uint64_t rep = (na_pos == NA_LAST) ? range1 : 0;
+  uint64_t inc = (na_pos == NA_LAST) ? 0 : 1;
+  for (int64_t j = 0; j < n; j++) {
+    int na; int64_t t = read_int(col, st, j, &na);
+    if (na) x[j] = rep;
+    else x[j] = (desc ? ((uint64_t)mx - (uint64_t)t + inc)
+                      : ((uint64_t)t - (uint64_t)mn + inc)) & tmask;
+  }
+  *nacount = nna;
+  return nsig;
+}
+
+/* Stable LSD counting sort of (key, row) pairs on `nbits` low bits of key.
+ * The reference sorts MSD-first with insertion-sort leaves
+ * (sort.cc:1129-1353, sort_insert.cc:96-144); its contract is only
+ * "stable ascending order of the normalised key" (sort.cc:27-33), which an
+ * LSD pass sequence satisfies identically. */
+static void lsd_pairs(uint64_t* k, int32_t* o, uint64_t* k2, int32_t* o2,
+                      int64_t n, int nbits)
+{
+  for (int shift = 0; shift < nbits; shift += 8) {
+    int64_t hist[256]; memset(hist, 0, sizeof hist);
+    for (int64_t i = 0; i < n; i++) hist[(k[i] >> shift) & 255]++;
+    int constant = 0;
+    for (int b = 0; b < 256; b++) if (hist[b] == n) constant = 1;
+    if (constant) continue;
+    int64_t run = 0;
+    for (int b = 0; b < 256; b++) { int64_t c = hist[b]; hist[b] = run; run += c; }
+    for (int64_t i = 0; i < n; i++) {
+      int64_t d = hist[(k[i] >> shift) & 255]++;
+      k2[d] = k[i]; o2[d] = o[i];
+    }
+    memcpy(k, k2, (size_t)n * sizeof(uint64_t));
+    memcpy(o, o2, (size_t)n * sizeof(int32_t));
+  }
+}
+
+/*---------------------------------------------------------------------------
+ * orc_group: restates group() (sort.cc:1411-1495).
+ *   cols/stypes/flags : ncols key columns (flag bits: 2 = DESCENDING,
+ *                       4 = SORT_ONLY, sort.h:36-41)
+ *   order   [n]   : the RowIndex ARR32 payload (sort.cc:598-608)
+ *   offsets [n+1] : Groupby offsets, offsets[0]=0 .. offsets[ng]=n
+ *                   (groupby.h:41-47); written only when groups are produced
+ *   *ngroups      : number of groups, or -1 when the reference returns an
+ *                   empty Groupby (first flag SORT_ONLY, sort.cc:1491)
+ *   *nskip        : rows to drop from the front of `order` when
+ *                   na_pos == REMOVE (= NA count of the LAST key column,
+ *                   sort.cc:598-605 -- quirk of the reference kept as is)
+ * Returns 0, or -1 for an unsupported stype.
+ *--------------------------------------------------------------------------*/
+int orc_group(const void** cols, const int* stypes, const int* flags,
+              int ncols, int na_pos, int64_t n,
+              int32_t* order, int32_t* offsets,
+              int64_t* ngroups, int64_t* nskip)
+{
+  *nskip = 0;
+  if (n == 0) {                         /* sort.cc:1431-1434 */
+    offsets[0] = 0; *ngroups = 0; return 0;
+  }
+  if (n == 1) {                         /* sort.cc:1435-1439 */
+    order[0] = 0; offsets[0] = 0; offsets[1] = 1; *ngroups = 1; return 0;
+  }
+  uint64_t* x  = (uint64_t*)malloc((size_t)n * 8);
+  uint64_t* k  = (uint64_t*)malloc((size_t)n * 8);
+  uint64_t* k2 = (uint64_t*)malloc((size_t)n * 8);
+  int32_t*  o2 = (int32_t*) malloc((size_t)n * 4);
+  uint8_t* head = (uint8_t*)calloc((size_t)n, 1);
+  for (int64_t i = 0; i < n; i++) order[i] = (int32_t)i;
+
+  /* number of leading "by" columns whose values define the groups
+   * (sort.cc:1471-1482: groups are frozen at the by -> sort transition) */
+  int nby = 0;
+  while (nby < ncols && !(flags[nby] & FLAG_SORT_ONLY)) nby++;
+
+  int rc = 0;
+  int64_t nacount_last = 0;
+  /* least-significant key first; each pass is stable */
+  for (int c = ncols - 1; c >= 0; c--) {
+    int64_t nna;
+    int nsig = normalise(cols[c], stypes[c], (flags[c] & FLAG_DESCENDING) != 0,
+                         na_pos, n, x, &nna);
+    if (nsig < 0) { rc = -1; break; }
+    if (c == ncols - 1) nacount_last = nna;
+    for (int64_t i = 0; i < n; i++) k[i] = x[order[i]];
+    lsd_pairs(k, order, k2, o2, n, nsig);
+  }
+  if (rc == 0) {
+    if (nby > 0) {
+      /* adjacent-compare group detection (sort_groups.cc:48-62 from_data) */
+      head[0] = 1;
+      for (int c = 0; c < nby; c++) {
+        int64_t nna;
+        normalise(cols[c], stypes[c], (flags[c] & FLAG_DESCENDING) != 0,
+                  na_pos, n, x, &nna);
+        for (int64_t i = 1; i < n; i++)
+          if (x[order[i]] != x[order[i - 1]]) head[i] = 1;
+      }
+      int64_t ng = 0;
+      for (int64_t i = 0; i < n; i++) if (head[i]) offsets[ng++] = (int32_t)i;
+      offsets[ng] = (int32_t)n;
+      *ngroups = ng;
+    } else {
+      *ngroups = -1;
+    }
+    if (na_pos == NA_REMOVE) *nskip = nacount_last;
+  }
+  free(x); free(k); free(k2); free(o2); free(head);
+  return rc;
+}
+
+/*---------------------------------------------------------------------------
+ * orc_gather: restates ArrayView_ColumnImpl<int32_t>::get_element
+ * (column/view.cc:138-155) materialised by _materialize_fw
+ * (column/column_impl.cc:78-103): out[i] = idx[i] < 0 ? NA : src[idx[i]].
+ *--------------------------------------------------------------------------*/
+int orc_gather(const void* src, int st, const int32_t* idx, int64_t n, void* out)
+{
+  int sz = stype_size(st);
+  if (!sz) return -1;
+  for (int64_t i = 0; i < n; i++) {
+    int32_t j = idx[i];
+    char* dst = (char*)out + i * sz;
+    if (j >= 0) { memcpy(dst, (const char*)src + (int64_t)j * sz, (size_t)sz); continue; }
+    switch (st) {
+      case ST_BOOL: case ST_INT8: *(int8_t*)dst = INT8_MIN; break;
+      case ST_INT16: *(int16_t*)dst = INT16_MIN; break;
+      case ST_INT32: case ST_DATE32: *(int32_t*)dst = INT32_MIN; break;
+      case ST_INT64: case ST_TIME64: *(int64_t*)dst = INT64_MIN; break;
+      case ST_FLOAT32: *(float*)dst = NAN; break;
+      case ST_FLOAT64: *(double*)dst = NAN; break;
+    }
+  }
+  return 0;
+}
+
+/*---------------------------------------------------------------------------
+ * orc_reduce: restates the per-group reducers.  `order` may be NULL
+ * (identity RowIndex).  Output stypes and NA rules:
+ *   SUM   column/sumprod.h:34-59, expr/fexpr_sumprod.cc:47-66
+ *         bool/int* -> int64 (wraps), float32 -> float32 accumulated in
+ *         float32, float64 -> float64; sequential in sorted order; NA skipped;
+ *         never NA (empty -> 0).
+ *   MEAN  column/mean.h:33-51, expr/fexpr_mean.cc:45-78
+ *         double accumulator; ints/bool/float64 -> float64, float32 ->
+ *         float32; no valid rows -> NA (NaN).
+ *   MIN/MAX column/minmax.h:33-60, expr/fexpr_minmax.cc:47-72
+ *         same stype as input (bool -> int8); first strictly-better valid
+ *         value wins; no valid rows -> NA.
+ *   COUNT/COUNTNA column/count.h:35-56; NROWS column/count.h:82-87 -> int64.
+ *--------------------------------------------------------------------------*/
+int orc_reduce(int op, const void* v, int st, const int32_t* order,
+               const int32_t* offsets, int64_t ng, void* out)
+{
+  int isf = (st == ST_FLOAT32 || st == ST_FLOAT64);
+  if (op != OP_NROWS && !stype_size(st)) return -1;
+  for (int64_t g = 0; g < ng; g++) {
+    int64_t i0 = offsets[g], i1 = offsets[g + 1];
+    if (op == OP_NROWS) { ((int64_t*)out)[g] = i1 - i0; continue; }
+    int64_t isum = 0; float fsum = 0.0f; double dsum = 0.0;
+    int64_t cnt = 0;
+    int have = 0; int64_t ibest = 0; double dbest = 0;
+    for (int64_t gi = i0; gi < i1; gi++) {
+      int64_t j = order ? order[gi] : gi;
+      if (isf) {
+        double d = (st == ST_FLOAT32) ? (double)((const float*)v)[j]
+                                      : ((const double*)v)[j];
+        if (isnan(d)) continue;
+        cnt++;
+        if (op == OP_SUM) {
+          if (st == ST_FLOAT32) fsum = fsum + ((const float*)v)[j];
+          else dsum = dsum + d;
+        } else if (op == OP_MEAN) dsum += d;
+        else if (op == OP_MIN) { if (!have || d < dbest) { dbest = d; have = 1; } }
+        else if (op == OP_MAX) { if (!have || d > dbest) { dbest = d; have = 1; } }
+      } else {
+        int na; int64_t t = read_int(v, st, j, &na);
+        if (na) continue;
+        cnt++;
+        if (op == OP_SUM) isum = (int64_t)((uint64_t)isum + (uint64_t)t);
+        else if (op == OP_MEAN) dsum += (double)t;
+        else if (op == OP_MIN) { if (!have || t < ibest) { ibest = t; have = 1; } }
+        else if (op == OP_MAX) { if (!have || t > ibest) { ibest = t; have = 1; } }
+      }
+    }
+    switch (op) {
+      case OP_SUM:
+        if (st == ST_FLOAT32) ((float*)out)[g] = fsum;
+        else if (st == ST_FLOAT64) ((double*)out)[g] = dsum;
+        else ((int64_t*)out)[g] = isum;
+        break;
+      case OP_MEAN:
+        if (st == ST_FLOAT32) ((float*)out)[g] = cnt ? (float)(dsum / (double)cnt) : NAN;
+        else ((double*)out)[g] = cnt ? dsum / (double)cnt : NAN;
+        break;
+      case OP_MIN: case OP_MAX:
+        switch (st) {
+          case ST_BOOL: case ST_INT8: ((int8_t*)out)[g] = have ? (int8_t)ibest : INT8_MIN; break;
+          case ST_INT16: ((int16_t*)out)[g] = have ? (int16_t)ibest : INT16_MIN; break;
+          case ST_INT32: case ST_DATE32: ((int32_t*)out)[g] = have ? (int32_t)ibest : INT32_MIN; break;
+          case ST_INT64: case ST_TIME64: ((int64_t*)out)[g] = have ? ibest : INT64_MIN; break;
+          case ST_FLOAT32: ((float*)out)[g] = have ? (float)dbest : NAN; break;
+          case ST_FLOAT64: ((double*)out)[g] = have ? dbest : NAN; break;
+        }
+        break;
+      case OP_COUNT:   ((int64_t*)out)[g] = cnt; break;
+      case OP_COUNTNA: ((int64_t*)out)[g] = (i1 - i0) - cnt; break;
+      default: return -1;
+    }
+  }
+  return 0;
+}

@@ -1,0 +1,131 @@
+"""
+NumPy/ctypes front-end of the CPU oracle (oracle/dt_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(datatable_b200/) never imports this module.
+
+Parity status: pinned against the reference (see dt_oracle.c header and
+tests/test_oracle_golden.py).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborc.so")
+
+# stype codes: /root/reference/src/datatable/include/datatable.h:32-42
+BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64 = 1, 2, 3, 4, 5, 6, 7
+# sort flags / NA position: /root/reference/src/core/sort.h:36-48
+DESCENDING, SORT_ONLY = 2, 4
+NA_FIRST, NA_LAST, NA_REMOVE = 1, 2, 3
+SUM, MEAN, MIN, MAX, COUNT, COUNTNA, NROWS = 1, 2, 3, 4, 5, 6, 7
+
+_NP2ST = {
+    np.dtype(np.bool_): BOOL, np.dtype(np.int8): INT8, np.dtype(np.int16): INT16,
+    np.dtype(np.int32): INT32, np.dtype(np.int64): INT64,
+    np.dtype(np.float32): FLOAT32, np.dtype(np.float64): FLOAT64,
+}
+_ST2NP = {BOOL: np.int8, INT8: np.int8, INT16: np.int16, INT32: np.int32,
+          INT64: np.int64, FLOAT32: np.float32, FLOAT64: np.float64}
+
+
+def build(force=False):
+    if force or not os.path.exists(_SO) or \
+            os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "dt_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liborc.so"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.orc_group.restype = ctypes.c_int
+        _lib.orc_reduce.restype = ctypes.c_int
+        _lib.orc_gather.restype = ctypes.c_int
+    return _lib
+
+
+def stype_of(a, stype=None):
+    """stype code of a numpy array (bool columns may be passed as int8 + stype=BOOL)."""
+    if stype is not None:
+        return stype
+    return _NP2ST[a.dtype]
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def group(cols, flags=None, na_pos=NA_FIRST, stypes=None):
+    """Returns (order int32[n'], offsets int32[ng+1] or None, ngroups or None).
+
+    `order` already has the NA rows removed when na_pos == NA_REMOVE.
+    """
+    cols = [np.ascontiguousarray(c) for c in cols]
+    n = len(cols[0])
+    nc = len(cols)
+    flags = list(flags) if flags is not None else [0] * nc
+    sts = [stype_of(c, None if stypes is None else stypes[i]) for i, c in enumerate(cols)]
+    cp = (ctypes.c_void_p * nc)(*[c.ctypes.data for c in cols])
+    st = (ctypes.c_int * nc)(*sts)
+    fl = (ctypes.c_int * nc)(*flags)
+    order = np.empty(n, dtype=np.int32)
+    offsets = np.empty(n + 1, dtype=np.int32)
+    ng = ctypes.c_int64(0)
+    nskip = ctypes.c_int64(0)
+    rc = lib().orc_group(cp, st, fl, ctypes.c_int(nc), ctypes.c_int(na_pos),
+                         ctypes.c_int64(n), _ptr(order), _ptr(offsets),
+                         ctypes.byref(ng), ctypes.byref(nskip))
+    if rc != 0:
+        raise NotImplementedError("oracle: unsupported stype")
+    if nskip.value:
+        order = order[nskip.value:].copy()
+    if ng.value < 0:
+        return order, None, None
+    return order, offsets[:ng.value + 1].copy(), ng.value
+
+
+def out_dtype(op, st):
+    """Output numpy dtype of a reducer (see orc_reduce header)."""
+    if op in (COUNT, COUNTNA, NROWS):
+        return np.int64
+    if op == SUM:
+        return {FLOAT32: np.float32, FLOAT64: np.float64}.get(st, np.int64)
+    if op == MEAN:
+        return np.float32 if st == FLOAT32 else np.float64
+    return _ST2NP[st]
+
+
+def reduce(op, v, order, offsets, stype=None):
+    v = np.ascontiguousarray(v) if v is not None else np.zeros(1, np.int8)
+    st = stype_of(v, stype)
+    ng = len(offsets) - 1
+    out = np.empty(ng, dtype=out_dtype(op, st))
+    offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+    op_ = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+    rc = lib().orc_reduce(ctypes.c_int(op), _ptr(v), ctypes.c_int(st),
+                          _ptr(op_) if op_ is not None else ctypes.c_void_p(0),
+                          _ptr(offsets), ctypes.c_int64(ng), _ptr(out))
+    if rc != 0:
+        raise NotImplementedError("oracle: unsupported reducer/stype")
+    return out
+
+
+def gather(src, idx, stype=None):
+    src = np.ascontiguousarray(src)
+    st = stype_of(src, stype)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    out = np.empty(len(idx), dtype=src.dtype)
+    rc = lib().orc_gather(_ptr(src), ctypes.c_int(st), _ptr(idx),
+                          ctypes.c_int64(len(idx)), _ptr(out))
+    if rc != 0:
+        raise NotImplementedError("oracle: unsupported stype")
+    return out
