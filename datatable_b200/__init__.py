@@ -1,0 +1,12 @@
+"""
+datatable_b200 -- B200-native groupby/sort engine behind h2oai/datatable's
+DT[i, j, by(), sort()] hot path.  See DESIGN.md / INTEGRATION.md.
+
+Importing this package loads libdtb200.so (sm_100a CUDA); it raises if the
+library has not been built.  There is no CPU fallback.
+"""
+from . import _lib
+from ._lib import (DtbError, DtbValueError, DtbNotImplError, DtbCudaError, DtbMemoryError)
+from . import engine
+
+__all__ = ["engine", "DtbError", "DtbValueError", "DtbNotImplError", "DtbCudaError", "DtbMemoryError"]

@@ -1,0 +1,563 @@
+// dtb_api.cu -- the C-ABI (include/dtb200.h): call planning, HBM scratch,
+// host<->device staging and error reporting.  No compute happens on the host:
+// without a CUDA device every entry point fails with DTB_ECUDA.
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "dtb_common.cuh"
+
+namespace dtb {
+
+// ---------------------------------------------------------------------------
+// thread-local state
+// ---------------------------------------------------------------------------
+static thread_local std::string t_error;
+static thread_local dtb_call_stats t_stats = {0, 0, 0, 0, 0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+void count_launch(int n) { t_stats.kernels_launched += n; }
+
+// ---------------------------------------------------------------------------
+// options (analogue of dt.options.sort.*, sort.cc:259-349)
+// ---------------------------------------------------------------------------
+static int64_t opt_radix_bits = 8;
+static int64_t opt_verbose = 0;
+
+// ---------------------------------------------------------------------------
+// per-device context: the stream-ordered memory pool keeps scratch resident
+// ---------------------------------------------------------------------------
+static std::mutex g_ctx_mutex;
+static bool g_ctx_ready[64] = {false};
+
+static int ensure_context() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+    return DTB_ECUDA;
+  }
+  if (dev < 0 || dev >= 64) { set_error("device ordinal out of range"); return DTB_EINVAL; }
+  if (g_ctx_ready[dev]) return DTB_OK;
+  std::lock_guard<std::mutex> lock(g_ctx_mutex);
+  if (g_ctx_ready[dev]) return DTB_OK;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error(std::string("no usable CUDA device: ") + cudaGetErrorString(e));
+    return DTB_ECUDA;
+  }
+  if (prop.major != 10) {
+    set_error("dtb200 is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
+              std::to_string(prop.minor));
+    return DTB_ECUDA;
+  }
+  cudaMemPool_t pool;
+  DTB_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thresh = UINT64_MAX;          // keep freed scratch cached in the pool
+  DTB_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  g_ctx_ready[dev] = true;
+  return DTB_OK;
+}
+
+// Stream-ordered scratch buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  int alloc(size_t nbytes, cudaStream_t stream) {
+    release();
+    s = stream; bytes = nbytes ? nbytes : 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, s);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      set_error("cudaMallocAsync(" + std::to_string(bytes) + " bytes): " + cudaGetErrorString(e));
+      cudaGetLastError();
+      return e == cudaErrorMemoryAllocation ? DTB_ENOMEM : DTB_ECUDA;
+    }
+    t_stats.scratch_bytes += (int64_t)bytes;
+    return DTB_OK;
+  }
+  void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; } }
+  void* detach() { void* q = p; p = nullptr; return q; }
+  template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Input that may live on the host: staged into HBM when needed.
+struct DevIn {
+  const void* dptr = nullptr;
+  DevBuf buf;
+  int bind(const void* p, size_t bytes, cudaStream_t s) {
+    if (!p || bytes == 0) { dptr = p; return DTB_OK; }
+    if (is_device_ptr(p)) { dptr = p; return DTB_OK; }
+    DTB_TRY(buf.alloc(bytes, s));
+    DTB_CUDA_CHECK(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, s));
+    dptr = buf.p;
+    return DTB_OK;
+  }
+};
+
+// Output that may live on the host: computed in HBM, copied back by finish().
+struct DevOut {
+  void* dptr = nullptr;
+  void* host = nullptr;
+  size_t bytes = 0;
+  DevBuf buf;
+  int bind(void* p, size_t nbytes, cudaStream_t s) {
+    bytes = nbytes;
+    if (!p) { dptr = nullptr; return DTB_OK; }
+    if (is_device_ptr(p)) { dptr = p; return DTB_OK; }
+    host = p;
+    DTB_TRY(buf.alloc(nbytes, s));
+    dptr = buf.p;
+    return DTB_OK;
+  }
+  bool staged() const { return host != nullptr; }
+  int finish(size_t nbytes, cudaStream_t s) {
+    if (host && nbytes) DTB_CUDA_CHECK(cudaMemcpyAsync(host, dptr, nbytes, cudaMemcpyDeviceToHost, s));
+    return DTB_OK;
+  }
+};
+
+static int bitlen(u64 v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
+static int ctz64(u64 v) { int c = 0; while (!(v & 1)) { v >>= 1; c++; } return c; }
+
+static bool stype_supported(int st) { return stype_bytes(st) != 0; }
+static bool stype_is_float(int st) { return st == DTB_STYPE_FLOAT32 || st == DTB_STYPE_FLOAT64; }
+
+// ---------------------------------------------------------------------------
+// group(): plan + launch
+// ---------------------------------------------------------------------------
+struct GroupResult {
+  DevBuf order;          // int32[n]
+  DevBuf offsets;        // int32[ng+1] (capacity n+1) when groups were requested
+  int64_t n = 0;
+  int64_t nskip = 0;     // leading NA rows to drop (na_position = remove)
+  int64_t ngroups = -1;
+};
+
+// Builds the per-column normalisation from device-computed stats.
+static int plan_keys(const dtb_col* keys, const void* const* dptrs, int nkeys, const int* flags,
+                     int na_pos, const ColStats* st, KeyPlan& kp, int64_t& nacount_last)
+{
+  kp.nkeys = nkeys;
+  int total = 0, sort_bits = 0;
+  // the last key is the least significant part of the composite
+  for (int c = nkeys - 1; c >= 0; c--) {
+    KeyNorm& k = kp.k[c];
+    const ColStats& cs = st[c];
+    k.data = dptrs[c];
+    k.stype = keys[c].stype;
+    k.desc = (flags[c] & DTB_FLAG_DESCENDING) ? 1 : 0;
+    k.pad = 0;
+    u64 lo = cs.lo, hi = cs.hi;
+    if (cs.nvalid == 0) { lo = hi = 0; }
+    const u64 vary = cs.nvalid ? (cs.bits_or ^ cs.bits_and) : 0;
+    k.cshift = vary ? ctz64(vary) : 0;
+    const u64 rng = (hi - lo) >> k.cshift;                 // values span 0..rng after the shift
+    k.edge = k.desc ? hi : lo;
+    if (cs.nacount == 0) {                                 // no NA slot needed
+      k.inc = 0; k.na_value = 0; k.bits = bitlen(rng);
+    } else if (na_pos == DTB_NA_LAST) {                    // sort.cc:749-751: NA -> max-min+1, increment 0
+      k.inc = 0; k.na_value = rng + 1; k.bits = bitlen(rng + 1);
+    } else {                                               // NA -> 0, values shifted up by one
+      k.inc = 1; k.na_value = 0; k.bits = bitlen(rng + 1);
+    }
+    if (cs.nvalid == 0) { k.bits = 0; k.na_value = 0; }    // all-NA column is constant
+    k.lshift = total;
+    total += k.bits;
+    if (flags[c] & DTB_FLAG_SORT_ONLY) sort_bits = total;
+    if (c == nkeys - 1) nacount_last = (int64_t)cs.nacount;
+  }
+  kp.total_bits = total;
+  // groups are defined by the leading by-columns only (sort.cc:1471-1482)
+  int gs = 0;
+  for (int c = nkeys - 1; c >= 0 && (flags[c] & DTB_FLAG_SORT_ONLY); c--) gs = kp.k[c].lshift + kp.k[c].bits;
+  kp.group_shift = gs;
+  (void)sort_bits;
+  return DTB_OK;
+}
+
+static void plan_passes(int total_bits, int width, PassPlan& pp) {
+  int np = (total_bits + width - 1) / width;
+  if (np < 1) np = 1;
+  pp.npasses = np;
+  int base = total_bits / np, extra = total_bits % np, sh = 0;
+  for (int p = 0; p < np; p++) {
+    int b = base + (p < extra ? 1 : 0);
+    if (b < 1) b = 1;
+    pp.shift[p] = sh; pp.bits[p] = b; sh += b;
+  }
+}
+
+static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t n,
+                      cudaStream_t s, int32_t* order_dev /*optional caller buffer*/,
+                      int32_t* offsets_dev /*optional caller buffer, n+1*/, GroupResult& res)
+{
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  if (nkeys < 1 || nkeys > MAX_KEYS) { set_error("number of key columns must be in 1.." + std::to_string(MAX_KEYS)); return DTB_EINVAL; }
+  if (!keys || !flags) { set_error("keys/flags must not be NULL"); return DTB_EINVAL; }
+  if (na_pos < DTB_NA_FIRST || na_pos > DTB_NA_REMOVE) { set_error("na position value is not supported"); return DTB_EINVAL; }
+  if (n < 0) { set_error("nrows must be non-negative"); return DTB_EINVAL; }
+  for (int c = 0; c < nkeys; c++) {
+    if (!stype_supported(keys[c].stype)) {
+      set_error("Unable to sort Column of stype " + std::to_string(keys[c].stype));   // sort.cc:673
+      return DTB_ENOTIMPL;
+    }
+    if (n > 0 && !keys[c].data) { set_error("key column data is NULL"); return DTB_EINVAL; }
+  }
+  if (n > (int64_t)INT32_MAX) { set_error("nrows > INT32_MAX needs an ARR64 RowIndex: not implemented"); return DTB_ENOTIMPL; }
+  DTB_TRY(ensure_context());
+
+  const bool do_groups = !(flags[0] & DTB_FLAG_SORT_ONLY);
+  res.n = n; res.nskip = 0; res.ngroups = do_groups ? 0 : -1;
+
+  int32_t* order = order_dev;
+  if (!order) { DTB_TRY(res.order.alloc(sizeof(int32_t) * (size_t)n, s)); order = res.order.as<int32_t>(); }
+  int32_t* offsets = offsets_dev;
+  if (do_groups && !offsets) {
+    DTB_TRY(res.offsets.alloc(sizeof(int32_t) * (size_t)(n + 1), s)); offsets = res.offsets.as<int32_t>();
+  }
+
+  if (n == 0) {                                           // sort.cc:1431-1434
+    if (do_groups) DTB_CUDA_CHECK(cudaMemsetAsync(offsets, 0, sizeof(int32_t), s));
+    res.ngroups = do_groups ? 0 : -1;
+    return DTB_OK;
+  }
+
+  // ---- stage host inputs, column statistics -------------------------------------
+  std::vector<DevIn> in(nkeys);
+  const void* dptrs[MAX_KEYS];
+  for (int c = 0; c < nkeys; c++) {
+    DTB_TRY(in[c].bind(keys[c].data, (size_t)n * stype_bytes(keys[c].stype), s));
+    dptrs[c] = in[c].dptr;
+  }
+  DevBuf d_stats; DTB_TRY(d_stats.alloc(sizeof(ColStats) * nkeys, s));
+  for (int c = 0; c < nkeys; c++)
+    DTB_TRY(launch_col_stats(dptrs[c], keys[c].stype, n, d_stats.as<ColStats>() + c, s));
+  ColStats h_stats[MAX_KEYS];
+  DTB_CUDA_CHECK(cudaMemcpyAsync(h_stats, d_stats.p, sizeof(ColStats) * nkeys, cudaMemcpyDeviceToHost, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+
+  KeyPlan kp; memset(&kp, 0, sizeof(kp));
+  int64_t nacount_last = 0;
+  DTB_TRY(plan_keys(keys, dptrs, nkeys, flags, na_pos, h_stats, kp, nacount_last));
+  if (na_pos == DTB_NA_REMOVE) res.nskip = nacount_last;   // sort.cc:598-605
+  t_stats.key_bits = kp.total_bits;
+  if (kp.total_bits > 64) {
+    set_error("composite key of " + std::to_string(kp.total_bits) + " bits (> 64) is not implemented");
+    return DTB_ENOTIMPL;
+  }
+
+  if (kp.total_bits == 0) {
+    // every key column is constant: identity order, one group (cf. sort.cc:1435-1439)
+    DTB_TRY(launch_iota32(order, n, s));
+    if (do_groups) {
+      int32_t h[2] = {0, (int32_t)n};
+      DTB_CUDA_CHECK(cudaMemcpyAsync(offsets, h, sizeof(h), cudaMemcpyHostToDevice, s));
+      DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+      res.ngroups = 1;
+    }
+    return DTB_OK;
+  }
+
+  const int key_bytes = kp.total_bits <= 32 ? 4 : 8;
+  const int nbins_log2 = 8;
+  int width = (int)opt_radix_bits; if (width < 1) width = 1; if (width > nbins_log2) width = nbins_log2;
+  PassPlan pp; plan_passes(kp.total_bits, width, pp);
+  t_stats.radix_passes = pp.npasses;
+  if (opt_verbose) {
+    fprintf(stderr, "[dtb200] group: n=%lld keys=%d bits=%d key_bytes=%d passes=%d group_shift=%d\n",
+            (long long)n, nkeys, kp.total_bits, key_bytes, pp.npasses, kp.group_shift);
+    for (int c = 0; c < nkeys; c++)
+      fprintf(stderr, "[dtb200]   key %d: stype=%d desc=%d bits=%d cshift=%d lshift=%d na=%llu\n", c,
+              kp.k[c].stype, kp.k[c].desc, kp.k[c].bits, kp.k[c].cshift, kp.k[c].lshift,
+              (unsigned long long)h_stats[c].nacount);
+  }
+
+  // ---- key source ----------------------------------------------------------------
+  DevBuf keyA, keyB, idxA, idxB;
+  DTB_TRY(keyA.alloc((size_t)n * key_bytes, s));
+  const bool need_b = pp.npasses > 1 || nkeys > 1;
+  if (need_b) DTB_TRY(keyB.alloc((size_t)n * key_bytes, s));
+  if (pp.npasses > 1) DTB_TRY(idxA.alloc((size_t)n * 4, s));
+  if (pp.npasses > 2) DTB_TRY(idxB.alloc((size_t)n * 4, s));
+
+  int src_kind = 1;
+  if (nkeys > 1) { DTB_TRY(launch_compose_keys(kp, n, keyA.p, key_bytes, s)); src_kind = 0; }
+
+  // ---- histograms -> global digit offsets -------------------------------------------
+  const int nbins = 1 << nbins_log2;
+  DevBuf hist; DTB_TRY(hist.alloc(sizeof(u32) * pp.npasses * nbins, s));
+  DTB_TRY(launch_histograms(src_kind, keyA.p, kp, key_bytes, n, pp, nbins_log2, hist.as<u32>(), s));
+  DTB_TRY(launch_scan_histograms(hist.as<u32>(), pp.npasses, nbins_log2, s));
+
+  // ---- look-back state for all passes, zeroed once ------------------------------------
+  const int64_t tile_rows = radix_pass_tile_rows(key_bytes, nbins_log2);
+  const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+  const size_t status_words = (size_t)ntiles * nbins;
+  DevBuf status; DTB_TRY(status.alloc(sizeof(u32) * (status_words * pp.npasses + pp.npasses), s));
+  DTB_CUDA_CHECK(cudaMemsetAsync(status.p, 0, status.bytes, s));
+  u32* counters = status.as<u32>() + status_words * pp.npasses;
+
+  // ---- passes ----------------------------------------------------------------------
+  // key buffers ping-pong; the composed keys (multi-column) start in keyA.
+  void* kin = keyA.p; void* kout = (nkeys > 1) ? keyB.p : keyA.p;
+  const int32_t* iin = nullptr;
+  void* sorted_keys = nullptr;
+  for (int p = 0; p < pp.npasses; p++) {
+    const bool last = (p == pp.npasses - 1);
+    PassIO io;
+    io.src_kind = (p == 0) ? src_kind : 0;
+    io.keys_in = kin;
+    io.idx_in = iin;
+    io.keys_out = (last && !do_groups) ? nullptr : kout;
+    int32_t* iout = last ? order : ((p & 1) ? idxB.as<int32_t>() : idxA.as<int32_t>());
+    io.idx_out = iout;
+    DTB_TRY(launch_radix_pass(io, kp, key_bytes, n, pp.shift[p], pp.bits[p], nbins_log2,
+                              hist.as<u32>() + (size_t)p * nbins,
+                              status.as<u32>() + status_words * p, counters + p, s));
+    if (last) sorted_keys = kout;
+    // next pass reads what this one wrote
+    kin = kout;
+    kout = (kout == keyA.p) ? keyB.p : keyA.p;
+    iin = iout;
+  }
+
+  // ---- group offsets -----------------------------------------------------------------
+  if (do_groups) {
+    const int64_t otiles = offsets_num_tiles(n);
+    DevBuf oscr; DTB_TRY(oscr.alloc(sizeof(u64) * (size_t)(otiles + 3), s));
+    DTB_CUDA_CHECK(cudaMemsetAsync(oscr.p, 0, oscr.bytes, s));
+    u64* d_ng = oscr.as<u64>() + otiles + 2;
+    DTB_TRY(launch_group_offsets(sorted_keys, key_bytes, kp.group_shift, n, offsets, d_ng,
+                                 oscr.as<u64>(), s));
+    u64 h_ng = 0;
+    DTB_CUDA_CHECK(cudaMemcpyAsync(&h_ng, d_ng, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+    res.ngroups = (int64_t)h_ng;
+  }
+  return DTB_OK;
+}
+
+}  // namespace dtb
+
+using namespace dtb;
+
+// ===========================================================================
+// extern "C"
+// ===========================================================================
+struct dtb_groupby {
+  void* order = nullptr;      // device int32[norder] (view into order_base)
+  void* order_base = nullptr;
+  void* offsets = nullptr;    // device int32[ngroups+1]
+  int64_t norder = 0;
+  int64_t ngroups = -1;
+};
+
+extern "C" {
+
+const char* dtb_last_error(void) { return t_error.c_str(); }
+int dtb_abi_version(void) { return DTB_ABI_VERSION; }
+int dtb_stype_size(int stype) { return stype_bytes(stype); }
+int dtb_reduce_out_stype(int op, int stype) { return reduce_out_stype_host(op, stype); }
+
+int dtb_init(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return DTB_ECUDA;
+  }
+  return ensure_context();
+}
+
+int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nbytes < 0 || (nbytes > 0 && (!dst || !src))) { set_error("bad dtb_memcpy arguments"); return DTB_EINVAL; }
+  if (nbytes == 0) return DTB_OK;
+  DTB_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDefault, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return DTB_OK;
+}
+
+int dtb_set_option(const char* name, int64_t value) {
+  if (!name) { set_error("option name is NULL"); return DTB_EINVAL; }
+  if (!strcmp(name, "radix_bits")) {
+    if (value < 1 || value > 8) { set_error("radix_bits must be in 1..8"); return DTB_EINVAL; }
+    opt_radix_bits = value; return DTB_OK;
+  }
+  if (!strcmp(name, "verbose")) { opt_verbose = value; return DTB_OK; }
+  set_error(std::string("unknown option ") + name);
+  return DTB_EINVAL;
+}
+
+int dtb_get_option(const char* name, int64_t* value) {
+  if (!name || !value) { set_error("NULL argument"); return DTB_EINVAL; }
+  if (!strcmp(name, "radix_bits")) { *value = opt_radix_bits; return DTB_OK; }
+  if (!strcmp(name, "verbose")) { *value = opt_verbose; return DTB_OK; }
+  set_error(std::string("unknown option ") + name);
+  return DTB_EINVAL;
+}
+
+int dtb_last_call_stats(dtb_call_stats* out) {
+  if (!out) { set_error("NULL argument"); return DTB_EINVAL; }
+  *out = t_stats;
+  return DTB_OK;
+}
+
+int dtb_group(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t nrows,
+              dtb_stream stream, void* order_out, void* offsets_out, int64_t offsets_cap,
+              int64_t* ngroups_out, int64_t* norder_out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!order_out && nrows > 0) { set_error("order_out is NULL"); return DTB_EINVAL; }
+  if (nkeys >= 1 && flags && !(flags[0] & DTB_FLAG_SORT_ONLY) && !offsets_out) {
+    set_error("offsets_out is NULL but groups were requested"); return DTB_EINVAL;
+  }
+  GroupResult res;
+  // compute straight into the caller's device buffers when they are large enough
+  int32_t* order_dev = (nrows > 0 && is_device_ptr(order_out) && na_pos != DTB_NA_REMOVE) ? (int32_t*)order_out : nullptr;
+  int32_t* offsets_dev = (offsets_out && is_device_ptr(offsets_out) && offsets_cap >= nrows + 1) ? (int32_t*)offsets_out : nullptr;
+  int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, order_dev, offsets_dev, res);
+  if (rc != DTB_OK) return rc;
+  const int64_t norder = res.n - res.nskip;
+  if (norder_out) *norder_out = norder;
+  if (ngroups_out) *ngroups_out = res.ngroups;
+  if (!order_dev && norder > 0) {
+    const int32_t* src = res.order.as<int32_t>() + res.nskip;
+    DTB_CUDA_CHECK(cudaMemcpyAsync(order_out, src, sizeof(int32_t) * (size_t)norder, cudaMemcpyDefault, s));
+  }
+  if (res.ngroups >= 0 && !offsets_dev) {
+    if (offsets_cap < res.ngroups + 1) {
+      cudaStreamSynchronize(s);
+      set_error("offsets_out holds " + std::to_string(offsets_cap) + " entries, need " + std::to_string(res.ngroups + 1));
+      return DTB_ENOSPACE;
+    }
+    DTB_CUDA_CHECK(cudaMemcpyAsync(offsets_out, res.offsets.p, sizeof(int32_t) * (size_t)(res.ngroups + 1), cudaMemcpyDefault, s));
+  }
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return DTB_OK;
+}
+
+int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t nrows,
+                       dtb_stream stream, dtb_groupby** out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!out) { set_error("out is NULL"); return DTB_EINVAL; }
+  *out = nullptr;
+  GroupResult res;
+  int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, nullptr, nullptr, res);
+  if (rc != DTB_OK) return rc;
+  dtb_groupby* g = new dtb_groupby();
+  g->norder = res.n - res.nskip;
+  g->ngroups = res.ngroups;
+  if (res.ngroups >= 0) {
+    // shrink the worst-case offsets buffer to ngroups+1 entries
+    DevBuf exact;
+    rc = exact.alloc(sizeof(int32_t) * (size_t)(res.ngroups + 1), s);
+    if (rc != DTB_OK) { delete g; return rc; }
+    cudaError_t e = cudaMemcpyAsync(exact.p, res.offsets.p, sizeof(int32_t) * (size_t)(res.ngroups + 1),
+                                    cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); delete g; return DTB_ECUDA; }
+    g->offsets = exact.detach();
+  }
+  g->order_base = res.order.detach();
+  g->order = (int32_t*)g->order_base + res.nskip;
+  *out = g;
+  return DTB_OK;
+}
+
+int64_t dtb_groupby_norder(const dtb_groupby* g) { return g ? g->norder : 0; }
+int64_t dtb_groupby_ngroups(const dtb_groupby* g) { return g ? g->ngroups : -1; }
+const void* dtb_groupby_order(const dtb_groupby* g) { return g ? g->order : nullptr; }
+const void* dtb_groupby_offsets(const dtb_groupby* g) { return g ? g->offsets : nullptr; }
+
+int dtb_groupby_destroy(dtb_groupby* g, dtb_stream stream) {
+  if (!g) return DTB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g->order_base) cudaFreeAsync(g->order_base, s);
+  if (g->offsets) cudaFreeAsync(g->offsets, s);
+  delete g;
+  return DTB_OK;
+}
+
+int dtb_reduce(int op, dtb_col value, int64_t nrows_value, const void* order, int order_is64,
+               const void* offsets, int64_t ngroups, dtb_stream stream, void* out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  if (ngroups < 0) { set_error("ngroups must be non-negative"); return DTB_EINVAL; }
+  if (!offsets) { set_error("offsets is NULL"); return DTB_EINVAL; }
+  if (!out && ngroups > 0) { set_error("out is NULL"); return DTB_EINVAL; }
+  const int out_st = (op == DTB_OP_NROWS) ? DTB_STYPE_INT64 : reduce_out_stype_host(op, value.stype);
+  if (!out_st) {
+    set_error("Invalid column of stype " + std::to_string(value.stype) + " in reducer " + std::to_string(op));
+    return stype_supported(value.stype) ? DTB_EINVAL : DTB_ENOTIMPL;
+  }
+  if (op != DTB_OP_NROWS && !value.data && nrows_value > 0) { set_error("value column data is NULL"); return DTB_EINVAL; }
+  DTB_TRY(ensure_context());
+  if (ngroups == 0) return DTB_OK;
+
+  DevIn d_off; DTB_TRY(d_off.bind(offsets, sizeof(int32_t) * (size_t)(ngroups + 1), s));
+  int32_t n32 = 0;
+  if (is_device_ptr(offsets)) {
+    DTB_CUDA_CHECK(cudaMemcpyAsync(&n32, (const int32_t*)offsets + ngroups, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  } else {
+    n32 = ((const int32_t*)offsets)[ngroups];
+  }
+  const int64_t n = n32;
+  DevIn d_val, d_ord;
+  if (op != DTB_OP_NROWS) {
+    DTB_TRY(d_val.bind(value.data, (size_t)nrows_value * stype_bytes(value.stype), s));
+    DTB_TRY(d_ord.bind(order, (size_t)n * (order_is64 ? 8 : 4), s));
+  }
+  DevOut d_out; DTB_TRY(d_out.bind(out, (size_t)ngroups * stype_bytes(out_st), s));
+  DevBuf acc; DTB_TRY(acc.alloc(sizeof(u64) * (size_t)ngroups * 2, s));
+  DTB_TRY(launch_reduce_impl(op, d_val.dptr, value.stype, nrows_value, d_ord.dptr, order_is64,
+                             (const int32_t*)d_off.dptr, ngroups, n, acc.as<u64>(),
+                             acc.as<u64>() + ngroups, d_out.dptr, s));
+  if (d_out.staged()) {
+    DTB_TRY(d_out.finish((size_t)ngroups * stype_bytes(out_st), s));
+    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  return DTB_OK;
+}
+
+int dtb_gather(dtb_col src, int64_t nrows_src, const void* order, int order_is64, int64_t n,
+               dtb_stream stream, void* out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  const int esz = stype_bytes(src.stype);
+  if (!esz) { set_error("Unable to gather Column of stype " + std::to_string(src.stype)); return DTB_ENOTIMPL; }
+  if (n < 0 || nrows_src < 0) { set_error("negative size"); return DTB_EINVAL; }
+  if (n > 0 && (!order || !out)) { set_error("order/out is NULL"); return DTB_EINVAL; }
+  DTB_TRY(ensure_context());
+  if (n == 0) return DTB_OK;
+  DevIn d_src, d_ord;
+  DTB_TRY(d_src.bind(src.data, (size_t)nrows_src * esz, s));
+  DTB_TRY(d_ord.bind(order, (size_t)n * (order_is64 ? 8 : 4), s));
+  DevOut d_out; DTB_TRY(d_out.bind(out, (size_t)n * esz, s));
+  DTB_TRY(launch_gather(d_src.dptr, src.stype, nrows_src, d_ord.dptr, order_is64, n, d_out.dptr, s));
+  if (d_out.staged()) {
+    DTB_TRY(d_out.finish((size_t)n * esz, s));
+    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  return DTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,150 @@
+// dtb_groups.cu -- the Groupby group-offset scan.
+//
+// Replaces GroupGatherer (sort.h:119-148, sort_groups.cc:34-117): the
+// reference collects cumulative group ends serially per radix range and
+// memmove-compacts them.  Here the sorted composite keys are read once, rows
+// whose group key (key >> group_shift) differs from their predecessor are
+// flagged as group heads, and the head positions are compacted into
+// offsets[] with a single-pass block scan + decoupled look-back over tiles.
+//
+// Output layout == Groupby::offsets_ (groupby.h:41-47): int32[ng+1],
+// offsets[0] = 0, strictly increasing, offsets[ng] = nrows.
+//
+// Bound: HBM, 1 read of the sorted keys (sizeof(KeyT) B/row) + 4 B/group.
+#include "dtb_common.cuh"
+
+namespace dtb {
+
+constexpr int OFF_THREADS = 512;
+constexpr u64 OST_AGG  = 1ull << 62;
+constexpr u64 OST_INCL = 2ull << 62;
+constexpr u64 OST_MASK = (1ull << 62) - 1;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(OFF_THREADS)
+group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
+                     int32_t* __restrict__ offsets, u64* d_ngroups, u64* scratch /*[0]=ticket, [1..]=status*/)
+{
+  constexpr int IPT = 32 / sizeof(KeyT);
+  constexpr int TILE = OFF_THREADS * IPT;
+  constexpr int WARPS = OFF_THREADS / 32;
+  __shared__ u64 s_tile;
+  __shared__ u32 s_wsum[WARPS];
+  __shared__ u64 s_prefix;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&scratch[0], 1ull);
+  __syncthreads();
+  const int64_t tile = (int64_t)s_tile;
+  const int64_t ntiles = (n + TILE - 1) / TILE;
+  u64* status = scratch + 1;
+
+  const int64_t p0 = tile * TILE + (int64_t)tid * IPT;
+  KeyT k[IPT];
+  KeyT prev = 0;
+  if (p0 + IPT <= n) {
+    const uint4* v = reinterpret_cast<const uint4*>(keys + p0);
+    uint4 q0 = __ldg(v), q1 = __ldg(v + 1);
+    *reinterpret_cast<uint4*>(&k[0]) = q0;
+    *reinterpret_cast<uint4*>(&k[IPT / 2]) = q1;
+  } else {
+#pragma unroll
+    for (int i = 0; i < IPT; i++) k[i] = (p0 + i < n) ? keys[p0 + i] : (KeyT)0;
+  }
+  if (p0 > 0 && p0 < n) prev = keys[p0 - 1];
+
+  unsigned heads = 0; int c = 0;
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    const int64_t p = p0 + i;
+    bool h = false;
+    if (p < n) {
+      const KeyT before = (i == 0) ? prev : k[i - 1];
+      h = (p == 0) || ((k[i] >> gshift) != (before >> gshift));
+    }
+    heads |= (h ? 1u : 0u) << i;
+    c += h;
+  }
+
+  // block exclusive scan of c
+  u32 incl = (u32)c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    u32 w = lane < WARPS ? s_wsum[lane] : 0;
+    u32 wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += o;
+    }
+    if (lane < WARPS) s_wsum[lane] = wi - w;
+    if (lane == WARPS - 1) {
+      // lane WARPS-1 knows the tile total: publish and look back
+      const u64 total = wi;
+      u64 excl = 0;
+      if (tile == 0) {
+        st_relaxed_u64(&status[0], OST_INCL | total);
+      } else {
+        st_relaxed_u64(&status[tile], OST_AGG | total);
+        int64_t t = tile - 1;
+        while (true) {
+          u64 sv = ld_relaxed_u64(&status[t]);
+          const u64 flag = sv & ~OST_MASK;
+          if (flag == 0) continue;
+          excl += sv & OST_MASK;
+          if (flag == OST_INCL) break;
+          --t;
+        }
+        st_relaxed_u64(&status[tile], OST_INCL | (excl + total));
+      }
+      s_prefix = excl;
+      if (tile == ntiles - 1) {
+        const u64 ng = excl + total;
+        *d_ngroups = ng;
+        offsets[ng] = (int32_t)n;
+      }
+    }
+  }
+  __syncthreads();
+  u64 out = s_prefix + s_wsum[warp] + (incl - (u32)c);
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    if (heads & (1u << i)) offsets[out++] = (int32_t)(p0 + i);
+  }
+}
+
+int64_t offsets_num_tiles(int64_t n) {
+  // the smaller tile (8-byte keys: 4 items/thread) bounds the status array
+  const int64_t tile = OFF_THREADS * 4;
+  return (n + tile - 1) / tile;
+}
+
+int launch_group_offsets(const void* sorted_keys, int key_bytes, int group_shift, int64_t n,
+                         int32_t* offsets_out, unsigned long long* d_ngroups,
+                         unsigned long long* scratch, cudaStream_t s)
+{
+  if (n == 0) return DTB_OK;
+  if (reinterpret_cast<uintptr_t>(sorted_keys) & 15) {
+    set_error("internal: sorted key buffer must be 16-byte aligned"); return DTB_EINVAL;
+  }
+  if (key_bytes == 4) {
+    const int64_t tile = OFF_THREADS * 8;
+    group_offsets_kernel<u32><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
+        (const u32*)sorted_keys, group_shift, n, offsets_out, d_ngroups, scratch);
+  } else {
+    const int64_t tile = OFF_THREADS * 4;
+    group_offsets_kernel<u64><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
+        (const u64*)sorted_keys, group_shift, n, offsets_out, d_ngroups, scratch);
+  }
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+}  // namespace dtb

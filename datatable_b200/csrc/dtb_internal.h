@@ -1,0 +1,143 @@
+// dtb_internal.h -- declarations shared by the engine's translation units.
+// Host-side launch wrappers live next to their kernels; dtb_api.cu plans a
+// call and strings them together on one stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/dtb200.h"
+
+namespace dtb {
+
+constexpr int MAX_KEYS = 8;
+constexpr int MAX_PASSES = 16;
+
+// Thread-local error slot + launch counter (dtb_api.cu)
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define DTB_CUDA_CHECK(expr)                                                     \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) {                                                     \
+      ::dtb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+      return DTB_ECUDA;                                                          \
+    }                                                                            \
+  } while (0)
+
+#define DTB_TRY(expr)                                                            \
+  do { int _rc = (expr); if (_rc != DTB_OK) return _rc; } while (0)
+
+// ---------------------------------------------------------------------------
+// Column statistics (replaces NumericStats<T>::compute_minmax, stats.cc:601-634)
+// ---------------------------------------------------------------------------
+// For integer stypes lo/hi are the signed min/max of the non-NA values; for
+// float stypes they are the min/max of the order-preserving unsigned image
+// (sort.cc:809-845 ASC transform).  bits_or / bits_and are OR / AND of that
+// same image over the non-NA rows: bits that never vary need not be sorted.
+struct ColStats {
+  unsigned long long lo;       // int: (uint64)(int64 min); float: min image
+  unsigned long long hi;
+  unsigned long long bits_or;
+  unsigned long long bits_and;
+  unsigned long long nacount;
+  unsigned long long nvalid;
+};
+
+int launch_col_stats(const void* data, int stype, int64_t n, ColStats* d_stats,
+                     cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// Key normalisation parameters for one key column (restates _initB/_initI/_initF,
+// sort.cc:690-845, as a function evaluated on the fly inside the kernels).
+//   x = NA ? na_value : (((desc ? edge - u : u - edge) >> cshift) + inc)
+// where u is the raw integer (sign-extended) or the float's ordered image.
+// ---------------------------------------------------------------------------
+struct KeyNorm {
+  const void* data;
+  int32_t  stype;
+  int32_t  desc;
+  unsigned long long edge;      // min (ASC) or max (DESC)
+  unsigned long long na_value;  // 0 (NA first) or range+1 (NA last)
+  unsigned long long inc;       // 1 (NA first) or 0 (NA last)
+  int32_t  cshift;              // constant low bits dropped
+  int32_t  bits;                // significant bits of x
+  int32_t  lshift;              // position of x inside the composite key
+  int32_t  pad;
+};
+
+struct KeyPlan {
+  int      nkeys;
+  int      total_bits;          // bits of the composite key
+  int      group_shift;         // composite >> group_shift = group key (by-columns only)
+  KeyNorm  k[MAX_KEYS];
+};
+
+// ---------------------------------------------------------------------------
+// Radix sort (replaces SortContext::radix_psort / _radix_recurse,
+// sort.cc:1129-1353, with stable LSD single-sweep passes)
+// ---------------------------------------------------------------------------
+struct PassPlan {
+  int npasses;
+  int shift[MAX_PASSES];
+  int bits[MAX_PASSES];
+};
+
+// Composite key materialisation for multi-column keys: out[i] = X(row i).
+int launch_compose_keys(const KeyPlan& kp, int64_t n, void* keys_out, int key_bytes,
+                        cudaStream_t s);
+
+// Digit histograms of every pass in one read of the key source.
+//   src_kind 0: packed composite keys (key_bytes 4 or 8) at `packed`
+//   src_kind 1: raw single column described by kp.k[0]
+// hist: uint32[npasses][nbins] (zeroed by the callee).
+int launch_histograms(int src_kind, const void* packed, const KeyPlan& kp, int key_bytes,
+                      int64_t n, const PassPlan& pp, int nbins_log2, uint32_t* hist,
+                      cudaStream_t s);
+
+// Exclusive scan of each pass' histogram in place.
+int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, cudaStream_t s);
+
+struct PassIO {
+  int         src_kind;     // 0 packed keys + idx_in (idx_in NULL = identity), 1 raw column (identity idx)
+  const void* keys_in;      // packed keys (src_kind 0)
+  const int32_t* idx_in;
+  void*       keys_out;     // may be NULL on the last pass of a sort-only call
+  int32_t*    idx_out;
+};
+
+int radix_pass_tile_rows(int key_bytes, int nbins_log2);
+
+// One stable scatter pass.  status: uint32[ntiles * nbins] zeroed by the caller;
+// tile_counter: uint32 zeroed by the caller.
+int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
+                      int shift, int bits, int nbins_log2,
+                      const uint32_t* bin_start, uint32_t* status, uint32_t* tile_counter,
+                      cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// Group offsets (replaces GroupGatherer, sort_groups.cc:34-117): heads where
+// (key >> group_shift) changes, compacted into offsets[] by a single-pass scan.
+// ---------------------------------------------------------------------------
+// scratch: uint64[ntiles + 2] zeroed by the caller.  ngroups_out: device int64.
+int64_t offsets_num_tiles(int64_t n);
+int launch_group_offsets(const void* sorted_keys, int key_bytes, int group_shift, int64_t n,
+                         int32_t* offsets_out, unsigned long long* d_ngroups,
+                         unsigned long long* scratch, cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// Reducers / gather
+// ---------------------------------------------------------------------------
+// acc0/acc1: device scratch, ngroups uint64 each.  n = offsets[ngroups] (rows under the groups).
+int launch_reduce_impl(int op, const void* value, int stype, int64_t nrows_value,
+                       const void* order, int order_is64, const int32_t* offsets, int64_t ngroups,
+                       int64_t n, unsigned long long* acc0, unsigned long long* acc1,
+                       void* out, cudaStream_t s);
+int reduce_out_stype_host(int op, int stype);
+
+int launch_gather(const void* src, int stype, int64_t nrows_src, const void* order,
+                  int order_is64, int64_t n, void* out, cudaStream_t s);
+
+int launch_iota32(int32_t* out, int64_t n, cudaStream_t s);
+
+}  // namespace dtb

@@ -1,0 +1,444 @@
+// dtb_radix.cu -- stable LSD radix sort passes over normalised composite keys.
+//
+// Replaces SortContext::build_histogram / reorder_data / radix_psort /
+// _radix_recurse (sort.cc:950-1353).  The reference is an MSD recursion over
+// a chunk x radix size_t histogram with insertion-sort leaves -- a CPU idiom.
+// Here every pass is ONE kernel that reads each (key, row) pair once and
+// writes it once ("single sweep"): tiles take ticket numbers from an atomic
+// counter, rank their rows with warp match/ballot histogramming in shared
+// memory, publish per-digit tile counts and resolve the global digit offsets
+// with a decoupled look-back over earlier tiles' status words.  Stability
+// (ties keep ascending row index, sort.cc:27-33) follows from ranking rows in
+// (item, lane) = position order inside a tile and tiles in ticket order.
+//
+// Key normalisation (sort.cc:690-845) is evaluated on the fly in the first
+// pass and in the histogram kernel: no separate `x` array is materialised for
+// single-column keys.
+//
+// Bound: HBM.  Algorithmic bytes per row per pass = read (key + idx) + write
+// (key + idx); first pass reads the raw column only, last pass of a sort-only
+// call writes idx only.
+#include "dtb_common.cuh"
+
+namespace dtb {
+
+// ===========================================================================
+// Composite key materialisation (multi-column keys)
+// ===========================================================================
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+compose_keys_kernel(KeyPlan kp, int64_t n, KeyT* __restrict__ out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u64 x = 0;
+    for (int c = 0; c < kp.nkeys; c++)
+      x |= norm_load_dynamic(kp.k[c], i) << kp.k[c].lshift;
+    out[i] = (KeyT)x;
+  }
+}
+
+int launch_compose_keys(const KeyPlan& kp, int64_t n, void* keys_out, int key_bytes, cudaStream_t s)
+{
+  if (n == 0) return DTB_OK;
+  int64_t want = (n + 255) / 256;
+  int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
+  if (key_bytes == 4) compose_keys_kernel<u32><<<grid, 256, 0, s>>>(kp, n, (u32*)keys_out);
+  else                compose_keys_kernel<u64><<<grid, 256, 0, s>>>(kp, n, (u64*)keys_out);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+// ===========================================================================
+// Digit histograms for all passes (one read of the key source)
+// ===========================================================================
+struct HistPlan {
+  int npasses;
+  int shift[MAX_PASSES];
+  u32 mask[MAX_PASSES];
+};
+
+template <typename KeyT, typename Src, int NBINS>
+__global__ void __launch_bounds__(512)
+histogram_kernel(Src src, int64_t n, HistPlan hp, u32* __restrict__ ghist)
+{
+  extern __shared__ u32 shist[];            // [npasses][NBINS]
+  const int nwords = hp.npasses * NBINS;
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) shist[i] = 0;
+  __syncthreads();
+
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    KeyT x = src.load(i);
+    for (int p = 0; p < hp.npasses; p++) {
+      u32 d = (u32)(x >> hp.shift[p]) & hp.mask[p];
+      atomicAdd(&shist[p * NBINS + d], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+    u32 c = shist[i];
+    if (c) atomicAdd(&ghist[i], c);
+  }
+}
+
+template <typename KeyT, typename Src>
+static int run_hist(Src src, int64_t n, const PassPlan& pp, int nbins_log2, u32* hist, cudaStream_t s)
+{
+  HistPlan hp; hp.npasses = pp.npasses;
+  for (int p = 0; p < pp.npasses; p++) { hp.shift[p] = pp.shift[p]; hp.mask[p] = (1u << pp.bits[p]) - 1; }
+  const int nbins = 1 << nbins_log2;
+  DTB_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(u32) * pp.npasses * nbins, s));
+  if (n == 0) return DTB_OK;
+  int64_t want = (n + 512 * 16 - 1) / (512 * 16);
+  int grid = (int)(want < 1 ? 1 : (want > NUM_SMS_B200 * 4 ? NUM_SMS_B200 * 4 : want));
+  size_t smem = sizeof(u32) * pp.npasses * nbins;
+  if (nbins_log2 != 8) { set_error("internal: only 8-bit digit kernels are built"); return DTB_EINVAL; }
+  histogram_kernel<KeyT, Src, 256><<<grid, 512, smem, s>>>(src, n, hp, hist);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+template <typename KeyT>
+static int run_hist_raw(const KeyPlan& kp, int64_t n, const PassPlan& pp, int nbins_log2, u32* hist,
+                        cudaStream_t s)
+{
+  const KeyNorm& k = kp.k[0];
+#define DTB_CASE(T)                                                                          \
+  { RawSrc<T, KeyT> src; src.p = (const typename RawKey<T>::load_t*)k.data; src.k = k;       \
+    return run_hist<KeyT>(src, n, pp, nbins_log2, hist, s); }
+  switch (k.stype) {
+    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
+    case DTB_STYPE_INT16:                        DTB_CASE(int16_t)
+    case DTB_STYPE_INT32: case DTB_STYPE_DATE32: DTB_CASE(int32_t)
+    case DTB_STYPE_INT64: case DTB_STYPE_TIME64: DTB_CASE(int64_t)
+    case DTB_STYPE_FLOAT32:                      DTB_CASE(float)
+    case DTB_STYPE_FLOAT64:                      DTB_CASE(double)
+  }
+#undef DTB_CASE
+  set_error("internal: bad stype in histogram"); return DTB_EINVAL;
+}
+
+int launch_histograms(int src_kind, const void* packed, const KeyPlan& kp, int key_bytes,
+                      int64_t n, const PassPlan& pp, int nbins_log2, uint32_t* hist, cudaStream_t s)
+{
+  if (src_kind == 0) {
+    if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)packed}; return run_hist<u32>(src, n, pp, nbins_log2, hist, s); }
+    else                { PackedSrc<u64> src{(const u64*)packed}; return run_hist<u64>(src, n, pp, nbins_log2, hist, s); }
+  }
+  return key_bytes == 4 ? run_hist_raw<u32>(kp, n, pp, nbins_log2, hist, s)
+                        : run_hist_raw<u64>(kp, n, pp, nbins_log2, hist, s);
+}
+
+// Exclusive scan of each pass' NBINS counters (one block per pass).
+__global__ void scan_hist_kernel(u32* hist, int nbins)
+{
+  __shared__ u32 wsum[32];
+  u32* h = hist + (size_t)blockIdx.x * nbins;
+  // nbins <= 1024 = blockDim.x
+  const int t = threadIdx.x;
+  u32 v = t < nbins ? h[t] : 0;
+  u32 incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((t & 31) >= d) incl += o;
+  }
+  if ((t & 31) == 31) wsum[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    u32 w = t < (blockDim.x >> 5) ? wsum[t] : 0;
+    u32 wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (t >= d) wi += o;
+    }
+    wsum[t] = wi - w;
+  }
+  __syncthreads();
+  if (t < nbins) h[t] = incl - v + wsum[t >> 5];
+}
+
+int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, cudaStream_t s)
+{
+  const int nbins = 1 << nbins_log2;
+  int threads = nbins < 32 ? 32 : nbins;
+  scan_hist_kernel<<<npasses, threads, 0, s>>>(hist, nbins);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+// ===========================================================================
+// The single-sweep scatter pass
+// ===========================================================================
+constexpr u32 ST_FLAG_AGG  = 1u << 30;     // tile count published
+constexpr u32 ST_FLAG_INCL = 2u << 30;     // inclusive prefix published
+constexpr u32 ST_MASK      = (1u << 30) - 1;
+
+template <typename KeyT, typename Src>
+struct PassArgs {
+  Src            src;
+  const int32_t* idx_in;        // NULL = identity
+  KeyT*          keys_out;      // NULL = do not write keys
+  int32_t*       idx_out;
+  int64_t        n;
+  int            shift;
+  u32            mask;
+  const u32*     bin_start;     // [NBINS] global exclusive digit offsets
+  u32*           status;        // [ntiles][NBINS]
+  u32*           tile_counter;
+};
+
+template <typename KeyT, typename Src, int NBINS, int THREADS, int IPT>
+__global__ void __launch_bounds__(THREADS)
+radix_pass_kernel(PassArgs<KeyT, Src> a)
+{
+  constexpr int WARPS = THREADS / 32;
+  constexpr int TILE = THREADS * IPT;
+  constexpr int BPT = (NBINS + THREADS - 1) / THREADS;       // bins per thread in the scan phase
+  static_assert(NBINS % 32 == 0, "NBINS must be a multiple of the warp size");
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: whist[WARPS][NBINS] u16 | tile_start[NBINS] u32 | bin_dst[NBINS] u32 | skey[TILE] | sidx[TILE]
+  unsigned short* whist = reinterpret_cast<unsigned short*>(smem_raw);
+  u32* tile_start = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
+  u32* bin_dst    = tile_start + NBINS;
+  KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);   // +4 words: scan scratch below
+  int32_t* sidx   = reinterpret_cast<int32_t*>(skey + TILE);
+  u32* s_misc     = bin_dst + NBINS;                                 // [0] = ticket
+  __shared__ u32 s_wsum[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) s_misc[0] = atomicAdd(a.tile_counter, 1u);
+  {
+    u32* z = reinterpret_cast<u32*>(whist);
+    for (int i = tid; i < WARPS * NBINS / 2; i += THREADS) z[i] = 0;
+  }
+  __syncthreads();
+  const u32 tile = s_misc[0];
+  const int64_t base = (int64_t)tile * TILE;
+  const int tile_n = (int)((a.n - base) < (int64_t)TILE ? (a.n - base) : (int64_t)TILE);
+
+  // ---- load (warp-striped: item i of lane l sits at warp_base + i*32 + l) ----
+  KeyT key[IPT];
+  int32_t idx[IPT];
+  const int wbase = warp * 32 * IPT;
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    const int lp = wbase + i * 32 + lane;
+    if (lp < tile_n) {
+      key[i] = a.src.load(base + lp);
+      idx[i] = a.idx_in ? a.idx_in[base + lp] : (int32_t)(base + lp);
+    } else { key[i] = 0; idx[i] = 0; }
+  }
+
+  // ---- rank inside the warp: rows with equal digits keep (item, lane) order ----
+  unsigned short rank[IPT];
+  unsigned short* myhist = whist + warp * NBINS;
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    const bool valid = (wbase + i * 32 + lane) < tile_n;
+    const u32 d = valid ? ((u32)(key[i] >> a.shift) & a.mask) : (u32)NBINS;
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const int leader = __ffs(peers) - 1;
+    unsigned short old = 0;
+    if (lane == leader && valid) { old = myhist[d]; myhist[d] = old + (unsigned short)__popc(peers); }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[i] = old + (unsigned short)__popc(peers & lt);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per-digit: prefix over warps, publish tile count, scan over digits, look back ----
+  u32 cnt[BPT];
+#pragma unroll
+  for (int j = 0; j < BPT; j++) {
+    const int b = tid * BPT + j;
+    u32 run = 0;
+    if (b < NBINS) {
+#pragma unroll
+      for (int w = 0; w < WARPS; w++) {
+        unsigned short c = whist[w * NBINS + b];
+        whist[w * NBINS + b] = (unsigned short)run;
+        run += c;
+      }
+      st_relaxed_u32(&a.status[(size_t)tile * NBINS + b],
+                     (tile == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | run);
+    }
+    cnt[j] = run;
+  }
+  {
+    // block-wide exclusive scan of the tile's digit counts (thread t owns bins t*BPT..)
+    u32 tsum = 0;
+#pragma unroll
+    for (int j = 0; j < BPT; j++) tsum += cnt[j];
+    u32 incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      u32 w = lane < WARPS ? s_wsum[lane] : 0;
+      u32 wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        u32 o = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += o;
+      }
+      s_wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    u32 excl = incl - tsum + s_wsum[warp];
+#pragma unroll
+    for (int j = 0; j < BPT; j++) {
+      const int b = tid * BPT + j;
+      if (b < NBINS) tile_start[b] = excl;
+      excl += cnt[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < BPT; j++) {
+    const int b = tid * BPT + j;
+    if (b < NBINS) {
+      u32 prev = 0;
+      if (tile > 0) {
+        int64_t t = (int64_t)tile - 1;
+        while (true) {
+          u32 sv = ld_relaxed_u32(&a.status[(size_t)t * NBINS + b]);
+          const u32 flag = sv & ~ST_MASK;
+          if (flag == 0) continue;                  // predecessor has a ticket, hence is running
+          prev += sv & ST_MASK;
+          if (flag == ST_FLAG_INCL) break;
+          --t;
+        }
+        st_relaxed_u32(&a.status[(size_t)tile * NBINS + b], ST_FLAG_INCL | ((prev + cnt[j]) & ST_MASK));
+      }
+      bin_dst[b] = a.bin_start[b] + prev - tile_start[b];
+    }
+  }
+  __syncthreads();
+
+  // ---- reorder the tile in shared memory ----
+#pragma unroll
+  for (int i = 0; i < IPT; i++) {
+    if ((wbase + i * 32 + lane) < tile_n) {
+      const u32 d = (u32)(key[i] >> a.shift) & a.mask;
+      const u32 lp = tile_start[d] + myhist[d] + rank[i];
+      skey[lp] = key[i];
+      sidx[lp] = idx[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
+  for (int p = tid; p < tile_n; p += THREADS) {
+    const KeyT k = skey[p];
+    const u32 d = (u32)(k >> a.shift) & a.mask;
+    const u32 dst = bin_dst[d] + (u32)p;
+    if (a.keys_out) a.keys_out[dst] = k;
+    a.idx_out[dst] = sidx[p];
+  }
+}
+
+template <typename KeyT> struct PassCfg;
+template <> struct PassCfg<u32> { static constexpr int THREADS = 256, IPT = 16; };
+template <> struct PassCfg<u64> { static constexpr int THREADS = 256, IPT = 16; };
+
+template <typename KeyT, int NBINS>
+static constexpr size_t pass_smem_bytes() {
+  return sizeof(unsigned short) * (PassCfg<KeyT>::THREADS / 32) * NBINS + sizeof(u32) * (2 * NBINS + 4)
+       + (sizeof(KeyT) + sizeof(int32_t)) * PassCfg<KeyT>::THREADS * PassCfg<KeyT>::IPT;
+}
+
+int radix_pass_tile_rows(int key_bytes, int /*nbins_log2*/) {
+  return key_bytes == 4 ? PassCfg<u32>::THREADS * PassCfg<u32>::IPT
+                        : PassCfg<u64>::THREADS * PassCfg<u64>::IPT;
+}
+
+template <typename KeyT, typename Src>
+static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits,
+                    const u32* bin_start, u32* status, u32* tile_counter, cudaStream_t s)
+{
+  constexpr int NBINS = 256;
+  constexpr int THREADS = PassCfg<KeyT>::THREADS, IPT = PassCfg<KeyT>::IPT;
+  if (n == 0) return DTB_OK;
+  PassArgs<KeyT, Src> a;
+  a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
+  a.n = n; a.shift = shift; a.mask = (1u << bits) - 1;
+  a.bin_start = bin_start; a.status = status; a.tile_counter = tile_counter;
+  const int64_t ntiles = (n + THREADS * IPT - 1) / (THREADS * IPT);
+  constexpr size_t smem = pass_smem_bytes<KeyT, NBINS>();
+  auto kern = radix_pass_kernel<KeyT, Src, NBINS, THREADS, IPT>;
+  static bool configured = false;   // per instantiation
+  if (!configured) {
+    DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  kern<<<(unsigned)ntiles, THREADS, smem, s>>>(a);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+template <typename KeyT>
+static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shift, int bits,
+                        const u32* bin_start, u32* status, u32* tile_counter, cudaStream_t s)
+{
+  const KeyNorm& k = kp.k[0];
+#define DTB_CASE(T)                                                                          \
+  { RawSrc<T, KeyT> src; src.p = (const typename RawKey<T>::load_t*)k.data; src.k = k;       \
+    return run_pass<KeyT>(src, io, n, shift, bits, bin_start, status, tile_counter, s); }
+  switch (k.stype) {
+    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
+    case DTB_STYPE_INT16:                        DTB_CASE(int16_t)
+    case DTB_STYPE_INT32: case DTB_STYPE_DATE32: DTB_CASE(int32_t)
+    case DTB_STYPE_INT64: case DTB_STYPE_TIME64: DTB_CASE(int64_t)
+    case DTB_STYPE_FLOAT32:                      DTB_CASE(float)
+    case DTB_STYPE_FLOAT64:                      DTB_CASE(double)
+  }
+#undef DTB_CASE
+  set_error("internal: bad stype in radix pass"); return DTB_EINVAL;
+}
+
+int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
+                      int shift, int bits, int nbins_log2,
+                      const uint32_t* bin_start, uint32_t* status, uint32_t* tile_counter,
+                      cudaStream_t s)
+{
+  if (nbins_log2 != 8) { set_error("internal: only 8-bit digit kernels are built"); return DTB_EINVAL; }
+  if (n >= (int64_t)ST_MASK) { set_error("nrows too large for 30-bit look-back words"); return DTB_ENOTIMPL; }
+  if (io.src_kind == 0) {
+    if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)io.keys_in};
+      return run_pass<u32>(src, io, n, shift, bits, bin_start, status, tile_counter, s); }
+    else { PackedSrc<u64> src{(const u64*)io.keys_in};
+      return run_pass<u64>(src, io, n, shift, bits, bin_start, status, tile_counter, s); }
+  }
+  return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, bin_start, status, tile_counter, s)
+                        : run_pass_raw<u64>(io, kp, n, shift, bits, bin_start, status, tile_counter, s);
+}
+
+__global__ void iota32_kernel(int32_t* out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int32_t)i;
+}
+
+int launch_iota32(int32_t* out, int64_t n, cudaStream_t s) {
+  if (n == 0) return DTB_OK;
+  int64_t want = (n + 255) / 256;
+  int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
+  iota32_kernel<<<grid, 256, 0, s>>>(out, n);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+}  // namespace dtb

@@ -1,0 +1,409 @@
+// dtb_reduce.cu -- per-group reducers and the RowIndex gather.
+//
+// Replaces the reference's reducer columns, which are evaluated one group per
+// virtual get_element() call with two more virtual calls per row
+// (column/sumprod.h:34-59, mean.h:33-51, minmax.h:33-60, count.h:35-89, driven
+// by column/column_impl.cc:78-103), and ArrayView_ColumnImpl's gather
+// (column/view.cc:138-155).
+//
+// Design: rows, not groups, are the unit of parallelism, so skewed group
+// sizes cannot unbalance the grid (the reference partitions groups statically,
+// column_impl.h:106).  A tile of consecutive sorted positions finds the groups
+// it intersects from `offsets`, every thread folds its 8 consecutive rows
+// (gathered through the RowIndex), partials of the same group are combined
+// across the warp with a segmented shuffle scan, and one atomic per
+// (warp, group) lands in an L2-resident accumulator table.  A finalize kernel
+// turns accumulators into the reference's output stype and NA sentinels.
+//
+// Bound: HBM (random 8-byte gathers: one 32-byte sector per row).
+// Algorithmic bytes per row: sizeof(order elem) + sizeof(value elem).
+#include <type_traits>
+#include "dtb_common.cuh"
+
+namespace dtb {
+
+enum { CAT_SUMI = 0, CAT_SUMF = 1, CAT_MEAN = 2, CAT_MINMAX = 3, CAT_COUNT = 4 };
+
+constexpr int RT = 256;          // threads per tile
+constexpr int RIPT = 8;          // consecutive rows per thread
+constexpr int RTILE = RT * RIPT;
+
+template <int CAT> struct Partial;
+template <> struct Partial<CAT_SUMI> { u64 s; };
+template <> struct Partial<CAT_SUMF> { double s; };
+template <> struct Partial<CAT_MEAN> { double s; u32 c; };
+template <> struct Partial<CAT_MINMAX> { u64 key; };
+template <> struct Partial<CAT_COUNT> { u32 c; };
+
+template <int CAT>
+__device__ __forceinline__ void p_init(Partial<CAT>& p, int flag) {
+  if constexpr (CAT == CAT_SUMI) p.s = 0;
+  else if constexpr (CAT == CAT_SUMF) p.s = 0.0;
+  else if constexpr (CAT == CAT_MEAN) { p.s = 0.0; p.c = 0; }
+  else if constexpr (CAT == CAT_MINMAX) p.key = flag ? ~0ull : 0ull;   // flag: 1 = MIN
+  else p.c = 0;
+}
+
+template <int CAT>
+__device__ __forceinline__ void p_merge(Partial<CAT>& a, const Partial<CAT>& b, int flag) {
+  if constexpr (CAT == CAT_SUMI) a.s += b.s;
+  else if constexpr (CAT == CAT_SUMF) a.s += b.s;
+  else if constexpr (CAT == CAT_MEAN) { a.s += b.s; a.c += b.c; }
+  else if constexpr (CAT == CAT_MINMAX) a.key = flag ? (b.key < a.key ? b.key : a.key) : (b.key > a.key ? b.key : a.key);
+  else a.c += b.c;
+}
+
+template <int CAT>
+__device__ __forceinline__ Partial<CAT> p_shfl_up(const Partial<CAT>& a, int d) {
+  Partial<CAT> r;
+  if constexpr (CAT == CAT_SUMI) r.s = __shfl_up_sync(0xffffffffu, a.s, d);
+  else if constexpr (CAT == CAT_SUMF) r.s = __shfl_up_sync(0xffffffffu, a.s, d);
+  else if constexpr (CAT == CAT_MEAN) { r.s = __shfl_up_sync(0xffffffffu, a.s, d); r.c = __shfl_up_sync(0xffffffffu, a.c, d); }
+  else if constexpr (CAT == CAT_MINMAX) r.key = __shfl_up_sync(0xffffffffu, a.key, d);
+  else r.c = __shfl_up_sync(0xffffffffu, a.c, d);
+  return r;
+}
+
+template <int CAT>
+__device__ __forceinline__ void p_flush(const Partial<CAT>& p, int64_t g, u64* acc0, u64* acc1, int flag) {
+  if constexpr (CAT == CAT_SUMI) { if (p.s) atomicAdd(&acc0[g], p.s); }
+  else if constexpr (CAT == CAT_SUMF) { if (p.s != 0.0) atomicAdd(reinterpret_cast<double*>(acc0) + g, p.s); }
+  else if constexpr (CAT == CAT_MEAN) {
+    if (p.c) { atomicAdd(reinterpret_cast<double*>(acc0) + g, p.s); atomicAdd(&acc1[g], (u64)p.c); }
+  }
+  else if constexpr (CAT == CAT_MINMAX) {
+    if (flag) { if (p.key != ~0ull) atomicMin(&acc0[g], p.key); }
+    else      { if (p.key != 0ull)  atomicMax(&acc0[g], p.key); }
+  }
+  else { if (p.c) atomicAdd(&acc0[g], (u64)p.c); }
+}
+
+// fold one (possibly NA) raw element into a partial
+template <typename T, int CAT>
+__device__ __forceinline__ void p_add(Partial<CAT>& p, typename RawKey<T>::load_t raw, bool row_valid, int flag) {
+  constexpr bool ISF = std::is_floating_point<T>::value;
+  u64 u; bool valid = RawKey<T>::get(raw, u) && row_valid;   // u: sign-extended int or float image
+  if constexpr (CAT == CAT_COUNT) { p.c += (flag ? !valid : valid); return; }
+  if (!valid) return;
+  if constexpr (CAT == CAT_SUMI) p.s += u;
+  else if constexpr (CAT == CAT_SUMF || CAT == CAT_MEAN) {
+    double x;
+    if constexpr (std::is_same<T, float>::value) x = (double)__uint_as_float((u32)raw);
+    else if constexpr (std::is_same<T, double>::value) x = __longlong_as_double((long long)raw);
+    else x = (double)(int64_t)u;
+    p.s += x;
+    if constexpr (CAT == CAT_MEAN) p.c += 1;
+  }
+  else if constexpr (CAT == CAT_MINMAX) {
+    u64 key = ISF ? u : (u ^ 0x8000000000000000ull);      // order-preserving unsigned key, never 0 for ints
+    if (flag) { if (!ISF) key -= 1; p.key = key < p.key ? key : p.key; }
+    else p.key = key > p.key ? key : p.key;
+  }
+}
+
+template <typename T, int CAT, typename OrdT>
+__global__ void __launch_bounds__(RT)
+reduce_kernel(const typename RawKey<T>::load_t* __restrict__ v, int64_t nv,
+              const OrdT* __restrict__ order, const int32_t* __restrict__ offsets,
+              int64_t ng, int64_t n, u64* acc0, u64* acc1, int flag)
+{
+  typedef typename RawKey<T>::load_t L;
+  __shared__ int64_t s_g[2];
+  __shared__ u32 s_bits[RTILE / 32];
+  __shared__ u32 s_wpre[RTILE / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t t0 = (int64_t)blockIdx.x * RTILE;
+  const int64_t t1 = (t0 + RTILE < n) ? t0 + RTILE : n;
+
+  if (tid < RTILE / 32) s_bits[tid] = 0;
+  if (tid == 0 || tid == 32) {
+    // largest g with offsets[g] <= pos
+    const int64_t pos = (tid == 0) ? t0 : (t1 - 1);
+    int64_t lo = 0, hi = ng;             // offsets[0] = 0 <= pos < offsets[ng] = n
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)offsets[mid] <= pos) lo = mid; else hi = mid;
+    }
+    s_g[tid ? 1 : 0] = lo;
+  }
+  __syncthreads();
+  const int64_t g_lo = s_g[0], g_hi = s_g[1];
+  for (int64_t g = g_lo + 1 + tid; g <= g_hi; g += RT) {
+    const int p = (int)((int64_t)offsets[g] - t0);          // 1 .. RTILE-1
+    atomicOr(&s_bits[p >> 5], 1u << (p & 31));
+  }
+  __syncthreads();
+  if (tid < 32) {
+    // exclusive prefix of popcounts over the RTILE/32 = 64 bitmap words (2 per lane)
+    u32 a = __popc(s_bits[2 * lane]), b = __popc(s_bits[2 * lane + 1]);
+    u32 incl = a + b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    s_wpre[2 * lane] = incl - a - b;
+    s_wpre[2 * lane + 1] = incl - b;
+  }
+  __syncthreads();
+
+  const int c0 = tid * RIPT;                                   // RIPT = 8 rows: one byte of the bitmap
+  const u32 word = s_bits[c0 >> 5];
+  const u32 mybits = (word >> (c0 & 31)) & 0xffu;
+  int64_t g_cur = g_lo + s_wpre[c0 >> 5] + __popc(word & ((1u << (c0 & 31)) - 1u));
+
+  // gather: all index loads first, then all value loads
+  const int64_t p0 = t0 + c0;
+  int64_t row[RIPT];
+#pragma unroll
+  for (int i = 0; i < RIPT; i++) {
+    const int64_t p = p0 + i;
+    row[i] = (p < n) ? (order ? (int64_t)order[p] : p) : -2;
+  }
+  L val[RIPT];
+#pragma unroll
+  for (int i = 0; i < RIPT; i++) val[i] = (row[i] >= 0 && row[i] < nv) ? v[row[i]] : (L)0;
+
+  Partial<CAT> part; p_init(part, flag);
+#pragma unroll
+  for (int i = 0; i < RIPT; i++) {
+    if (mybits & (1u << i)) {                 // a new group starts at this row: close the previous run
+      p_flush(part, g_cur, acc0, acc1, flag);
+      p_init(part, flag);
+      g_cur++;
+    }
+    if (p0 + i < n) p_add<T, CAT>(part, val[i], row[i] >= 0 && row[i] < nv, flag);
+  }
+
+  // segmented combine of the open partials across the warp (keys ascend with the lane)
+  const int64_t key = (p0 < n) ? g_cur : (int64_t)-1 - lane;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Partial<CAT> o = p_shfl_up(part, d);
+    int64_t ok = __shfl_up_sync(0xffffffffu, key, d);
+    if (lane >= d && ok == key) p_merge(part, o, flag);
+  }
+  const int64_t nkey = __shfl_down_sync(0xffffffffu, key, 1);
+  if (key >= 0 && (lane == 31 || nkey != key)) p_flush(part, key, acc0, acc1, flag);
+}
+
+// ---- accumulator init / finalize ------------------------------------------------
+__global__ void fill_u64_kernel(u64* p, int64_t n, u64 v) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+
+__global__ void nrows_kernel(const int32_t* __restrict__ offsets, int64_t ng, int64_t* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride)
+    out[g] = (int64_t)offsets[g + 1] - (int64_t)offsets[g];
+}
+
+// NA bit patterns (stype.h:186-197)
+__device__ __forceinline__ void store_result(void* out, int out_stype, int64_t g, bool valid, u64 bits) {
+  switch (out_stype) {
+    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:
+      ((int8_t*)out)[g] = valid ? (int8_t)bits : INT8_MIN; break;
+    case DTB_STYPE_INT16: ((int16_t*)out)[g] = valid ? (int16_t)bits : INT16_MIN; break;
+    case DTB_STYPE_INT32: case DTB_STYPE_DATE32:
+      ((int32_t*)out)[g] = valid ? (int32_t)bits : INT32_MIN; break;
+    case DTB_STYPE_INT64: case DTB_STYPE_TIME64:
+      ((int64_t*)out)[g] = valid ? (int64_t)bits : INT64_MIN; break;
+    case DTB_STYPE_FLOAT32: ((u32*)out)[g] = valid ? (u32)bits : 0x7FC00000u; break;
+    case DTB_STYPE_FLOAT64: ((u64*)out)[g] = valid ? bits : 0x7FF8000000000000ull; break;
+  }
+}
+
+__global__ void finalize_kernel(int op, int in_stype, int out_stype, const u64* __restrict__ acc0,
+                                const u64* __restrict__ acc1, int64_t ng, void* out)
+{
+  const bool in_float = (in_stype == DTB_STYPE_FLOAT32 || in_stype == DTB_STYPE_FLOAT64);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride) {
+    const u64 a = acc0[g];
+    bool valid = true; u64 bits = a;
+    switch (op) {
+      case DTB_OP_SUM:
+        if (out_stype == DTB_STYPE_FLOAT32) bits = __float_as_uint((float)__longlong_as_double((long long)a));
+        break;                                            // int64 / float64: accumulator bits are the result
+      case DTB_OP_MEAN: {
+        const u64 c = acc1[g];
+        valid = c != 0;
+        const double m = __longlong_as_double((long long)a) / (double)c;
+        bits = (out_stype == DTB_STYPE_FLOAT32) ? (u64)__float_as_uint((float)m)
+                                                : (u64)__double_as_longlong(m);
+        break; }
+      case DTB_OP_MIN: case DTB_OP_MAX: {
+        const bool is_min = (op == DTB_OP_MIN);
+        valid = is_min ? (a != ~0ull) : (a != 0ull);
+        if (in_float) bits = (in_stype == DTB_STYPE_FLOAT32) ? (u64)f32_unimage((u32)a) : f64_unimage(a);
+        else bits = (is_min ? a + 1 : a) ^ 0x8000000000000000ull;
+        break; }
+      default: break;                                     // COUNT / COUNTNA: as is
+    }
+    store_result(out, out_stype, g, valid, bits);
+  }
+}
+
+static int reduce_out_stype(int op, int st) {
+  const bool isint = (st == DTB_STYPE_BOOL || st == DTB_STYPE_INT8 || st == DTB_STYPE_INT16 ||
+                      st == DTB_STYPE_INT32 || st == DTB_STYPE_INT64);
+  const bool isflt = (st == DTB_STYPE_FLOAT32 || st == DTB_STYPE_FLOAT64);
+  switch (op) {
+    case DTB_OP_NROWS: return DTB_STYPE_INT64;
+    case DTB_OP_COUNT: case DTB_OP_COUNTNA: return (isint || isflt) ? DTB_STYPE_INT64 : 0;
+    case DTB_OP_SUM:  return isint ? DTB_STYPE_INT64 : (isflt ? st : 0);           // fexpr_sumprod.cc:50-66
+    case DTB_OP_MEAN: return isint ? DTB_STYPE_FLOAT64 : (isflt ? st : 0);         // fexpr_mean.cc:49-78
+    case DTB_OP_MIN: case DTB_OP_MAX:
+      return st == DTB_STYPE_BOOL ? DTB_STYPE_INT8 : ((isint || isflt) ? st : 0);  // fexpr_minmax.cc:50-72
+  }
+  return 0;
+}
+
+template <typename T, int CAT>
+static int run_reduce(const void* v, int64_t nv, const void* order, int order_is64,
+                      const int32_t* offsets, int64_t ng, int64_t n, u64* acc0, u64* acc1,
+                      int flag, cudaStream_t s)
+{
+  typedef typename RawKey<T>::load_t L;
+  const unsigned grid = (unsigned)((n + RTILE - 1) / RTILE);
+  if (order_is64)
+    reduce_kernel<T, CAT, int64_t><<<grid, RT, 0, s>>>((const L*)v, nv, (const int64_t*)order, offsets, ng, n, acc0, acc1, flag);
+  else
+    reduce_kernel<T, CAT, int32_t><<<grid, RT, 0, s>>>((const L*)v, nv, (const int32_t*)order, offsets, ng, n, acc0, acc1, flag);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+template <int CAT>
+static int dispatch_T(int st, const void* v, int64_t nv, const void* order, int order_is64,
+                      const int32_t* offsets, int64_t ng, int64_t n, u64* acc0, u64* acc1,
+                      int flag, cudaStream_t s)
+{
+  switch (st) {
+    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:
+      if constexpr (CAT != CAT_SUMF) return run_reduce<int8_t, CAT>(v, nv, order, order_is64, offsets, ng, n, acc0, acc1, flag, s);
+      break;
+    case DTB_STYPE_INT16:
+      if constexpr (CAT != CAT_SUMF) return run_reduce<int16_t, CAT>(v, nv, order, order_is64, offsets, ng, n, acc0, acc1, flag, s);
+      break;
+    case DTB_STYPE_INT32:
+      if constexpr (CAT != CAT_SUMF) return run_reduce<int32_t, CAT>(v, nv, order, order_is64, offsets, ng, n, acc0, acc1, flag, s);
+      break;
+    case DTB_STYPE_INT64:
+      if constexpr (CAT != CAT_SUMF) return run_reduce<int64_t, CAT>(v, nv, order, order_is64, offsets, ng, n, acc0, acc1, flag, s);
+      break;
+    case DTB_STYPE_FLOAT32:
+      if constexpr (CAT != CAT_SUMI) return run_reduce<float, CAT>(v, nv, order, order_is64, offsets, ng, n, acc0, acc1, flag, s);
+      break;
+    case DTB_STYPE_FLOAT64:
+      if constexpr (CAT != CAT_SUMI) return run_reduce<double, CAT>(v, nv, order, order_is64, offsets, ng, n, acc0, acc1, flag, s);
+      break;
+  }
+  set_error("internal: reducer/stype combination"); return DTB_EINVAL;
+}
+
+// acc0/acc1: device scratch of ng u64 each (allocated by the caller in dtb_api.cu)
+int launch_reduce_impl(int op, const void* value, int stype, int64_t nv, const void* order, int order_is64,
+                       const int32_t* offsets, int64_t ng, int64_t n, u64* acc0, u64* acc1,
+                       void* out, cudaStream_t s)
+{
+  const int out_st = reduce_out_stype(op, stype);
+  if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
+  if (ng == 0) return DTB_OK;
+  const int fgrid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+  if (op == DTB_OP_NROWS) {
+    nrows_kernel<<<fgrid, 256, 0, s>>>(offsets, ng, (int64_t*)out);
+    count_launch();
+    DTB_CUDA_CHECK(cudaGetLastError());
+    return DTB_OK;
+  }
+  const bool isflt = (stype == DTB_STYPE_FLOAT32 || stype == DTB_STYPE_FLOAT64);
+  u64 init0 = (op == DTB_OP_MIN) ? ~0ull : 0ull;          // 0.0 == 0 bits for float sums
+  fill_u64_kernel<<<fgrid, 256, 0, s>>>(acc0, ng, init0);
+  count_launch();
+  if (op == DTB_OP_MEAN) { fill_u64_kernel<<<fgrid, 256, 0, s>>>(acc1, ng, 0ull); count_launch(); }
+  DTB_CUDA_CHECK(cudaGetLastError());
+  if (n > 0) {
+    int rc = DTB_OK;
+    switch (op) {
+      case DTB_OP_SUM:
+        rc = isflt ? dispatch_T<CAT_SUMF>(stype, value, nv, order, order_is64, offsets, ng, n, acc0, acc1, 0, s)
+                   : dispatch_T<CAT_SUMI>(stype, value, nv, order, order_is64, offsets, ng, n, acc0, acc1, 0, s);
+        break;
+      case DTB_OP_MEAN: rc = dispatch_T<CAT_MEAN>(stype, value, nv, order, order_is64, offsets, ng, n, acc0, acc1, 0, s); break;
+      case DTB_OP_MIN:  rc = dispatch_T<CAT_MINMAX>(stype, value, nv, order, order_is64, offsets, ng, n, acc0, acc1, 1, s); break;
+      case DTB_OP_MAX:  rc = dispatch_T<CAT_MINMAX>(stype, value, nv, order, order_is64, offsets, ng, n, acc0, acc1, 0, s); break;
+      case DTB_OP_COUNT:   rc = dispatch_T<CAT_COUNT>(stype, value, nv, order, order_is64, offsets, ng, n, acc0, acc1, 0, s); break;
+      case DTB_OP_COUNTNA: rc = dispatch_T<CAT_COUNT>(stype, value, nv, order, order_is64, offsets, ng, n, acc0, acc1, 1, s); break;
+      default: set_error("unknown reducer"); return DTB_EINVAL;
+    }
+    if (rc != DTB_OK) return rc;
+  }
+  finalize_kernel<<<fgrid, 256, 0, s>>>(op, stype, out_st, acc0, acc1, ng, out);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+int reduce_out_stype_host(int op, int st) { return reduce_out_stype(op, st); }
+
+// ===========================================================================
+// RowIndex gather (ArrayView materialisation)
+// ===========================================================================
+template <typename E, typename OrdT>
+__global__ void __launch_bounds__(256)
+gather_kernel(const E* __restrict__ src, int64_t nsrc, const OrdT* __restrict__ order, int64_t n,
+              E* __restrict__ out, E na)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
+    int64_t j[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) j[k] = (i0 + k < n) ? (int64_t)order[i0 + k] : -1;
+    E e[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) e[k] = (j[k] >= 0 && j[k] < nsrc) ? src[j[k]] : na;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (i0 + k < n) out[i0 + k] = e[k];
+  }
+}
+
+template <typename E>
+static int run_gather(const void* src, int64_t nsrc, const void* order, int order_is64, int64_t n,
+                      void* out, E na, cudaStream_t s)
+{
+  if (n == 0) return DTB_OK;
+  int64_t want = (n + 1023) / 1024;
+  int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
+  if (order_is64) gather_kernel<E, int64_t><<<grid, 256, 0, s>>>((const E*)src, nsrc, (const int64_t*)order, n, (E*)out, na);
+  else            gather_kernel<E, int32_t><<<grid, 256, 0, s>>>((const E*)src, nsrc, (const int32_t*)order, n, (E*)out, na);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+int launch_gather(const void* src, int stype, int64_t nrows_src, const void* order,
+                  int order_is64, int64_t n, void* out, cudaStream_t s)
+{
+  switch (stype) {
+    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:
+      return run_gather<uint8_t>(src, nrows_src, order, order_is64, n, out, (uint8_t)0x80, s);
+    case DTB_STYPE_INT16:
+      return run_gather<uint16_t>(src, nrows_src, order, order_is64, n, out, (uint16_t)0x8000, s);
+    case DTB_STYPE_INT32: case DTB_STYPE_DATE32:
+      return run_gather<u32>(src, nrows_src, order, order_is64, n, out, 0x80000000u, s);
+    case DTB_STYPE_FLOAT32:
+      return run_gather<u32>(src, nrows_src, order, order_is64, n, out, 0x7FC00000u, s);
+    case DTB_STYPE_INT64: case DTB_STYPE_TIME64:
+      return run_gather<u64>(src, nrows_src, order, order_is64, n, out, 0x8000000000000000ull, s);
+    case DTB_STYPE_FLOAT64:
+      return run_gather<u64>(src, nrows_src, order, order_is64, n, out, 0x7FF8000000000000ull, s);
+  }
+  set_error("Unable to gather Column of stype " + std::to_string(stype));
+  return DTB_ENOTIMPL;
+}
+
+}  // namespace dtb

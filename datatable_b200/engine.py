@@ -1,0 +1,239 @@
+"""
+Functional host layer over the C-ABI: group() / reduce() / gather() on raw
+columns.  Mirrors the reference's internal seam:
+
+    RiGb group(columns, flags, na_pos)              src/core/sort.h:56-58
+    reducer columns materialised over a Groupby     src/core/column/reduce_unary.h:30-68
+    ArrayView gather                                src/core/column/view.cc:88-155
+
+Columns are numpy arrays (host; staged by the engine) or torch CUDA tensors
+(device-resident; zero-copy).  Results come back in the same kind of memory.
+Everything is computed by libdtb200.so on the GPU; there is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import (BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, FLAG_DESCENDING,
+                   FLAG_SORT_ONLY, NA_FIRST, NA_LAST, NA_REMOVE, check, dtb_col, lib)
+
+try:  # torch is plumbing only: device memory + streams
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_NP2ST = {np.dtype(np.bool_): BOOL, np.dtype(np.int8): INT8, np.dtype(np.int16): INT16,
+          np.dtype(np.int32): INT32, np.dtype(np.int64): INT64,
+          np.dtype(np.float32): FLOAT32, np.dtype(np.float64): FLOAT64}
+_ST2NP = {BOOL: np.int8, INT8: np.int8, INT16: np.int16, INT32: np.int32, INT64: np.int64,
+          FLOAT32: np.float32, FLOAT64: np.float64}
+
+
+def _torch_dtype(st):
+    return {BOOL: torch.int8, INT8: torch.int8, INT16: torch.int16, INT32: torch.int32,
+            INT64: torch.int64, FLOAT32: torch.float32, FLOAT64: torch.float64}[st]
+
+
+def is_tensor(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+class Col:
+    """A material fixed-width column handed to the engine: pointer + stype + nrows."""
+
+    def __init__(self, data, stype=None):
+        if isinstance(data, Col):
+            self.__dict__.update(data.__dict__)
+            return
+        if is_tensor(data):
+            if not data.is_contiguous():
+                data = data.contiguous()
+            self.data = data
+            self.on_device = data.is_cuda
+            self.ptr = data.data_ptr()
+            self.nrows = data.numel()
+            npdt = np.dtype(str(data.dtype).replace("torch.", "")) if data.dtype != torch.bool else np.dtype(np.bool_)
+        else:
+            data = np.ascontiguousarray(data)
+            self.data = data
+            self.on_device = False
+            self.ptr = data.ctypes.data
+            self.nrows = data.shape[0]
+            npdt = data.dtype
+        if stype is None:
+            if npdt not in _NP2ST:
+                raise _lib.DtbNotImplError(f"Unable to sort Column of dtype {npdt}")
+            stype = _NP2ST[npdt]
+        self.stype = stype
+
+    def c(self):
+        return dtb_col(ctypes.c_void_p(self.ptr), self.stype, 0)
+
+
+def _stream():
+    if torch is not None and torch.cuda.is_available():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(0)
+
+
+def _alloc(n, st, device):
+    """Output buffer: torch CUDA tensor for device results, numpy otherwise."""
+    if device:
+        t = torch.empty(max(n, 0), dtype=_torch_dtype(st), device="cuda")
+        return t, t.data_ptr()
+    a = np.empty(max(n, 0), dtype=_ST2NP[st])
+    return a, a.ctypes.data
+
+
+def group(cols, flags=None, na_pos=NA_FIRST):
+    """group() of the reference: returns (order, offsets, ngroups).
+
+    order   : int32 RowIndex (ARR32) -- stable order of the rows
+    offsets : int32[ngroups+1] Groupby offsets, or None when flags[0] has SORT_ONLY
+    """
+    cols = [Col(c) for c in cols]
+    nk = len(cols)
+    if nk == 0:
+        raise _lib.DtbValueError("group() needs at least one key column")
+    n = cols[0].nrows
+    for c in cols:
+        if c.nrows != n:
+            raise _lib.DtbValueError("key columns have different numbers of rows")
+    flags = list(flags) if flags is not None else [0] * nk
+    device = all(c.on_device for c in cols)
+    do_groups = not (flags[0] & FLAG_SORT_ONLY)
+    ckeys = (dtb_col * nk)(*[c.c() for c in cols])
+    cflags = (ctypes.c_int * nk)(*flags)
+    order, optr = _alloc(n, INT32, device)
+    offs, fptr = (_alloc(n + 1, INT32, device) if do_groups else (None, 0))
+    ng = ctypes.c_int64(-1)
+    no = ctypes.c_int64(0)
+    check(lib.dtb_group(ckeys, nk, cflags, na_pos, n, _stream(), ctypes.c_void_p(optr),
+                        ctypes.c_void_p(fptr), n + 1 if do_groups else 0,
+                        ctypes.byref(ng), ctypes.byref(no)))
+    order = order[:no.value]
+    if ng.value < 0:
+        return order, None, None
+    return order, offs[:ng.value + 1], ng.value
+
+
+class Groupby:
+    """Device-resident result of group(): owns the RowIndex and the Groupby offsets in HBM
+    (dtb_groupby handle).  Mirrors the pair the reference keeps in EvalContext
+    (src/core/expr/eval_context.cc:278-280)."""
+
+    def __init__(self, cols, flags=None, na_pos=NA_FIRST):
+        cols = [Col(c) for c in cols]
+        nk = len(cols)
+        n = cols[0].nrows
+        flags = list(flags) if flags is not None else [0] * nk
+        ckeys = (dtb_col * nk)(*[c.c() for c in cols])
+        cflags = (ctypes.c_int * nk)(*flags)
+        h = ctypes.c_void_p(0)
+        check(lib.dtb_groupby_create(ckeys, nk, cflags, na_pos, n, _stream(), ctypes.byref(h)))
+        self._h = h
+        self.norder = lib.dtb_groupby_norder(h)
+        self.ngroups = lib.dtb_groupby_ngroups(h)
+        self.order_ptr = lib.dtb_groupby_order(h)
+        self.offsets_ptr = lib.dtb_groupby_offsets(h)
+
+    def reduce(self, op, value, out=None):
+        v = Col(value)
+        out_st = lib.dtb_reduce_out_stype(op, v.stype)
+        if out is None:
+            out, optr = _alloc(self.ngroups, out_st, v.on_device)
+        else:
+            optr = out.data_ptr() if is_tensor(out) else out.ctypes.data
+        check(lib.dtb_reduce(op, v.c(), v.nrows, ctypes.c_void_p(self.order_ptr), 0,
+                             ctypes.c_void_p(self.offsets_ptr), self.ngroups, _stream(),
+                             ctypes.c_void_p(optr)))
+        return out
+
+    def order(self):
+        t = torch.empty(self.norder, dtype=torch.int32, device="cuda")
+        if self.norder:
+            _memcpy_d2d(t.data_ptr(), self.order_ptr, 4 * self.norder)
+        return t
+
+    def offsets(self):
+        if self.ngroups < 0:
+            return None
+        t = torch.empty(self.ngroups + 1, dtype=torch.int32, device="cuda")
+        _memcpy_d2d(t.data_ptr(), self.offsets_ptr, 4 * (self.ngroups + 1))
+        return t
+
+    def close(self):
+        if self._h:
+            lib.dtb_groupby_destroy(self._h, _stream())
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _memcpy_d2d(dst, src, nbytes):
+    check(lib.dtb_memcpy(ctypes.c_void_p(dst), ctypes.c_void_p(src), nbytes, _stream()))
+
+
+def reduce_out_stype(op, stype):
+    return lib.dtb_reduce_out_stype(op, stype)
+
+
+def reduce(op, value, order, offsets, stype=None):
+    """Per-group reducer over `value` viewed through RowIndex `order` (None = identity)."""
+    ngroups = int(offsets.shape[0]) - 1
+    if op == _lib.OP_NROWS:
+        v = None
+        vst, vptr, vn, vdev = INT8, 0, 0, is_tensor(offsets) and offsets.is_cuda
+    else:
+        v = Col(value, stype)
+        vst, vptr, vn, vdev = v.stype, v.ptr, v.nrows, v.on_device
+    out_st = lib.dtb_reduce_out_stype(op, vst)
+    if not out_st:
+        raise _lib.DtbValueError(f"Invalid column of stype {vst} in reducer {op}")
+    out, optr = _alloc(ngroups, out_st, vdev)
+    o = None if order is None else Col(order)
+    f = Col(offsets)
+    is64 = 0
+    if o is not None:
+        if o.stype == INT64:
+            is64 = 1
+        elif o.stype != INT32:
+            raise _lib.DtbValueError("order must be int32 or int64")
+    check(lib.dtb_reduce(op, dtb_col(ctypes.c_void_p(vptr), vst, 0), vn,
+                         ctypes.c_void_p(o.ptr) if o is not None else None, is64,
+                         ctypes.c_void_p(f.ptr), ngroups, _stream(), ctypes.c_void_p(optr)))
+    return out
+
+
+def gather(src, order, stype=None):
+    """Materialise `src` through RowIndex `order` (negative index -> NA)."""
+    s = Col(src, stype)
+    o = Col(order)
+    if o.stype not in (INT32, INT64):
+        raise _lib.DtbValueError("order must be int32 or int64")
+    n = o.nrows
+    device = s.on_device and o.on_device
+    if device:
+        out = torch.empty(n, dtype=s.data.dtype, device="cuda")
+        optr = out.data_ptr()
+    else:
+        out = np.empty(n, dtype=s.data.dtype if not is_tensor(s.data) else _ST2NP[s.stype])
+        optr = out.ctypes.data
+    check(lib.dtb_gather(s.c(), s.nrows, ctypes.c_void_p(o.ptr), 1 if o.stype == INT64 else 0, n,
+                         _stream(), ctypes.c_void_p(optr)))
+    return out
+
+
+def set_option(name, value):
+    check(lib.dtb_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    v = ctypes.c_int64(0)
+    check(lib.dtb_get_option(name.encode(), ctypes.byref(v)))
+    return v.value

@@ -1,0 +1,206 @@
+/*
+ * dtb200.h -- C-ABI of the B200-native groupby/sort engine that sits behind
+ * h2oai/datatable's DT[i, j, by(), sort()] hot path.
+ *
+ * The reference has no FFI seam on this path: the boundary is
+ * its internal C++ function group() and the materialize() of its reducer /
+ * view columns.  Every entry point below names the reference interface it
+ * replaces (paths relative to /root/reference/src/core/).  INTEGRATION.md
+ * shows the reference-side binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary.
+ *   - every data pointer may be DEVICE memory or HOST memory (pinned or
+ *     pageable); the engine detects which (cudaPointerGetAttributes).  Host
+ *     inputs are staged to HBM, host outputs are copied back, inside the call.
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  Calls that
+ *     return scalars (dtb_group*) block until their results are final; calls
+ *     whose outputs are all in device memory (dtb_reduce, dtb_gather) only
+ *     enqueue work on `stream`.  Host outputs are always complete on return.
+ *   - return value 0 = success, negative = DTB_E*; dtb_last_error() gives the
+ *     thread-local message (the reference throws dt::Error subclasses,
+ *     utils/exceptions.h:43; a C ABI must not throw).
+ *   - there is NO CPU fallback: without a usable CUDA device every compute
+ *     call fails with DTB_ECUDA.
+ */
+#ifndef DTB200_H
+#define DTB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#  define DTB_API __attribute__((visibility("default")))
+#else
+#  define DTB_API
+#endif
+
+/* stype codes == DtStype_* of src/datatable/include/datatable.h:32-42 */
+#define DTB_STYPE_BOOL     1
+#define DTB_STYPE_INT8     2
+#define DTB_STYPE_INT16    3
+#define DTB_STYPE_INT32    4
+#define DTB_STYPE_INT64    5
+#define DTB_STYPE_FLOAT32  6
+#define DTB_STYPE_FLOAT64  7
+#define DTB_STYPE_DATE32   17   /* sorted as int32, sort.cc:666 */
+#define DTB_STYPE_TIME64   18   /* sorted as int64, sort.cc:668 */
+
+/* SortFlag bits, sort.h:36-41 */
+#define DTB_FLAG_NONE        0
+#define DTB_FLAG_DESCENDING  2
+#define DTB_FLAG_SORT_ONLY   4
+
+/* NaPosition, sort.h:43-48 */
+#define DTB_NA_FIRST   1
+#define DTB_NA_LAST    2
+#define DTB_NA_REMOVE  3
+
+/* reducers: one per reference ColumnImpl */
+#define DTB_OP_SUM      1   /* SumProd_ColumnImpl<T,true,..>  column/sumprod.h:30-62 */
+#define DTB_OP_MEAN     2   /* Mean_ColumnImpl                column/mean.h:29-52    */
+#define DTB_OP_MIN      3   /* MinMax_ColumnImpl<T,true>      column/minmax.h:29-62  */
+#define DTB_OP_MAX      4   /* MinMax_ColumnImpl<T,false>                            */
+#define DTB_OP_COUNT    5   /* CountUnary_ColumnImpl<T,false> column/count.h:31-56   */
+#define DTB_OP_COUNTNA  6   /* CountUnary_ColumnImpl<T,true>                         */
+#define DTB_OP_NROWS    7   /* CountNullary_ColumnImpl        column/count.h:60-89   */
+
+/* error codes */
+#define DTB_OK         0
+#define DTB_EINVAL    -1   /* bad argument (ValueError / TypeError in the reference) */
+#define DTB_ENOTIMPL  -2   /* unsupported stype (NotImplError, sort.cc:673): caller falls back outside the path */
+#define DTB_ECUDA     -3   /* CUDA runtime failure or no device */
+#define DTB_ENOMEM    -4
+#define DTB_ENOSPACE  -5   /* caller-provided output too small; *ngroups_out still set */
+
+typedef void* dtb_stream;           /* cudaStream_t */
+
+/* A material fixed-width column: raw typed buffer with NA sentinels
+ * (SentinelFw_ColumnImpl, column/sentinel_fw.h:34-78; NA constants stype.h:186-197). */
+typedef struct dtb_col {
+  const void* data;
+  int32_t     stype;
+  int32_t     reserved;
+} dtb_col;
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+DTB_API const char* dtb_last_error(void);
+
+/* DTB_ABI_VERSION of the loaded library (cf. DtABIVersion(), datatable.h:49). */
+DTB_API int dtb_abi_version(void);
+
+/* Bytes per element of an stype (0 = unsupported on this path). */
+DTB_API int dtb_stype_size(int stype);
+
+/* Output stype of reducer `op` applied to a column of `stype`
+ * (expr/fexpr_sumprod.cc:50-66, fexpr_mean.cc:49-78, fexpr_minmax.cc:50-72,
+ *  fexpr_count.cc:47-128); 0 if the combination is invalid. */
+DTB_API int dtb_reduce_out_stype(int op, int stype);
+
+/* Selects the CUDA device used by this thread's subsequent calls and creates
+ * the engine context on it.  Optional: the first compute call does it for the
+ * current device. */
+DTB_API int dtb_init(int device);
+
+/*
+ * dtb_group -- replaces RiGb group(columns, flags, na_pos)  (sort.h:56-58,
+ * sort.cc:1411-1495) for material bool/int/float key columns.
+ *
+ *   keys[nkeys], flags[nkeys] : key columns (by-columns first) and their
+ *                               SortFlag bits
+ *   na_pos                    : DTB_NA_*
+ *   nrows                     : rows per column (<= INT32_MAX)
+ *   order_out                 : int32[nrows]  -- the ARR32 RowIndex payload
+ *                               (sort.cc:598-608); with DTB_NA_REMOVE only the
+ *                               first *norder_out entries are written
+ *   offsets_out               : int32[offsets_cap] -- Groupby offsets,
+ *                               offsets[0]=0 .. offsets[ng]=nrows
+ *                               (groupby.h:41-47); may be NULL when flags[0]
+ *                               has SORT_ONLY
+ *   *ngroups_out              : number of groups; -1 when the reference
+ *                               returns an empty Groupby (sort.cc:1491-1493)
+ *   *norder_out               : valid entries in order_out
+ *
+ * Bit-exact with the reference for order and offsets.
+ */
+DTB_API int dtb_group(const dtb_col* keys, int nkeys, const int* flags, int na_pos,
+              int64_t nrows, dtb_stream stream,
+              void* order_out, void* offsets_out, int64_t offsets_cap,
+              int64_t* ngroups_out, int64_t* norder_out);
+
+/*
+ * Handle variant: results stay resident in HBM (no worst-case caller buffers,
+ * no host round trip before the reducers).  The handle owns order/offsets.
+ */
+typedef struct dtb_groupby dtb_groupby;
+
+DTB_API int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags,
+                       int na_pos, int64_t nrows, dtb_stream stream,
+                       dtb_groupby** out);
+DTB_API int64_t     dtb_groupby_norder(const dtb_groupby* g);    /* RowIndex length               */
+DTB_API int64_t     dtb_groupby_ngroups(const dtb_groupby* g);   /* -1 = no Groupby (sort only)   */
+DTB_API const void* dtb_groupby_order(const dtb_groupby* g);     /* device int32[norder]          */
+DTB_API const void* dtb_groupby_offsets(const dtb_groupby* g);   /* device int32[ngroups+1]/NULL  */
+DTB_API int         dtb_groupby_destroy(dtb_groupby* g, dtb_stream stream);
+
+/*
+ * dtb_reduce -- replaces ColumnImpl::materialize() of the per-group reducer
+ * columns (column/reduce_unary.h:30-68 driven by column/latent.cc:103-135 and
+ * column/column_impl.cc:78-103): value column viewed through the RowIndex
+ * `order` (NULL = identity), segmented by `offsets`.
+ *
+ *   out : ngroups elements of stype dtb_reduce_out_stype(op, value.stype);
+ *         NA results are written as the stype's NA sentinel.
+ *   nrows_value : rows in the value column (bounds the gather).
+ *
+ * SUM over integers/bool, MIN, MAX, COUNT*, NROWS are bit-exact.  Floating
+ * SUM/MEAN are accumulated in float64 with an unspecified association order:
+ * within 1e-6 relative of the reference's sequential sum (float32 SUM: the
+ * reference accumulates sequentially in float32, so agreement is O(n*2^-24)).
+ */
+DTB_API int dtb_reduce(int op, dtb_col value, int64_t nrows_value,
+               const void* order, int order_is64,
+               const void* offsets, int64_t ngroups,
+               dtb_stream stream, void* out);
+
+/*
+ * dtb_gather -- replaces materialisation of ArrayView_ColumnImpl<int32/int64>
+ * (column/view.cc:88-155): out[i] = order[i] < 0 ? NA : src[order[i]].
+ */
+DTB_API int dtb_gather(dtb_col src, int64_t nrows_src,
+               const void* order, int order_is64, int64_t n,
+               dtb_stream stream, void* out);
+
+/* Copies nbytes between any two host/device buffers on `stream`
+ * (cudaMemcpyDefault) and waits for completion.  Lets a binding read the
+ * HBM-resident results of a dtb_groupby without linking the CUDA runtime. */
+DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream stream);
+
+/*
+ * Engine options, the analogue of dt.options.sort.* (sort.cc:259-349).
+ *   "radix_bits"   digit width of the LSD passes (default 8)
+ *   "verbose"      1 = print the pass plan to stderr
+ */
+DTB_API int dtb_set_option(const char* name, int64_t value);
+DTB_API int dtb_get_option(const char* name, int64_t* value);
+
+/* Per-call statistics of the last dtb_group / dtb_groupby_create on this thread:
+ * number of kernels launched, radix passes, significant key bits. */
+typedef struct dtb_call_stats {
+  int32_t kernels_launched;
+  int32_t radix_passes;
+  int32_t key_bits;
+  int32_t reserved;
+  int64_t scratch_bytes;
+} dtb_call_stats;
+DTB_API int dtb_last_call_stats(dtb_call_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTB200_H */

@@ -1,0 +1,167 @@
+"""GPU: seeded random parity against the oracle at growing sizes, plus size-independent
+properties at sizes the oracle cannot reach in seconds."""
+import numpy as np
+import pytest
+
+from helpers import (BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, DESCENDING, SORT_ONLY,
+                     OPS, assert_reducer_equal)
+
+pytestmark = pytest.mark.gpu
+
+NA = {INT8: -2**7, INT16: -2**15, INT32: -2**31, INT64: -2**63}
+NPT = {BOOL: np.int8, INT8: np.int8, INT16: np.int16, INT32: np.int32, INT64: np.int64,
+       FLOAT32: np.float32, FLOAT64: np.float64}
+
+
+def make_col(rng, st, n, spread, na_frac):
+    if st == BOOL:
+        a = rng.integers(0, 2, n).astype(np.int8)
+    elif st in (FLOAT32, FLOAT64):
+        if spread == "few":
+            a = (rng.integers(-50, 50, n) / 4).astype(NPT[st])
+        elif spread == "unit":
+            a = rng.random(n).astype(NPT[st])
+        else:
+            a = (rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)).astype(NPT[st])
+    else:
+        info = np.iinfo(NPT[st])
+        if spread == "few":
+            lo, hi = -20, 20
+        elif spread == "unit":
+            lo, hi = max(info.min + 1, -30000), min(info.max, 1000000)
+        else:
+            lo, hi = info.min + 1, info.max
+        a = rng.integers(lo, hi, n, dtype=np.int64, endpoint=True).astype(NPT[st])
+    if na_frac:
+        m = rng.random(n) < na_frac
+        if st in NA:
+            a[m] = NA[st]
+        elif st == BOOL:
+            a[m] = -128
+        else:
+            a[m] = np.nan
+    return a
+
+
+@pytest.mark.parametrize("st", [BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64])
+@pytest.mark.parametrize("n", [1000, 4097, 100_000, 1_000_003])
+def test_single_key_sort_vs_oracle(st, n):
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    rng = np.random.default_rng(n * 31 + st)
+    for spread, na_frac, desc, na_pos in (("few", 0.1, False, 1), ("unit", 0.0, True, 2), ("wide", 0.05, False, 3),
+                                          ("wide", 0.02, True, 1)):
+        k = make_col(rng, st, n, spread, na_frac)
+        fl = [SORT_ONLY | (DESCENDING if desc else 0)]
+        want, _, _ = orc.group([k], fl, na_pos, stypes=[st])
+        got, offs, ng = engine.group([engine.Col(k, st)], fl, na_pos)
+        assert offs is None
+        assert np.array_equal(got, want), f"st={st} n={n} {spread} desc={desc} na_pos={na_pos}"
+
+
+@pytest.mark.parametrize("st", [INT8, INT32, INT64, FLOAT64])
+@pytest.mark.parametrize("n", [5000, 300_000])
+def test_groupby_reducers_vs_oracle(st, n):
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    rng = np.random.default_rng(n + st)
+    for spread in ("few", "unit"):
+        k = make_col(rng, st, n, spread, 0.03)
+        want_o, want_f, want_ng = orc.group([k], [0], 1, stypes=[st])
+        got_o, got_f, got_ng = engine.group([engine.Col(k, st)], [0], 1)
+        assert np.array_equal(got_o, want_o)
+        assert np.array_equal(got_f, want_f) and got_ng == want_ng
+        for vst in (BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64):
+            v = make_col(rng, vst, n, "few" if vst == BOOL else "unit", 0.1)
+            for op in ("sum", "mean", "min", "max", "count", "countna"):
+                want = orc.reduce(OPS[op], v, want_o, want_f, stype=vst)
+                got = engine.reduce(OPS[op], engine.Col(v, vst), got_o, got_f)
+                assert_reducer_equal(got, want, op, vst, ctx=f"key st={st} {spread} {op} vst={vst}")
+        got = engine.reduce(OPS["nrows"], None, got_o, got_f)
+        assert np.array_equal(got, np.diff(want_f).astype(np.int64))
+
+
+@pytest.mark.parametrize("sts", [(INT64, INT32), (INT8, FLOAT64, INT16), (FLOAT32, BOOL), (INT32, INT32, INT32, INT8)])
+def test_multikey_vs_oracle(sts):
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    n = 200_000
+    rng = np.random.default_rng(len(sts) * 7 + sts[0])
+    for trial in range(3):
+        keys = [make_col(rng, st, n, "few", 0.05) for st in sts]
+        flags = [DESCENDING if rng.integers(0, 2) else 0 for _ in sts]
+        nby = len(sts) if trial == 0 else (len(sts) - 1 if trial == 1 else 0)
+        for i in range(nby, len(sts)):
+            flags[i] |= SORT_ONLY
+        na_pos = 1 if trial < 2 else 2
+        want_o, want_f, want_ng = orc.group(keys, flags, na_pos, stypes=list(sts))
+        got_o, got_f, got_ng = engine.group([engine.Col(k, st) for k, st in zip(keys, sts)], flags, na_pos)
+        assert np.array_equal(got_o, want_o), f"{sts} trial {trial}"
+        if nby:
+            assert np.array_equal(got_f, want_f) and got_ng == want_ng
+        else:
+            assert got_f is None
+
+
+def test_c4_shape_keys_vs_oracle():
+    """(int64 with 33 constant low bits, int32) keys: the composite key must shrink to ~20 bits."""
+    from datatable_b200 import engine, _lib
+    from oracle import oracle as orc
+    n = 500_000
+    rng = np.random.default_rng(44)
+    k1 = rng.integers(0, 1000, n).astype(np.int64) << 33
+    k2 = rng.integers(0, 1000, n).astype(np.int32)
+    want_o, want_f, _ = orc.group([k1, k2], [0, 0], 1)
+    got_o, got_f, _ = engine.group([k1, k2], [0, 0], 1)
+    assert _lib.last_call_stats()["key_bits"] == 20
+    assert np.array_equal(got_o, want_o) and np.array_equal(got_f, want_f)
+
+
+@pytest.mark.parametrize("n", [20_000_000])
+def test_large_device_properties(n):
+    """Size-independent properties on device-resident data: the RowIndex is a permutation, the
+    gathered keys are sorted, ties keep ascending row index, offsets match the key run lengths,
+    and group sums add up to the column total."""
+    import torch
+    from datatable_b200 import engine
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    k = torch.randint(0, 100_000, (n,), generator=g, device="cuda", dtype=torch.int32)
+    v = torch.rand(n, generator=g, device="cuda", dtype=torch.float64)
+    order, offsets, ng = engine.group([k], [0], 1)
+    o64 = order.long()
+    assert torch.equal(torch.sort(o64).values, torch.arange(n, device="cuda"))
+    ks = k[o64]
+    assert bool((ks[1:] >= ks[:-1]).all())
+    same = ks[1:] == ks[:-1]
+    assert bool((o64[1:][same] > o64[:-1][same]).all()), "ties must keep ascending row index"
+    uniq, counts = torch.unique_consecutive(ks, return_counts=True)
+    assert ng == uniq.numel()
+    assert torch.equal(offsets.long(), torch.cat([torch.zeros(1, dtype=torch.long, device="cuda"), counts.cumsum(0)]))
+    sums = engine.reduce(OPS["sum"], v, order, offsets)
+    ref = torch.zeros(100_000, dtype=torch.float64, device="cuda").index_add_(0, k.long(), v)
+    assert torch.allclose(sums, ref[uniq.long()], rtol=1e-9, atol=0)
+    cnt = engine.reduce(OPS["count"], v, order, offsets)
+    assert torch.equal(cnt, counts)
+
+
+def test_large_float64_sort_properties():
+    import torch
+    from datatable_b200 import engine
+    n = 10_000_000
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    x = torch.randn(n, generator=g, device="cuda", dtype=torch.float64)
+    x[::1000] = float("nan")
+    x[1::1000] = 0.0
+    x[2::1000] = -0.0
+    order, offsets, ng = engine.group([x], [SORT_ONLY], 1)
+    assert offsets is None
+    xs = x[order.long()]
+    nn = int(torch.isnan(x).sum())
+    assert bool(torch.isnan(xs[:nn]).all()) and not bool(torch.isnan(xs[nn:]).any())   # NaN first
+    body = xs[nn:]
+    assert bool((body[1:] >= body[:-1]).all())
+    bits = body.view(torch.int64)
+    zero = body == 0
+    zb = bits[zero]
+    assert bool((zb[1:] >= zb[:-1]).all()), "-0.0 sorts before +0.0 (bit-pattern order)"
+    assert torch.equal(torch.sort(order.long()).values, torch.arange(n, device="cuda"))
