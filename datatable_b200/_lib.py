@@ -23,6 +23,7 @@ EXPORTS = [
     "dtb_group", "dtb_groupby_create", "dtb_groupby_norder", "dtb_groupby_ngroups",
     "dtb_groupby_order", "dtb_groupby_offsets", "dtb_groupby_destroy", "dtb_reduce",
     "dtb_gather", "dtb_memcpy", "dtb_set_option", "dtb_get_option", "dtb_last_call_stats",
+    "dtb_profile_count", "dtb_profile_get", "dtb_profile_reset",
 ]
 
 
@@ -93,6 +94,7 @@ def _load():
     lib.dtb_set_option.argtypes = [c.c_char_p, c.c_int64]
     lib.dtb_get_option.argtypes = [c.c_char_p, c.POINTER(c.c_int64)]
     lib.dtb_last_call_stats.argtypes = [c.POINTER(dtb_call_stats)]
+    lib.dtb_profile_get.argtypes = [c.c_int, c.c_char_p, c.c_int, c.POINTER(c.c_double)]
     if lib.dtb_abi_version() != ABI_VERSION:
         raise ImportError("libdtb200.so ABI version mismatch")
     return lib
@@ -113,3 +115,16 @@ def last_call_stats():
     check(lib.dtb_last_call_stats(ctypes.byref(st)))
     return {"kernels_launched": st.kernels_launched, "radix_passes": st.radix_passes,
             "key_bits": st.key_bits, "scratch_bytes": st.scratch_bytes}
+
+
+def profile_records(reset=True):
+    """[(kernel family, ms), ...] collected while option "profile" is on."""
+    out = []
+    buf = ctypes.create_string_buffer(64)
+    ms = ctypes.c_double(0)
+    for i in range(lib.dtb_profile_count()):
+        check(lib.dtb_profile_get(i, buf, 64, ctypes.byref(ms)))
+        out.append((buf.value.decode(), ms.value))
+    if reset:
+        lib.dtb_profile_reset()
+    return out

@@ -24,6 +24,36 @@ void count_launch(int n) { t_stats.kernels_launched += n; }
 // ---------------------------------------------------------------------------
 static int64_t opt_radix_bits = 8;
 static int64_t opt_verbose = 0;
+static int64_t opt_profile = 0;
+
+// ---------------------------------------------------------------------------
+// optional per-kernel timing with CUDA events on the launching stream
+// (option "profile"): the reference only times whole calls (call_logger.cc:153-174)
+// ---------------------------------------------------------------------------
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static thread_local std::vector<ProfRec> t_prof_open;
+static thread_local std::vector<std::pair<std::string, double>> t_prof_done;
+
+struct ProfScope {
+  bool on; cudaStream_t s; ProfRec r;
+  ProfScope(const char* name, cudaStream_t stream) : on(opt_profile != 0), s(stream) {
+    if (!on) return;
+    r.name = name;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.b, s); t_prof_open.push_back(r); } }
+};
+
+// call after the stream has been synchronised
+static void prof_collect() {
+  for (auto& r : t_prof_open) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) t_prof_done.emplace_back(r.name, (double)ms);
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  t_prof_open.clear();
+}
 
 // ---------------------------------------------------------------------------
 // per-device context: the stream-ordered memory pool keeps scratch resident
@@ -246,8 +276,10 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     dptrs[c] = in[c].dptr;
   }
   DevBuf d_stats; DTB_TRY(d_stats.alloc(sizeof(ColStats) * nkeys, s));
-  for (int c = 0; c < nkeys; c++)
+  for (int c = 0; c < nkeys; c++) {
+    ProfScope ps("col_stats", s);
     DTB_TRY(launch_col_stats(dptrs[c], keys[c].stype, n, d_stats.as<ColStats>() + c, s));
+  }
   ColStats h_stats[MAX_KEYS];
   DTB_CUDA_CHECK(cudaMemcpyAsync(h_stats, d_stats.p, sizeof(ColStats) * nkeys, cudaMemcpyDeviceToHost, s));
   DTB_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -257,11 +289,6 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   DTB_TRY(plan_keys(keys, dptrs, nkeys, flags, na_pos, h_stats, kp, nacount_last));
   if (na_pos == DTB_NA_REMOVE) res.nskip = nacount_last;   // sort.cc:598-605
   t_stats.key_bits = kp.total_bits;
-  if (kp.total_bits > 64) {
-    set_error("composite key of " + std::to_string(kp.total_bits) + " bits (> 64) is not implemented");
-    return DTB_ENOTIMPL;
-  }
-
   if (kp.total_bits == 0) {
     // every key column is constant: identity order, one group (cf. sort.cc:1435-1439)
     DTB_TRY(launch_iota32(order, n, s));
@@ -274,67 +301,110 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     return DTB_OK;
   }
 
-  const int key_bytes = kp.total_bits <= 32 ? 4 : 8;
+  // ---- rounds: a composite wider than 64 bits is sorted in several stable rounds,
+  //      least significant key columns first (the reference refines column by column,
+  //      sort.cc:561-595; here a round covers as many columns as fit in 64 bits) ----------
+  struct Round { KeyPlan kp; bool has_by; };
+  std::vector<Round> rounds;
+  {
+    int c = nkeys - 1;
+    while (c >= 0) {
+      int cols[MAX_KEYS], nc = 0, bits = 0;
+      while (c >= 0 && bits + kp.k[c].bits <= 64) { cols[nc++] = c; bits += kp.k[c].bits; c--; }
+      Round r; memset(&r.kp, 0, sizeof(r.kp)); r.has_by = false;
+      int sh = 0, gs = 0;
+      for (int j = 0; j < nc; j++) {
+        KeyNorm kn = kp.k[cols[j]];
+        kn.lshift = sh; sh += kn.bits;
+        r.kp.k[nc - 1 - j] = kn;
+        if (flags[cols[j]] & DTB_FLAG_SORT_ONLY) gs = sh; else r.has_by = true;
+      }
+      r.kp.nkeys = nc; r.kp.total_bits = sh; r.kp.group_shift = gs;
+      if (sh > 0) rounds.push_back(r);
+    }
+  }
+  const int nrounds = (int)rounds.size();
+  const bool fused_raw = (nrounds == 1 && rounds[0].kp.nkeys == 1);   // normalise on the fly
+  int max_bits = 0;
+  for (auto& r : rounds) if (r.kp.total_bits > max_bits) max_bits = r.kp.total_bits;
+  const int buf_key_bytes = max_bits <= 32 ? 4 : 8;
   const int nbins_log2 = 8;
+  const int nbins = 1 << nbins_log2;
   int width = (int)opt_radix_bits; if (width < 1) width = 1; if (width > nbins_log2) width = nbins_log2;
-  PassPlan pp; plan_passes(kp.total_bits, width, pp);
-  t_stats.radix_passes = pp.npasses;
+
   if (opt_verbose) {
-    fprintf(stderr, "[dtb200] group: n=%lld keys=%d bits=%d key_bytes=%d passes=%d group_shift=%d\n",
-            (long long)n, nkeys, kp.total_bits, key_bytes, pp.npasses, kp.group_shift);
+    fprintf(stderr, "[dtb200] group: n=%lld keys=%d bits=%d rounds=%d\n", (long long)n, nkeys, kp.total_bits, nrounds);
     for (int c = 0; c < nkeys; c++)
       fprintf(stderr, "[dtb200]   key %d: stype=%d desc=%d bits=%d cshift=%d lshift=%d na=%llu\n", c,
               kp.k[c].stype, kp.k[c].desc, kp.k[c].bits, kp.k[c].cshift, kp.k[c].lshift,
               (unsigned long long)h_stats[c].nacount);
   }
 
-  // ---- key source ----------------------------------------------------------------
-  DevBuf keyA, keyB, idxA, idxB;
-  DTB_TRY(keyA.alloc((size_t)n * key_bytes, s));
-  const bool need_b = pp.npasses > 1 || nkeys > 1;
-  if (need_b) DTB_TRY(keyB.alloc((size_t)n * key_bytes, s));
-  if (pp.npasses > 1) DTB_TRY(idxA.alloc((size_t)n * 4, s));
-  if (pp.npasses > 2) DTB_TRY(idxB.alloc((size_t)n * 4, s));
+  DevBuf keyA, keyB, idxA, idxB, idxR0, idxR1;
+  DTB_TRY(keyA.alloc((size_t)n * buf_key_bytes, s));
+  DTB_TRY(keyB.alloc((size_t)n * buf_key_bytes, s));
+  DTB_TRY(idxA.alloc((size_t)n * 4, s));
+  DTB_TRY(idxB.alloc((size_t)n * 4, s));
+  if (nrounds > 1) { DTB_TRY(idxR0.alloc((size_t)n * 4, s)); }
+  if (nrounds > 2) { DTB_TRY(idxR1.alloc((size_t)n * 4, s)); }
 
-  int src_kind = 1;
-  if (nkeys > 1) { DTB_TRY(launch_compose_keys(kp, n, keyA.p, key_bytes, s)); src_kind = 0; }
+  const int32_t* idx_cur = nullptr;        // rows in the order established by the previous rounds
+  void* sorted_keys = nullptr;             // last round's sorted composite keys
+  int last_key_bytes = 4;
+  for (int ri = 0; ri < nrounds; ri++) {
+    const KeyPlan& rk = rounds[ri].kp;
+    const bool last_round = (ri == nrounds - 1);
+    const int key_bytes = rk.total_bits <= 32 ? 4 : 8;
+    PassPlan pp; plan_passes(rk.total_bits, width, pp);
+    t_stats.radix_passes += pp.npasses;
 
-  // ---- histograms -> global digit offsets -------------------------------------------
-  const int nbins = 1 << nbins_log2;
-  DevBuf hist; DTB_TRY(hist.alloc(sizeof(u32) * pp.npasses * nbins, s));
-  DTB_TRY(launch_histograms(src_kind, keyA.p, kp, key_bytes, n, pp, nbins_log2, hist.as<u32>(), s));
-  DTB_TRY(launch_scan_histograms(hist.as<u32>(), pp.npasses, nbins_log2, s));
+    int src_kind = 1;
+    if (!fused_raw) {
+      ProfScope ps("compose_keys", s);
+      DTB_TRY(launch_compose_keys(rk, n, idx_cur, keyA.p, key_bytes, s)); src_kind = 0;
+    }
 
-  // ---- look-back state for all passes, zeroed once ------------------------------------
-  const int64_t tile_rows = radix_pass_tile_rows(key_bytes, nbins_log2);
-  const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
-  const size_t status_words = (size_t)ntiles * nbins;
-  DevBuf status; DTB_TRY(status.alloc(sizeof(u32) * (status_words * pp.npasses + pp.npasses), s));
-  DTB_CUDA_CHECK(cudaMemsetAsync(status.p, 0, status.bytes, s));
-  u32* counters = status.as<u32>() + status_words * pp.npasses;
+    // histograms -> global digit offsets
+    DevBuf hist; DTB_TRY(hist.alloc(sizeof(u32) * pp.npasses * nbins, s));
+    {
+      ProfScope ps("histogram", s);
+      DTB_TRY(launch_histograms(src_kind, keyA.p, rk, key_bytes, n, pp, nbins_log2, hist.as<u32>(), s));
+    }
+    DTB_TRY(launch_scan_histograms(hist.as<u32>(), pp.npasses, nbins_log2, s));
 
-  // ---- passes ----------------------------------------------------------------------
-  // key buffers ping-pong; the composed keys (multi-column) start in keyA.
-  void* kin = keyA.p; void* kout = (nkeys > 1) ? keyB.p : keyA.p;
-  const int32_t* iin = nullptr;
-  void* sorted_keys = nullptr;
-  for (int p = 0; p < pp.npasses; p++) {
-    const bool last = (p == pp.npasses - 1);
-    PassIO io;
-    io.src_kind = (p == 0) ? src_kind : 0;
-    io.keys_in = kin;
-    io.idx_in = iin;
-    io.keys_out = (last && !do_groups) ? nullptr : kout;
-    int32_t* iout = last ? order : ((p & 1) ? idxB.as<int32_t>() : idxA.as<int32_t>());
-    io.idx_out = iout;
-    DTB_TRY(launch_radix_pass(io, kp, key_bytes, n, pp.shift[p], pp.bits[p], nbins_log2,
-                              hist.as<u32>() + (size_t)p * nbins,
-                              status.as<u32>() + status_words * p, counters + p, s));
-    if (last) sorted_keys = kout;
-    // next pass reads what this one wrote
-    kin = kout;
-    kout = (kout == keyA.p) ? keyB.p : keyA.p;
-    iin = iout;
+    // look-back state for all passes of the round, zeroed once
+    const int64_t tile_rows = radix_pass_tile_rows(key_bytes, nbins_log2);
+    const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
+    const size_t status_words = (size_t)ntiles * nbins;
+    DevBuf status; DTB_TRY(status.alloc(sizeof(u32) * (status_words * pp.npasses + pp.npasses), s));
+    DTB_CUDA_CHECK(cudaMemsetAsync(status.p, 0, status.bytes, s));
+    u32* counters = status.as<u32>() + status_words * pp.npasses;
+
+    int32_t* round_out = last_round ? order : ((ri & 1) ? idxR1.as<int32_t>() : idxR0.as<int32_t>());
+    const bool want_sorted_keys = last_round && do_groups && rounds[ri].has_by;
+    void* kin = keyA.p; void* kout = fused_raw ? keyA.p : keyB.p;
+    const int32_t* iin = idx_cur;
+    for (int p = 0; p < pp.npasses; p++) {
+      const bool last = (p == pp.npasses - 1);
+      PassIO io;
+      io.src_kind = (p == 0) ? src_kind : 0;
+      io.keys_in = kin;
+      io.idx_in = iin;
+      io.keys_out = (last && !want_sorted_keys) ? nullptr : kout;
+      int32_t* iout = last ? round_out : ((p & 1) ? idxB.as<int32_t>() : idxA.as<int32_t>());
+      io.idx_out = iout;
+      {
+        ProfScope ps("radix_pass", s);
+        DTB_TRY(launch_radix_pass(io, rk, key_bytes, n, pp.shift[p], pp.bits[p], nbins_log2,
+                                  hist.as<u32>() + (size_t)p * nbins,
+                                  status.as<u32>() + status_words * p, counters + p, s));
+      }
+      if (last && want_sorted_keys) { sorted_keys = kout; last_key_bytes = key_bytes; }
+      kin = kout;
+      kout = (kout == keyA.p) ? keyB.p : keyA.p;
+      iin = iout;
+    }
+    idx_cur = round_out;
   }
 
   // ---- group offsets -----------------------------------------------------------------
@@ -343,13 +413,36 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     DevBuf oscr; DTB_TRY(oscr.alloc(sizeof(u64) * (size_t)(otiles + 3), s));
     DTB_CUDA_CHECK(cudaMemsetAsync(oscr.p, 0, oscr.bytes, s));
     u64* d_ng = oscr.as<u64>() + otiles + 2;
-    DTB_TRY(launch_group_offsets(sorted_keys, key_bytes, kp.group_shift, n, offsets, d_ng,
-                                 oscr.as<u64>(), s));
+    DevBuf headflags;
+    if (nrounds == 1) {
+      ProfScope ps("group_offsets", s);
+      DTB_TRY(launch_group_offsets(sorted_keys, last_key_bytes, rounds[0].kp.group_shift, n, offsets, d_ng,
+                                   oscr.as<u64>(), s));
+    } else {
+      // heads = rows where any by-column differs from the previous row: OR the per-round
+      // comparisons; earlier rounds' keys are re-composed through the final RowIndex.
+      DTB_TRY(headflags.alloc((size_t)n + 32, s));
+      DTB_CUDA_CHECK(cudaMemsetAsync(headflags.p, 0, headflags.bytes, s));
+      for (int ri = 0; ri < nrounds; ri++) {
+        if (!rounds[ri].has_by) continue;
+        const KeyPlan& rk = rounds[ri].kp;
+        const int key_bytes = rk.total_bits <= 32 ? 4 : 8;
+        const void* ks = sorted_keys;
+        if (ri != nrounds - 1 || !sorted_keys) {
+          void* tmp = (sorted_keys == keyA.p) ? keyB.p : keyA.p;
+          DTB_TRY(launch_compose_keys(rk, n, order, tmp, key_bytes, s));
+          ks = tmp;
+        }
+        DTB_TRY(launch_mark_heads(ks, key_bytes, rk.group_shift, n, headflags.as<uint8_t>(), s));
+      }
+      DTB_TRY(launch_group_offsets(headflags.p, 1, 0, n, offsets, d_ng, oscr.as<u64>(), s));
+    }
     u64 h_ng = 0;
     DTB_CUDA_CHECK(cudaMemcpyAsync(&h_ng, d_ng, sizeof(u64), cudaMemcpyDeviceToHost, s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
     res.ngroups = (int64_t)h_ng;
   }
+  if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   return DTB_OK;
 }
 
@@ -400,14 +493,28 @@ int dtb_set_option(const char* name, int64_t value) {
     opt_radix_bits = value; return DTB_OK;
   }
   if (!strcmp(name, "verbose")) { opt_verbose = value; return DTB_OK; }
+  if (!strcmp(name, "profile")) { opt_profile = value; return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
 }
+
+int dtb_profile_count(void) { return (int)t_prof_done.size(); }
+
+int dtb_profile_get(int i, char* name, int cap, double* ms) {
+  if (i < 0 || i >= (int)t_prof_done.size() || !name || cap < 1 || !ms) { set_error("bad dtb_profile_get arguments"); return DTB_EINVAL; }
+  strncpy(name, t_prof_done[i].first.c_str(), (size_t)cap - 1);
+  name[cap - 1] = 0;
+  *ms = t_prof_done[i].second;
+  return DTB_OK;
+}
+
+int dtb_profile_reset(void) { t_prof_done.clear(); return DTB_OK; }
 
 int dtb_get_option(const char* name, int64_t* value) {
   if (!name || !value) { set_error("NULL argument"); return DTB_EINVAL; }
   if (!strcmp(name, "radix_bits")) { *value = opt_radix_bits; return DTB_OK; }
   if (!strcmp(name, "verbose")) { *value = opt_verbose; return DTB_OK; }
+  if (!strcmp(name, "profile")) { *value = opt_profile; return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
 }
@@ -527,9 +634,13 @@ int dtb_reduce(int op, dtb_col value, int64_t nrows_value, const void* order, in
   }
   DevOut d_out; DTB_TRY(d_out.bind(out, (size_t)ngroups * stype_bytes(out_st), s));
   DevBuf acc; DTB_TRY(acc.alloc(sizeof(u64) * (size_t)ngroups * 2, s));
-  DTB_TRY(launch_reduce_impl(op, d_val.dptr, value.stype, nrows_value, d_ord.dptr, order_is64,
-                             (const int32_t*)d_off.dptr, ngroups, n, acc.as<u64>(),
-                             acc.as<u64>() + ngroups, d_out.dptr, s));
+  {
+    ProfScope ps("reduce", s);
+    DTB_TRY(launch_reduce_impl(op, d_val.dptr, value.stype, nrows_value, d_ord.dptr, order_is64,
+                               (const int32_t*)d_off.dptr, ngroups, n, acc.as<u64>(),
+                               acc.as<u64>() + ngroups, d_out.dptr, s));
+  }
+  if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   if (d_out.staged()) {
     DTB_TRY(d_out.finish((size_t)ngroups * stype_bytes(out_st), s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));

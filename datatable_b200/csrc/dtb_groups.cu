@@ -20,7 +20,7 @@ constexpr u64 OST_AGG  = 1ull << 62;
 constexpr u64 OST_INCL = 2ull << 62;
 constexpr u64 OST_MASK = (1ull << 62) - 1;
 
-template <typename KeyT>
+template <typename KeyT, bool FLAGS>
 __global__ void __launch_bounds__(OFF_THREADS)
 group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
                      int32_t* __restrict__ offsets, u64* d_ngroups, u64* scratch /*[0]=ticket, [1..]=status*/)
@@ -51,7 +51,7 @@ group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
 #pragma unroll
     for (int i = 0; i < IPT; i++) k[i] = (p0 + i < n) ? keys[p0 + i] : (KeyT)0;
   }
-  if (p0 > 0 && p0 < n) prev = keys[p0 - 1];
+  if (!FLAGS && p0 > 0 && p0 < n) prev = keys[p0 - 1];
 
   unsigned heads = 0; int c = 0;
 #pragma unroll
@@ -59,8 +59,11 @@ group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
     const int64_t p = p0 + i;
     bool h = false;
     if (p < n) {
-      const KeyT before = (i == 0) ? prev : k[i - 1];
-      h = (p == 0) || ((k[i] >> gshift) != (before >> gshift));
+      if (FLAGS) h = (p == 0) || (k[i] != 0);
+      else {
+        const KeyT before = (i == 0) ? prev : k[i - 1];
+        h = (p == 0) || ((k[i] >> gshift) != (before >> gshift));
+      }
     }
     heads |= (h ? 1u : 0u) << i;
     c += h;
@@ -119,6 +122,29 @@ group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
   }
 }
 
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+mark_heads_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n, uint8_t* __restrict__ flags)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (i > 0 && ((keys[i] >> gshift) != (keys[i - 1] >> gshift))) flags[i] = 1;
+  }
+}
+
+int launch_mark_heads(const void* sorted_keys, int key_bytes, int group_shift, int64_t n,
+                      uint8_t* flags, cudaStream_t s)
+{
+  if (n == 0) return DTB_OK;
+  int64_t want = (n + 255) / 256;
+  int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
+  if (key_bytes == 4) mark_heads_kernel<u32><<<grid, 256, 0, s>>>((const u32*)sorted_keys, group_shift, n, flags);
+  else                mark_heads_kernel<u64><<<grid, 256, 0, s>>>((const u64*)sorted_keys, group_shift, n, flags);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
 int64_t offsets_num_tiles(int64_t n) {
   // the smaller tile (8-byte keys: 4 items/thread) bounds the status array
   const int64_t tile = OFF_THREADS * 4;
@@ -133,13 +159,17 @@ int launch_group_offsets(const void* sorted_keys, int key_bytes, int group_shift
   if (reinterpret_cast<uintptr_t>(sorted_keys) & 15) {
     set_error("internal: sorted key buffer must be 16-byte aligned"); return DTB_EINVAL;
   }
-  if (key_bytes == 4) {
+  if (key_bytes == 1) {
+    const int64_t tile = OFF_THREADS * 32;
+    group_offsets_kernel<uint8_t, true><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
+        (const uint8_t*)sorted_keys, 0, n, offsets_out, d_ngroups, scratch);
+  } else if (key_bytes == 4) {
     const int64_t tile = OFF_THREADS * 8;
-    group_offsets_kernel<u32><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
+    group_offsets_kernel<u32, false><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
         (const u32*)sorted_keys, group_shift, n, offsets_out, d_ngroups, scratch);
   } else {
     const int64_t tile = OFF_THREADS * 4;
-    group_offsets_kernel<u64><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
+    group_offsets_kernel<u64, false><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
         (const u64*)sorted_keys, group_shift, n, offsets_out, d_ngroups, scratch);
   }
   count_launch();

@@ -83,9 +83,9 @@ struct PassPlan {
   int bits[MAX_PASSES];
 };
 
-// Composite key materialisation for multi-column keys: out[i] = X(row i).
-int launch_compose_keys(const KeyPlan& kp, int64_t n, void* keys_out, int key_bytes,
-                        cudaStream_t s);
+// Composite key materialisation for multi-column keys: out[i] = X(row idx[i]) (idx NULL = identity).
+int launch_compose_keys(const KeyPlan& kp, int64_t n, const int32_t* idx, void* keys_out,
+                        int key_bytes, cudaStream_t s);
 
 // Digit histograms of every pass in one read of the key source.
 //   src_kind 0: packed composite keys (key_bytes 4 or 8) at `packed`
@@ -121,9 +121,14 @@ int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_
 // ---------------------------------------------------------------------------
 // scratch: uint64[ntiles + 2] zeroed by the caller.  ngroups_out: device int64.
 int64_t offsets_num_tiles(int64_t n);
+// key_bytes 4/8: heads from adjacent sorted keys; key_bytes 1: `sorted_keys` is a uint8 head-flag
+// array (multi-round composites wider than 64 bits, see launch_mark_heads).
 int launch_group_offsets(const void* sorted_keys, int key_bytes, int group_shift, int64_t n,
                          int32_t* offsets_out, unsigned long long* d_ngroups,
                          unsigned long long* scratch, cudaStream_t s);
+// flags[i] |= (keys[i] >> shift) != (keys[i-1] >> shift)
+int launch_mark_heads(const void* sorted_keys, int key_bytes, int group_shift, int64_t n,
+                      uint8_t* flags, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // Reducers / gather

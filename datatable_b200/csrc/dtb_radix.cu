@@ -27,24 +27,26 @@ namespace dtb {
 // ===========================================================================
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
-compose_keys_kernel(KeyPlan kp, int64_t n, KeyT* __restrict__ out)
+compose_keys_kernel(KeyPlan kp, int64_t n, const int32_t* __restrict__ idx, KeyT* __restrict__ out)
 {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t row = idx ? (int64_t)idx[i] : i;     // later rounds see the rows in the current order
     u64 x = 0;
     for (int c = 0; c < kp.nkeys; c++)
-      x |= norm_load_dynamic(kp.k[c], i) << kp.k[c].lshift;
+      x |= norm_load_dynamic(kp.k[c], row) << kp.k[c].lshift;
     out[i] = (KeyT)x;
   }
 }
 
-int launch_compose_keys(const KeyPlan& kp, int64_t n, void* keys_out, int key_bytes, cudaStream_t s)
+int launch_compose_keys(const KeyPlan& kp, int64_t n, const int32_t* idx, void* keys_out, int key_bytes,
+                        cudaStream_t s)
 {
   if (n == 0) return DTB_OK;
   int64_t want = (n + 255) / 256;
   int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
-  if (key_bytes == 4) compose_keys_kernel<u32><<<grid, 256, 0, s>>>(kp, n, (u32*)keys_out);
-  else                compose_keys_kernel<u64><<<grid, 256, 0, s>>>(kp, n, (u64*)keys_out);
+  if (key_bytes == 4) compose_keys_kernel<u32><<<grid, 256, 0, s>>>(kp, n, idx, (u32*)keys_out);
+  else                compose_keys_kernel<u64><<<grid, 256, 0, s>>>(kp, n, idx, (u64*)keys_out);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;

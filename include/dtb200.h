@@ -185,9 +185,16 @@ DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream st
  * Engine options, the analogue of dt.options.sort.* (sort.cc:259-349).
  *   "radix_bits"   digit width of the LSD passes (default 8)
  *   "verbose"      1 = print the pass plan to stderr
+ *   "profile"      1 = bracket every kernel with CUDA events on the call's stream
  */
 DTB_API int dtb_set_option(const char* name, int64_t value);
 DTB_API int dtb_get_option(const char* name, int64_t* value);
+
+/* Kernel timings collected while option "profile" is on (accumulated on the calling
+ * thread until dtb_profile_reset): record i = (kernel family name, milliseconds). */
+DTB_API int dtb_profile_count(void);
+DTB_API int dtb_profile_get(int i, char* name, int cap, double* ms);
+DTB_API int dtb_profile_reset(void);
 
 /* Per-call statistics of the last dtb_group / dtb_groupby_create on this thread:
  * number of kernels launched, radix passes, significant key bits. */

@@ -1,0 +1,69 @@
+"""CPU: the N>1 exchange logic of datatable_b200.dist under gloo with world_size 2.
+The GPU kernels are replaced by the oracle here (tests may use the oracle as a checker/stand-in);
+what is exercised is the host side: size exchange, padding, all-gather, un-padding, merge order."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+class OracleKernels:
+    @staticmethod
+    def group(keys):
+        from oracle import oracle as orc
+        o, f, ng = orc.group([keys.numpy()], [0], orc.NA_FIRST)
+        return torch.from_numpy(o), torch.from_numpy(f), ng
+
+    @staticmethod
+    def reduce(op, v, order, offsets):
+        from oracle import oracle as orc
+        return torch.from_numpy(orc.reduce(op, v.numpy(), order.numpy(), offsets.numpy()))
+
+    @staticmethod
+    def take(src, idx):
+        return src[idx.long()]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from datatable_b200 import dist as ddist, _lib
+        from oracle import oracle as orc
+        rng = np.random.default_rng(100 + rank)
+        n = 5000 + 777 * rank                      # ragged partitions -> different group counts per rank
+        k = rng.integers(0, 300 + 50 * rank, n).astype(np.int32)
+        v = rng.random(n)
+        o, f, ng = orc.group([k], [0], orc.NA_FIRST)
+        part = orc.reduce(orc.SUM, v, o, f)
+        gkeys = k[o[f[:-1]]]
+        mk, mv = ddist.merge_partials(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
+                                      kernels=OracleKernels)
+        q.put((rank, k, v, mk.numpy(), mv.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_merge_partials_world2():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda t: t[0])
+    kall = np.concatenate([r[1] for r in res]); vall = np.concatenate([r[2] for r in res])
+    uk = np.unique(kall)
+    want = np.array([vall[kall == x].sum() for x in uk])
+    for r in res:                                   # every rank holds the full merged result
+        assert np.array_equal(r[3], uk)
+        assert np.allclose(r[4], want, rtol=1e-12)
