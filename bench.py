@@ -187,16 +187,18 @@ def run_b200(args, rank, local_rank, world):
     launches = [0]
 
     def step():
-        order, offsets, ng = engine.group([k], [0], _lib.NA_FIRST)
+        # group(): RowIndex int32[n] + Groupby offsets int32[ng+1], both left in HBM behind the handle
+        gb = engine.Groupby([k], [0], _lib.NA_FIRST)
         launches[0] += _lib.last_call_stats()["kernels_launched"]
-        sums = engine.reduce(_lib.OP_SUM, v, order, offsets)
+        sums = gb.reduce(_lib.OP_SUM, v)
         launches[0] += _lib.last_call_stats()["kernels_launched"]
+        ng = gb.ngroups
         if world > 1:
-            first = engine.gather(engine.Col(order, _lib.INT32), offsets[:-1])
-            gkeys = engine.gather(k, first)
+            gkeys = engine.gather(k, gb.first_rows())
             launches[0] += 2
             gkeys, sums = ddist.merge_partials(gkeys, sums, _lib.OP_SUM)
-        return order, offsets, ng, sums
+        gb.close()
+        return None, None, ng, sums
 
     def barrier():
         if world > 1:
@@ -270,6 +272,8 @@ def run_b200(args, rank, local_rank, world):
                 "alg_bytes_per_launch": alg_bytes_launch}
     step_alg = 16.0 * n / (ms_step / 1e3) / 1e9          # key 4 + value 8 + RowIndex 4 B/row
     kernel_ms = {nm: sum(v_) / args.steps for nm, v_ in fam.items()}
+    if rank == 0 and os.environ.get("DTB_BENCH_DEBUG"):
+        print("kernel_ms_per_step", kernel_ms, "step", ms_step, file=sys.stderr)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -2,6 +2,7 @@
 // host<->device staging and error reporting.  No compute happens on the host:
 // without a CUDA device every entry point fails with DTB_ECUDA.
 #include <stdio.h>
+#include <chrono>
 #include <string.h>
 #include <mutex>
 #include <string>
@@ -60,6 +61,11 @@ static void prof_collect() {
 // ---------------------------------------------------------------------------
 static std::mutex g_ctx_mutex;
 static bool g_ctx_ready[64] = {false};
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+#define DTB_TL(label) do { if (opt_verbose >= 2) fprintf(stderr, "[dtb200]   t=%9.3f ms  %s\n", now_ms() - tl0, label); } while (0)
 
 static int ensure_context() {
   int dev = 0;
@@ -177,6 +183,11 @@ struct GroupResult {
   int64_t n = 0;
   int64_t nskip = 0;     // leading NA rows to drop (na_position = remove)
   int64_t ngroups = -1;
+  // direct-address reducer support (small key domains, device-resident key columns)
+  bool    direct = false;
+  KeyPlan direct_kp;
+  int64_t direct_table = 0;
+  DevBuf  gkeys;         // uint32[ngroups]
 };
 
 // Builds the per-column normalisation from device-computed stats.
@@ -235,9 +246,11 @@ static void plan_passes(int total_bits, int width, PassPlan& pp) {
 
 static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t n,
                       cudaStream_t s, int32_t* order_dev /*optional caller buffer*/,
-                      int32_t* offsets_dev /*optional caller buffer, n+1*/, GroupResult& res)
+                      int32_t* offsets_dev /*optional caller buffer, n+1*/, GroupResult& res,
+                      bool want_direct = false)
 {
   t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  const double tl0 = now_ms();
   if (nkeys < 1 || nkeys > MAX_KEYS) { set_error("number of key columns must be in 1.." + std::to_string(MAX_KEYS)); return DTB_EINVAL; }
   if (!keys || !flags) { set_error("keys/flags must not be NULL"); return DTB_EINVAL; }
   if (na_pos < DTB_NA_FIRST || na_pos > DTB_NA_REMOVE) { set_error("na position value is not supported"); return DTB_EINVAL; }
@@ -284,6 +297,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   DTB_CUDA_CHECK(cudaMemcpyAsync(h_stats, d_stats.p, sizeof(ColStats) * nkeys, cudaMemcpyDeviceToHost, s));
   DTB_CUDA_CHECK(cudaStreamSynchronize(s));
 
+  DTB_TL("stats synced");
   KeyPlan kp; memset(&kp, 0, sizeof(kp));
   int64_t nacount_last = 0;
   DTB_TRY(plan_keys(keys, dptrs, nkeys, flags, na_pos, h_stats, kp, nacount_last));
@@ -348,6 +362,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   if (nrounds > 1) { DTB_TRY(idxR0.alloc((size_t)n * 4, s)); }
   if (nrounds > 2) { DTB_TRY(idxR1.alloc((size_t)n * 4, s)); }
 
+  DTB_TL("scratch allocated");
   const int32_t* idx_cur = nullptr;        // rows in the order established by the previous rounds
   void* sorted_keys = nullptr;             // last round's sorted composite keys
   int last_key_bytes = 4;
@@ -407,6 +422,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     idx_cur = round_out;
   }
 
+  DTB_TL("passes enqueued");
   // ---- group offsets -----------------------------------------------------------------
   if (do_groups) {
     const int64_t otiles = offsets_num_tiles(n);
@@ -441,7 +457,20 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     DTB_CUDA_CHECK(cudaMemcpyAsync(&h_ng, d_ng, sizeof(u64), cudaMemcpyDeviceToHost, s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
     res.ngroups = (int64_t)h_ng;
+    // group key of every group, for the direct-address reducers
+    bool staged = false;
+    for (int c = 0; c < nkeys; c++) staged = staged || (in[c].buf.p != nullptr);
+    const int dbits = (nrounds == 1) ? rounds[0].kp.total_bits - rounds[0].kp.group_shift : 99;
+    if (want_direct && nrounds == 1 && !staged && dbits <= 22 && na_pos != DTB_NA_REMOVE) {
+      DTB_TRY(res.gkeys.alloc(sizeof(u32) * (size_t)(res.ngroups + 1), s));
+      DTB_TRY(launch_group_keys(sorted_keys, last_key_bytes, offsets, rounds[0].kp.group_shift, res.ngroups,
+                                res.gkeys.as<u32>(), s));
+      res.direct = true;
+      res.direct_kp = rounds[0].kp;
+      res.direct_table = (int64_t)1 << dbits;
+    }
   }
+  DTB_TL("offsets synced");
   if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   return DTB_OK;
 }
@@ -459,6 +488,12 @@ struct dtb_groupby {
   void* offsets = nullptr;    // device int32[ngroups+1]
   int64_t norder = 0;
   int64_t ngroups = -1;
+  int64_t nrows = 0;
+  // direct-address reducers: valid while the caller keeps the key columns alive and unchanged
+  bool direct = false;
+  dtb::KeyPlan kp;
+  int64_t table = 0;
+  void* gkeys = nullptr;      // device uint32[ngroups]
 };
 
 extern "C" {
@@ -566,11 +601,13 @@ int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags, int na_
   if (!out) { set_error("out is NULL"); return DTB_EINVAL; }
   *out = nullptr;
   GroupResult res;
-  int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, nullptr, nullptr, res);
+  int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, nullptr, nullptr, res, true);
   if (rc != DTB_OK) return rc;
   dtb_groupby* g = new dtb_groupby();
   g->norder = res.n - res.nskip;
   g->ngroups = res.ngroups;
+  g->nrows = res.n;
+  if (res.direct) { g->direct = true; g->kp = res.direct_kp; g->table = res.direct_table; g->gkeys = res.gkeys.detach(); }
   if (res.ngroups >= 0) {
     // shrink the worst-case offsets buffer to ngroups+1 entries
     DevBuf exact;
@@ -597,6 +634,7 @@ int dtb_groupby_destroy(dtb_groupby* g, dtb_stream stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (g->order_base) cudaFreeAsync(g->order_base, s);
   if (g->offsets) cudaFreeAsync(g->offsets, s);
+  if (g->gkeys) cudaFreeAsync(g->gkeys, s);
   delete g;
   return DTB_OK;
 }
@@ -643,6 +681,39 @@ int dtb_reduce(int op, dtb_col value, int64_t nrows_value, const void* order, in
   if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   if (d_out.staged()) {
     DTB_TRY(d_out.finish((size_t)ngroups * stype_bytes(out_st), s));
+    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  }
+  return DTB_OK;
+}
+
+int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_value, dtb_stream stream, void* out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g) { set_error("groupby handle is NULL"); return DTB_EINVAL; }
+  if (g->ngroups < 0) { set_error("the handle holds no Groupby (sort-only call)"); return DTB_EINVAL; }
+  const bool device_value = (op == DTB_OP_NROWS) || is_device_ptr(value.data);
+  if (!g->direct || op == DTB_OP_NROWS || !device_value || nrows_value != g->nrows)
+    return dtb_reduce(op, value, nrows_value, g->order, 0, g->offsets, g->ngroups, stream, out);
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  const int out_st = reduce_out_stype_host(op, value.stype);
+  if (!out_st) {
+    set_error("Invalid column of stype " + std::to_string(value.stype) + " in reducer " + std::to_string(op));
+    return stype_supported(value.stype) ? DTB_EINVAL : DTB_ENOTIMPL;
+  }
+  if (!out && g->ngroups > 0) { set_error("out is NULL"); return DTB_EINVAL; }
+  DTB_TRY(ensure_context());
+  if (g->ngroups == 0) return DTB_OK;
+  DevOut d_out; DTB_TRY(d_out.bind(out, (size_t)g->ngroups * stype_bytes(out_st), s));
+  DevBuf acc; DTB_TRY(acc.alloc(sizeof(u64) * (size_t)g->table * 2, s));
+  {
+    ProfScope ps("reduce_direct", s);
+    DTB_TRY(launch_reduce_direct(op, g->kp, value.data, value.stype, g->nrows, g->table,
+                                 (const uint32_t*)g->gkeys, g->ngroups, acc.as<u64>(),
+                                 acc.as<u64>() + g->table, d_out.dptr, s));
+  }
+  if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
+  if (d_out.staged()) {
+    DTB_TRY(d_out.finish((size_t)g->ngroups * stype_bytes(out_st), s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
   }
   return DTB_OK;

@@ -140,6 +140,13 @@ int launch_reduce_impl(int op, const void* value, int stype, int64_t nrows_value
                        void* out, cudaStream_t s);
 int reduce_out_stype_host(int op, int stype);
 
+// Direct-address reducers over a small normalised key domain (see dtb_reduce.cu).
+int launch_reduce_direct(int op, const KeyPlan& kp, const void* value, int stype, int64_t n,
+                         int64_t table, const uint32_t* gkeys, int64_t ngroups,
+                         unsigned long long* acc0, unsigned long long* acc1, void* out, cudaStream_t s);
+int launch_group_keys(const void* sorted_keys, int key_bytes, const int32_t* offsets, int group_shift,
+                      int64_t ngroups, uint32_t* gkeys, cudaStream_t s);
+
 int launch_gather(const void* src, int stype, int64_t nrows_src, const void* order,
                   int order_is64, int64_t n, void* out, cudaStream_t s);
 

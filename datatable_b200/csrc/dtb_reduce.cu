@@ -351,6 +351,224 @@ int launch_reduce_impl(int op, const void* value, int stype, int64_t nv, const v
 int reduce_out_stype_host(int op, int st) { return reduce_out_stype(op, st); }
 
 // ===========================================================================
+// Direct-address reducers (small key domains)
+// ===========================================================================
+// When the group key of a row can be computed from the key columns alone -- the normalised
+// composite key x = X(row) >> group_shift spans at most 2^22 values -- the reducers do not
+// need the RowIndex at all: rows are streamed in storage order (coalesced, no gather), and
+// each row folds its value into acc[x] with one L2 atomic.  The table (<= 32 MB) stays
+// resident in the 126 MB L2.  Rows of a warp that share x are combined first
+// (__match_any_sync) so that hot keys do not serialise on one address.  A finalize kernel
+// maps group g -> acc[gkeys[g]] and applies the reference's output stype / NA rules.
+//
+// Bound: L2 atomic throughput (measured 170 G atomics/s on B200), then HBM.
+// Algorithmic bytes per row: key column(s) + value column, read once.
+template <typename T, int CAT, typename KSrc>
+__global__ void __launch_bounds__(512)
+direct_reduce_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load_t* __restrict__ v,
+                     int64_t n, u64* acc0, u64* acc1, int flag)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = ((n + 31) / 32) * 32;                // keep whole warps in the loop
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool in = i < n;
+    u32 x = 0xffffffffu;
+    Partial<CAT> part; p_init(part, flag);
+    if (in) {
+      x = (u32)(ksrc.load(i) >> gshift);
+      p_add<T, CAT>(part, v[i], true, flag);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, x);
+    if (peers != (1u << lane)) {
+      // rare for spread-out keys: fold the partials of equal keys into the lowest lane
+      const int leader = __ffs(peers) - 1;
+      unsigned rest = peers & ~(1u << leader);
+      Partial<CAT> tot = part;
+      while (__any_sync(0xffffffffu, rest != 0)) {
+        const int src = rest ? (__ffs(rest) - 1) : lane;
+        Partial<CAT> o;
+        if constexpr (CAT == CAT_SUMI) o.s = __shfl_sync(0xffffffffu, part.s, src);
+        else if constexpr (CAT == CAT_SUMF) o.s = __shfl_sync(0xffffffffu, part.s, src);
+        else if constexpr (CAT == CAT_MEAN) { o.s = __shfl_sync(0xffffffffu, part.s, src); o.c = __shfl_sync(0xffffffffu, part.c, src); }
+        else if constexpr (CAT == CAT_MINMAX) o.key = __shfl_sync(0xffffffffu, part.key, src);
+        else o.c = __shfl_sync(0xffffffffu, part.c, src);
+        if (rest && lane == leader) p_merge(tot, o, flag);
+        rest &= rest - 1;
+      }
+      if (lane == leader) part = tot; else p_init(part, flag);
+    }
+    if (in) p_flush(part, (int64_t)x, acc0, acc1, flag);
+  }
+}
+
+__global__ void finalize_direct_kernel(int op, int in_stype, int out_stype, const u64* __restrict__ acc0,
+                                       const u64* __restrict__ acc1, const u32* __restrict__ gkeys,
+                                       int64_t ng, void* out)
+{
+  const bool in_float = (in_stype == DTB_STYPE_FLOAT32 || in_stype == DTB_STYPE_FLOAT64);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride) {
+    const u32 x = gkeys[g];
+    const u64 a = acc0[x];
+    bool valid = true; u64 bits = a;
+    switch (op) {
+      case DTB_OP_SUM:
+        if (out_stype == DTB_STYPE_FLOAT32) bits = __float_as_uint((float)__longlong_as_double((long long)a));
+        break;
+      case DTB_OP_MEAN: {
+        const u64 c = acc1[x];
+        valid = c != 0;
+        const double m = __longlong_as_double((long long)a) / (double)c;
+        bits = (out_stype == DTB_STYPE_FLOAT32) ? (u64)__float_as_uint((float)m) : (u64)__double_as_longlong(m);
+        break; }
+      case DTB_OP_MIN: case DTB_OP_MAX: {
+        const bool is_min = (op == DTB_OP_MIN);
+        valid = is_min ? (a != ~0ull) : (a != 0ull);
+        if (in_float) bits = (in_stype == DTB_STYPE_FLOAT32) ? (u64)f32_unimage((u32)a) : f64_unimage(a);
+        else bits = (is_min ? a + 1 : a) ^ 0x8000000000000000ull;
+        break; }
+      default: break;
+    }
+    store_result(out, out_stype, g, valid, bits);
+  }
+}
+
+// key sources: one raw column normalised on the fly, or the general multi-column composite
+template <typename TK>
+struct DirectRawKey {
+  const typename RawKey<TK>::load_t* p; KeyNorm k;
+  __device__ __forceinline__ u64 load(int64_t i) const {
+    u64 u; bool valid = RawKey<TK>::get(p[i], u);
+    return norm_apply(valid, u, k);
+  }
+};
+struct DirectComposite {
+  KeyPlan kp;
+  __device__ __forceinline__ u64 load(int64_t i) const {
+    u64 x = 0;
+    for (int c = 0; c < kp.nkeys; c++) x |= norm_load_dynamic(kp.k[c], i) << kp.k[c].lshift;
+    return x;
+  }
+};
+
+template <typename T, int CAT, typename KSrc>
+static int run_direct(const KSrc& ks, int gshift, const void* v, int64_t n, u64* acc0, u64* acc1, int flag,
+                      cudaStream_t s)
+{
+  typedef typename RawKey<T>::load_t L;
+  int64_t want = (n + 511) / 512;
+  int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
+  direct_reduce_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+template <int CAT, typename KSrc>
+static int direct_T(int st, const KSrc& ks, int gshift, const void* v, int64_t n, u64* acc0, u64* acc1,
+                    int flag, cudaStream_t s)
+{
+  switch (st) {
+    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:
+      if constexpr (CAT != CAT_SUMF) return run_direct<int8_t, CAT>(ks, gshift, v, n, acc0, acc1, flag, s); break;
+    case DTB_STYPE_INT16:
+      if constexpr (CAT != CAT_SUMF) return run_direct<int16_t, CAT>(ks, gshift, v, n, acc0, acc1, flag, s); break;
+    case DTB_STYPE_INT32:
+      if constexpr (CAT != CAT_SUMF) return run_direct<int32_t, CAT>(ks, gshift, v, n, acc0, acc1, flag, s); break;
+    case DTB_STYPE_INT64:
+      if constexpr (CAT != CAT_SUMF) return run_direct<int64_t, CAT>(ks, gshift, v, n, acc0, acc1, flag, s); break;
+    case DTB_STYPE_FLOAT32:
+      if constexpr (CAT != CAT_SUMI) return run_direct<float, CAT>(ks, gshift, v, n, acc0, acc1, flag, s); break;
+    case DTB_STYPE_FLOAT64:
+      if constexpr (CAT != CAT_SUMI) return run_direct<double, CAT>(ks, gshift, v, n, acc0, acc1, flag, s); break;
+  }
+  set_error("internal: reducer/stype combination"); return DTB_EINVAL;
+}
+
+template <typename KSrc>
+static int direct_op(int op, int st, const KSrc& ks, int gshift, const void* v, int64_t n, u64* acc0,
+                     u64* acc1, cudaStream_t s)
+{
+  const bool isflt = (st == DTB_STYPE_FLOAT32 || st == DTB_STYPE_FLOAT64);
+  switch (op) {
+    case DTB_OP_SUM:
+      return isflt ? direct_T<CAT_SUMF>(st, ks, gshift, v, n, acc0, acc1, 0, s)
+                   : direct_T<CAT_SUMI>(st, ks, gshift, v, n, acc0, acc1, 0, s);
+    case DTB_OP_MEAN:    return direct_T<CAT_MEAN>(st, ks, gshift, v, n, acc0, acc1, 0, s);
+    case DTB_OP_MIN:     return direct_T<CAT_MINMAX>(st, ks, gshift, v, n, acc0, acc1, 1, s);
+    case DTB_OP_MAX:     return direct_T<CAT_MINMAX>(st, ks, gshift, v, n, acc0, acc1, 0, s);
+    case DTB_OP_COUNT:   return direct_T<CAT_COUNT>(st, ks, gshift, v, n, acc0, acc1, 0, s);
+    case DTB_OP_COUNTNA: return direct_T<CAT_COUNT>(st, ks, gshift, v, n, acc0, acc1, 1, s);
+  }
+  set_error("unknown reducer"); return DTB_EINVAL;
+}
+
+// acc0/acc1: device scratch of `table` u64 each; gkeys: uint32[ng] group key of every group.
+int launch_reduce_direct(int op, const KeyPlan& kp, const void* value, int stype, int64_t n,
+                         int64_t table, const uint32_t* gkeys, int64_t ng, u64* acc0, u64* acc1,
+                         void* out, cudaStream_t s)
+{
+  const int out_st = reduce_out_stype(op, stype);
+  if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
+  if (ng == 0) return DTB_OK;
+  const int tgrid = (int)((table + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (table + 255) / 256);
+  fill_u64_kernel<<<tgrid, 256, 0, s>>>(acc0, table, (op == DTB_OP_MIN) ? ~0ull : 0ull);
+  count_launch();
+  if (op == DTB_OP_MEAN) { fill_u64_kernel<<<tgrid, 256, 0, s>>>(acc1, table, 0ull); count_launch(); }
+  DTB_CUDA_CHECK(cudaGetLastError());
+  if (n > 0) {
+    int rc;
+    if (kp.nkeys == 1) {
+      const KeyNorm& k = kp.k[0];
+#define DTB_CASE(TK) { DirectRawKey<TK> ks; ks.p = (const typename RawKey<TK>::load_t*)k.data; ks.k = k; \
+                       rc = direct_op(op, stype, ks, kp.group_shift, value, n, acc0, acc1, s); break; }
+      switch (k.stype) {
+        case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
+        case DTB_STYPE_INT16:                        DTB_CASE(int16_t)
+        case DTB_STYPE_INT32: case DTB_STYPE_DATE32: DTB_CASE(int32_t)
+        case DTB_STYPE_INT64: case DTB_STYPE_TIME64: DTB_CASE(int64_t)
+        case DTB_STYPE_FLOAT32:                      DTB_CASE(float)
+        case DTB_STYPE_FLOAT64:                      DTB_CASE(double)
+        default: set_error("internal: bad key stype"); return DTB_EINVAL;
+      }
+#undef DTB_CASE
+    } else {
+      DirectComposite ks; ks.kp = kp;
+      rc = direct_op(op, stype, ks, kp.group_shift, value, n, acc0, acc1, s);
+    }
+    if (rc != DTB_OK) return rc;
+  }
+  const int fgrid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+  finalize_direct_kernel<<<fgrid, 256, 0, s>>>(op, stype, out_st, acc0, acc1, gkeys, ng, out);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+// gkeys[g] = sorted_keys[offsets[g]] >> gshift  (the normalised key of every group)
+template <typename KeyT>
+__global__ void group_keys_kernel(const KeyT* __restrict__ sorted, const int32_t* __restrict__ offsets,
+                                  int gshift, int64_t ng, u32* __restrict__ gkeys)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride)
+    gkeys[g] = (u32)(sorted[offsets[g]] >> gshift);
+}
+
+int launch_group_keys(const void* sorted_keys, int key_bytes, const int32_t* offsets, int gshift,
+                      int64_t ng, uint32_t* gkeys, cudaStream_t s)
+{
+  if (ng == 0) return DTB_OK;
+  const int grid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+  if (key_bytes == 4) group_keys_kernel<u32><<<grid, 256, 0, s>>>((const u32*)sorted_keys, offsets, gshift, ng, gkeys);
+  else                group_keys_kernel<u64><<<grid, 256, 0, s>>>((const u64*)sorted_keys, offsets, gshift, ng, gkeys);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+// ===========================================================================
 // RowIndex gather (ArrayView materialisation)
 // ===========================================================================
 template <typename E, typename OrdT>

@@ -67,6 +67,13 @@ class Col:
             stype = _NP2ST[npdt]
         self.stype = stype
 
+    @classmethod
+    def from_ptr(cls, ptr, stype, nrows, on_device=True, owner=None):
+        """Wrap a raw pointer (e.g. the HBM-resident RowIndex of a Groupby handle) without copying."""
+        self = cls.__new__(cls)
+        self.data, self.on_device, self.ptr, self.nrows, self.stype = owner, on_device, ptr, nrows, stype
+        return self
+
     def c(self):
         return dtb_col(ctypes.c_void_p(self.ptr), self.stype, 0)
 
@@ -133,22 +140,39 @@ class Groupby:
         h = ctypes.c_void_p(0)
         check(lib.dtb_groupby_create(ckeys, nk, cflags, na_pos, n, _stream(), ctypes.byref(h)))
         self._h = h
+        self._keys = cols            # the handle may re-read the key columns (direct-address reducers)
         self.norder = lib.dtb_groupby_norder(h)
         self.ngroups = lib.dtb_groupby_ngroups(h)
         self.order_ptr = lib.dtb_groupby_order(h)
         self.offsets_ptr = lib.dtb_groupby_offsets(h)
 
     def reduce(self, op, value, out=None):
-        v = Col(value)
-        out_st = lib.dtb_reduce_out_stype(op, v.stype)
+        if op == _lib.OP_NROWS:
+            v = Col(torch.empty(0, dtype=torch.int8, device="cuda"), INT8)
+            out_st = INT64
+        else:
+            v = Col(value)
+            out_st = lib.dtb_reduce_out_stype(op, v.stype)
+        if not out_st:
+            raise _lib.DtbValueError(f"Invalid column of stype {v.stype} in reducer {op}")
+        self._keepalive = getattr(self, "_keepalive", [])
         if out is None:
             out, optr = _alloc(self.ngroups, out_st, v.on_device)
         else:
             optr = out.data_ptr() if is_tensor(out) else out.ctypes.data
-        check(lib.dtb_reduce(op, v.c(), v.nrows, ctypes.c_void_p(self.order_ptr), 0,
-                             ctypes.c_void_p(self.offsets_ptr), self.ngroups, _stream(),
-                             ctypes.c_void_p(optr)))
+        check(lib.dtb_groupby_reduce(self._h, op, v.c(), v.nrows, _stream(), ctypes.c_void_p(optr)))
         return out
+
+    def order_col(self):
+        """The RowIndex as a zero-copy column view (valid while the handle lives)."""
+        return Col.from_ptr(self.order_ptr, INT32, self.norder, owner=self)
+
+    def offsets_col(self, drop_last=False):
+        return Col.from_ptr(self.offsets_ptr, INT32, self.ngroups + (0 if drop_last else 1), owner=self)
+
+    def first_rows(self):
+        """Row id of the first row of every group: order[offsets[:-1]] (eval_context.cc:124-135)."""
+        return gather(self.order_col(), self.offsets_col(drop_last=True))
 
     def order(self):
         t = torch.empty(self.norder, dtype=torch.int32, device="cuda")
@@ -218,12 +242,9 @@ def gather(src, order, stype=None):
         raise _lib.DtbValueError("order must be int32 or int64")
     n = o.nrows
     device = s.on_device and o.on_device
-    if device:
-        out = torch.empty(n, dtype=s.data.dtype, device="cuda")
-        optr = out.data_ptr()
-    else:
-        out = np.empty(n, dtype=s.data.dtype if not is_tensor(s.data) else _ST2NP[s.stype])
-        optr = out.ctypes.data
+    out, optr = _alloc(n, s.stype, device)
+    if not device and s.stype == BOOL and isinstance(s.data, np.ndarray) and s.data.dtype == np.bool_:
+        out = out.view(np.bool_)
     check(lib.dtb_gather(s.c(), s.nrows, ctypes.c_void_p(o.ptr), 1 if o.stype == INT64 else 0, n,
                          _stream(), ctypes.c_void_p(optr)))
     return out

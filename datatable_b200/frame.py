@@ -273,12 +273,18 @@ def _evaluate(DT, j, by_, sort_):
             flags.append((FLAG_DESCENDING if desc else 0) | FLAG_SORT_ONLY)
     order = offsets = None
     ngroups = None
-    if keycols:
-        order, offsets, ngroups = engine.group(keycols, flags, na_pos)
-
-    # ---- j ----
+    gb = None
     names, exprs = _resolve_j(DT, j)
     has_reducer = any(isinstance(e, Reducer) for e in exprs)
+    if keycols:
+        if by_ is not None and has_reducer:
+            # RowIndex + Groupby stay in HBM behind a handle; reducers go through it
+            gb = engine.Groupby(keycols, flags, na_pos)
+            ngroups = gb.ngroups
+        else:
+            order, offsets, ngroups = engine.group(keycols, flags, na_pos)
+
+    # ---- j ----
     out = Frame()
 
     def add(name, data, st):
@@ -294,19 +300,20 @@ def _evaluate(DT, j, by_, sort_):
     if by_ is not None:
         if has_reducer:
             # group keys = first row of every group (get_group_rowindex, eval_context.cc:124-135)
-            first = _index_through(order, offsets[:-1])
+            first = gb.first_rows()
             for ref in by_.cols:
                 c = dcol(ref.name)
                 add(ref.name, engine.gather(c, first), c.stype)
             for name, e in zip(names, exprs):
                 if isinstance(e, Reducer):
-                    add(name, _reduce(dcol, e, order, offsets), None)
+                    add(name, gb.reduce(e.op, None if e.arg is None else dcol(e.arg.name)), None)
                 else:
                     raise NotImplementedError("mixing reducers and plain columns under by() is outside the hot path")
             for n_ in out._cols:
                 if out._stypes[n_] is None:
                     out._stypes[n_] = engine.Col(out._cols[n_]).stype
             out._nrows = ngroups
+            gb.close()
             return out
         # by() without reducers: every row, grouped order, key columns first
         bynames = [r.name for r in by_.cols]

@@ -169,6 +169,17 @@ DTB_API int dtb_reduce(int op, dtb_col value, int64_t nrows_value,
                dtb_stream stream, void* out);
 
 /*
+ * dtb_groupby_reduce -- dtb_reduce over the handle's RowIndex / offsets.  When the handle's
+ * key domain is small (normalised group key < 2^22 values) and the key columns passed to
+ * dtb_groupby_create live in device memory, the reducer streams the key and value columns in
+ * storage order and accumulates with L2 atomics instead of gathering through the RowIndex;
+ * the caller must keep those key columns alive and unchanged while the handle is used.
+ * Results are identical to dtb_reduce (floating sums up to association order).
+ */
+DTB_API int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_value,
+                       dtb_stream stream, void* out);
+
+/*
  * dtb_gather -- replaces materialisation of ArrayView_ColumnImpl<int32/int64>
  * (column/view.cc:88-155): out[i] = order[i] < 0 ? NA : src[order[i]].
  */

@@ -165,3 +165,59 @@ def test_large_float64_sort_properties():
     zb = bits[zero]
     assert bool((zb[1:] >= zb[:-1]).all()), "-0.0 sorts before +0.0 (bit-pattern order)"
     assert torch.equal(torch.sort(order.long()).values, torch.arange(n, device="cuda"))
+
+
+@pytest.mark.parametrize("kst", [INT8, INT32, INT64, FLOAT64])
+def test_groupby_handle_direct_reducers_vs_oracle(kst):
+    """Groupby handle on device-resident columns: small key domains take the direct-address
+    (streaming + L2 atomics) reducers; results must equal the oracle's gather-based answer."""
+    import torch
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    n = 400_000
+    rng = np.random.default_rng(900 + kst)
+    for variant in ("uniform", "hot", "na"):
+        k = make_col(rng, kst, n, "few" if kst != INT32 else "unit", 0.05 if variant == "na" else 0.0)
+        if variant == "hot":
+            k[rng.random(n) < 0.7] = k[0]                  # one key owns 70% of the rows
+        want_o, want_f, want_ng = orc.group([k], [0], 1, stypes=[kst])
+        kd = torch.from_numpy(k).cuda()
+        gb = engine.Groupby([engine.Col(kd, kst)], [0], 1)
+        assert gb.ngroups == want_ng
+        assert np.array_equal(gb.order().cpu().numpy(), want_o)
+        assert np.array_equal(gb.offsets().cpu().numpy(), want_f)
+        for vst in (BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64):
+            v = make_col(rng, vst, n, "few" if vst == BOOL else "unit", 0.1)
+            vd = engine.Col(torch.from_numpy(v).cuda(), vst)
+            for op in ("sum", "mean", "min", "max", "count", "countna"):
+                want = orc.reduce(OPS[op], v, want_o, want_f, stype=vst)
+                got = gb.reduce(OPS[op], vd).cpu().numpy()
+                assert_reducer_equal(got, want, op, vst, ctx=f"direct key st={kst} {variant} {op} vst={vst}")
+        got = gb.reduce(OPS["nrows"], None).cpu().numpy()
+        assert np.array_equal(got, np.diff(want_f).astype(np.int64))
+        gb.close()
+
+
+def test_groupby_handle_multikey_direct():
+    import torch
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    n = 300_000
+    rng = np.random.default_rng(77)
+    k1 = make_col(rng, INT64, n, "few", 0.02) << 20
+    k1[k1 == (NA[INT64] << 20)] = NA[INT64]
+    k2 = make_col(rng, INT16, n, "few", 0.02)
+    x = make_col(rng, FLOAT64, n, "unit", 0.0)
+    v = make_col(rng, FLOAT64, n, "unit", 0.1)
+    # by(k1, k2) + sort(x): groups come from the by-columns only
+    flags = [0, DESCENDING, SORT_ONLY]
+    want_o, want_f, want_ng = orc.group([k1, k2, x], flags, 1)
+    gb = engine.Groupby([torch.from_numpy(a).cuda() for a in (k1, k2, x)], flags, 1)
+    assert np.array_equal(gb.order().cpu().numpy(), want_o)
+    assert np.array_equal(gb.offsets().cpu().numpy(), want_f)
+    vd = torch.from_numpy(v).cuda()
+    for op in ("sum", "mean", "min", "max", "count"):
+        want = orc.reduce(OPS[op], v, want_o, want_f)
+        got = gb.reduce(OPS[op], vd).cpu().numpy()
+        assert_reducer_equal(got, want, op, FLOAT64, ctx=f"multikey direct {op}")
+    gb.close()
