@@ -97,18 +97,93 @@ static int ensure_context() {
   return DTB_OK;
 }
 
-// Stream-ordered scratch buffer.
+// ---------------------------------------------------------------------------
+// Scratch arena.  Every API call carves its temporaries out of one HBM slab that the
+// calling thread keeps between calls: after the first call of a given size there are
+// no allocator calls at all on the hot path (cudaMallocAsync of multi-GB blocks costs
+// milliseconds even when the pool already holds the memory).  The slab only grows.
+// ---------------------------------------------------------------------------
+struct Arena {
+  struct Slab { char* p; size_t cap; };
+  std::vector<Slab> slabs;
+  size_t cur = 0, off = 0;
+  int depth = 0;
+  cudaStream_t last_stream = nullptr;
+  bool have_last = false;
+
+  int begin(cudaStream_t s) {
+    if (depth++ > 0) return DTB_OK;
+    // work enqueued by the previous call may still be using the slab on another stream
+    if (have_last && last_stream != s) DTB_CUDA_CHECK(cudaStreamSynchronize(last_stream));
+    last_stream = s; have_last = true;
+    if (slabs.size() > 1) {                         // coalesce what the last call needed into one slab
+      size_t total = 0;
+      for (auto& sl : slabs) total += sl.cap;
+      DTB_CUDA_CHECK(cudaDeviceSynchronize());
+      for (auto& sl : slabs) cudaFree(sl.p);
+      slabs.clear();
+      char* p = nullptr;
+      cudaError_t e = cudaMalloc(&p, total);
+      if (e != cudaSuccess) { cudaGetLastError(); }   // fall back to growing on demand
+      else slabs.push_back({p, total});
+    }
+    cur = 0; off = 0;
+    return DTB_OK;
+  }
+  void end() { if (depth > 0) depth--; }
+  int take(size_t bytes, void** out) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    while (cur < slabs.size()) {
+      if (off + bytes <= slabs[cur].cap) { *out = slabs[cur].p + off; off += bytes; return DTB_OK; }
+      cur++; off = 0;
+    }
+    size_t cap = bytes < ((size_t)64 << 20) ? ((size_t)64 << 20) : bytes;
+    char* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc(" + std::to_string(cap) + " bytes): " + cudaGetErrorString(e));
+      cudaGetLastError();
+      return e == cudaErrorMemoryAllocation ? DTB_ENOMEM : DTB_ECUDA;
+    }
+    slabs.push_back({p, cap});
+    cur = slabs.size() - 1; off = bytes;
+    *out = p;
+    return DTB_OK;
+  }
+  void trim() {
+    cudaDeviceSynchronize();
+    for (auto& sl : slabs) cudaFree(sl.p);
+    slabs.clear(); cur = 0; off = 0;
+  }
+};
+static thread_local Arena t_arena;
+
+struct ArenaScope {
+  int rc;
+  explicit ArenaScope(cudaStream_t s) { rc = t_arena.begin(s); }
+  ~ArenaScope() { t_arena.end(); }
+};
+
+// Device buffer: arena scratch by default (lives until the end of the API call), or an owned
+// stream-ordered allocation for results that outlive the call (RowIndex / offsets of a handle).
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   cudaStream_t s = nullptr;
+  bool owned = false;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   int alloc(size_t nbytes, cudaStream_t stream) {
     release();
-    s = stream; bytes = nbytes ? nbytes : 16;
+    s = stream; bytes = nbytes ? nbytes : 16; owned = false;
+    t_stats.scratch_bytes += (int64_t)bytes;
+    return t_arena.take(bytes, &p);
+  }
+  int alloc_owned(size_t nbytes, cudaStream_t stream) {
+    release();
+    s = stream; bytes = nbytes ? nbytes : 16; owned = true;
     cudaError_t e = cudaMallocAsync(&p, bytes, s);
     if (e != cudaSuccess) {
       p = nullptr;
@@ -116,10 +191,9 @@ struct DevBuf {
       cudaGetLastError();
       return e == cudaErrorMemoryAllocation ? DTB_ENOMEM : DTB_ECUDA;
     }
-    t_stats.scratch_bytes += (int64_t)bytes;
     return DTB_OK;
   }
-  void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; } }
+  void release() { if (p && owned) cudaFreeAsync(p, s); p = nullptr; }
   void* detach() { void* q = p; p = nullptr; return q; }
   template <typename T> T* as() { return reinterpret_cast<T*>(p); }
 };
@@ -249,6 +323,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
                       int32_t* offsets_dev /*optional caller buffer, n+1*/, GroupResult& res,
                       bool want_direct = false)
 {
+  // want_direct == the handle path: the RowIndex outlives the call and must be an owned allocation
   t_stats = dtb_call_stats{0, 0, 0, 0, 0};
   const double tl0 = now_ms();
   if (nkeys < 1 || nkeys > MAX_KEYS) { set_error("number of key columns must be in 1.." + std::to_string(MAX_KEYS)); return DTB_EINVAL; }
@@ -269,7 +344,11 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   res.n = n; res.nskip = 0; res.ngroups = do_groups ? 0 : -1;
 
   int32_t* order = order_dev;
-  if (!order) { DTB_TRY(res.order.alloc(sizeof(int32_t) * (size_t)n, s)); order = res.order.as<int32_t>(); }
+  if (!order) {
+    if (want_direct) DTB_TRY(res.order.alloc_owned(sizeof(int32_t) * (size_t)n, s));
+    else             DTB_TRY(res.order.alloc(sizeof(int32_t) * (size_t)n, s));
+    order = res.order.as<int32_t>();
+  }
   int32_t* offsets = offsets_dev;
   if (do_groups && !offsets) {
     DTB_TRY(res.offsets.alloc(sizeof(int32_t) * (size_t)(n + 1), s)); offsets = res.offsets.as<int32_t>();
@@ -462,7 +541,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     for (int c = 0; c < nkeys; c++) staged = staged || (in[c].buf.p != nullptr);
     const int dbits = (nrounds == 1) ? rounds[0].kp.total_bits - rounds[0].kp.group_shift : 99;
     if (want_direct && nrounds == 1 && !staged && dbits <= 22 && na_pos != DTB_NA_REMOVE) {
-      DTB_TRY(res.gkeys.alloc(sizeof(u32) * (size_t)(res.ngroups + 1), s));
+      DTB_TRY(res.gkeys.alloc_owned(sizeof(u32) * (size_t)(res.ngroups + 1), s));
       DTB_TRY(launch_group_keys(sorted_keys, last_key_bytes, offsets, rounds[0].kp.group_shift, res.ngroups,
                                 res.gkeys.as<u32>(), s));
       res.direct = true;
@@ -529,6 +608,7 @@ int dtb_set_option(const char* name, int64_t value) {
   }
   if (!strcmp(name, "verbose")) { opt_verbose = value; return DTB_OK; }
   if (!strcmp(name, "profile")) { opt_profile = value; return DTB_OK; }
+  if (!strcmp(name, "trim_scratch")) { if (t_arena.depth == 0) t_arena.trim(); return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
 }
@@ -565,6 +645,7 @@ int dtb_group(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int6
               int64_t* ngroups_out, int64_t* norder_out)
 {
   cudaStream_t s = (cudaStream_t)stream;
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   if (!order_out && nrows > 0) { set_error("order_out is NULL"); return DTB_EINVAL; }
   if (nkeys >= 1 && flags && !(flags[0] & DTB_FLAG_SORT_ONLY) && !offsets_out) {
     set_error("offsets_out is NULL but groups were requested"); return DTB_EINVAL;
@@ -600,6 +681,7 @@ int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags, int na_
   cudaStream_t s = (cudaStream_t)stream;
   if (!out) { set_error("out is NULL"); return DTB_EINVAL; }
   *out = nullptr;
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   GroupResult res;
   int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, nullptr, nullptr, res, true);
   if (rc != DTB_OK) return rc;
@@ -611,7 +693,7 @@ int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags, int na_
   if (res.ngroups >= 0) {
     // shrink the worst-case offsets buffer to ngroups+1 entries
     DevBuf exact;
-    rc = exact.alloc(sizeof(int32_t) * (size_t)(res.ngroups + 1), s);
+    rc = exact.alloc_owned(sizeof(int32_t) * (size_t)(res.ngroups + 1), s);
     if (rc != DTB_OK) { delete g; return rc; }
     cudaError_t e = cudaMemcpyAsync(exact.p, res.offsets.p, sizeof(int32_t) * (size_t)(res.ngroups + 1),
                                     cudaMemcpyDeviceToDevice, s);
@@ -643,6 +725,7 @@ int dtb_reduce(int op, dtb_col value, int64_t nrows_value, const void* order, in
                const void* offsets, int64_t ngroups, dtb_stream stream, void* out)
 {
   cudaStream_t s = (cudaStream_t)stream;
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   t_stats = dtb_call_stats{0, 0, 0, 0, 0};
   if (ngroups < 0) { set_error("ngroups must be non-negative"); return DTB_EINVAL; }
   if (!offsets) { set_error("offsets is NULL"); return DTB_EINVAL; }
@@ -691,6 +774,7 @@ int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_valu
   cudaStream_t s = (cudaStream_t)stream;
   if (!g) { set_error("groupby handle is NULL"); return DTB_EINVAL; }
   if (g->ngroups < 0) { set_error("the handle holds no Groupby (sort-only call)"); return DTB_EINVAL; }
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   const bool device_value = (op == DTB_OP_NROWS) || is_device_ptr(value.data);
   if (!g->direct || op == DTB_OP_NROWS || !device_value || nrows_value != g->nrows)
     return dtb_reduce(op, value, nrows_value, g->order, 0, g->offsets, g->ngroups, stream, out);
@@ -723,6 +807,7 @@ int dtb_gather(dtb_col src, int64_t nrows_src, const void* order, int order_is64
                dtb_stream stream, void* out)
 {
   cudaStream_t s = (cudaStream_t)stream;
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   t_stats = dtb_call_stats{0, 0, 0, 0, 0};
   const int esz = stype_bytes(src.stype);
   if (!esz) { set_error("Unable to gather Column of stype " + std::to_string(src.stype)); return DTB_ENOTIMPL; }

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(OFF_THREADS)
 group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
                      int32_t* __restrict__ offsets, u64* d_ngroups, u64* scratch /*[0]=ticket, [1..]=status*/)
 {
-  constexpr int IPT = 32 / sizeof(KeyT);
+  constexpr int IPT = FLAGS ? 32 : 128 / sizeof(KeyT);         // consecutive rows per thread (<= 32)
+  constexpr int NV = IPT * sizeof(KeyT) / 16;                   // 16-byte vector loads per thread
   constexpr int TILE = OFF_THREADS * IPT;
   constexpr int WARPS = OFF_THREADS / 32;
   __shared__ u64 s_tile;
@@ -44,9 +45,11 @@ group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
   KeyT prev = 0;
   if (p0 + IPT <= n) {
     const uint4* v = reinterpret_cast<const uint4*>(keys + p0);
-    uint4 q0 = __ldg(v), q1 = __ldg(v + 1);
-    *reinterpret_cast<uint4*>(&k[0]) = q0;
-    *reinterpret_cast<uint4*>(&k[IPT / 2]) = q1;
+    uint4 q[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) q[j] = __ldg(v + j);
+#pragma unroll
+    for (int j = 0; j < NV; j++) *reinterpret_cast<uint4*>(&k[j * (IPT / NV)]) = q[j];
   } else {
 #pragma unroll
     for (int i = 0; i < IPT; i++) k[i] = (p0 + i < n) ? keys[p0 + i] : (KeyT)0;
@@ -87,25 +90,30 @@ group_offsets_kernel(const KeyT* __restrict__ keys, int gshift, int64_t n,
       if (lane >= d) wi += o;
     }
     if (lane < WARPS) s_wsum[lane] = wi - w;
-    if (lane == WARPS - 1) {
-      // lane WARPS-1 knows the tile total: publish and look back
-      const u64 total = wi;
-      u64 excl = 0;
-      if (tile == 0) {
-        st_relaxed_u64(&status[0], OST_INCL | total);
-      } else {
-        st_relaxed_u64(&status[tile], OST_AGG | total);
-        int64_t t = tile - 1;
-        while (true) {
-          u64 sv = ld_relaxed_u64(&status[t]);
-          const u64 flag = sv & ~OST_MASK;
-          if (flag == 0) continue;
-          excl += sv & OST_MASK;
-          if (flag == OST_INCL) break;
-          --t;
-        }
-        st_relaxed_u64(&status[tile], OST_INCL | (excl + total));
-      }
+    // warp 0 resolves the tile's exclusive prefix: publish the tile total, then inspect the
+    // 32 preceding tiles per step (one status word per lane) until an inclusive prefix appears
+    const u64 total = __shfl_sync(0xffffffffu, wi, WARPS - 1);
+    if (lane == 0) st_relaxed_u64(&status[tile], (tile == 0 ? OST_INCL : OST_AGG) | total);
+    u64 excl = 0;
+    int64_t t = tile - 1;
+    while (tile > 0) {
+      const int64_t j = t - lane;
+      const u64 sv = (j >= 0) ? ld_relaxed_u64(&status[j]) : OST_INCL;
+      const u64 flag = sv & ~OST_MASK;
+      const unsigned incl_m = __ballot_sync(0xffffffffu, flag == OST_INCL);
+      const unsigned zero_m = __ballot_sync(0xffffffffu, flag == 0);
+      const int first = incl_m ? (__ffs(incl_m) - 1) : 32;
+      const unsigned relevant = (first < 31) ? ((2u << first) - 1u) : 0xffffffffu;
+      if (zero_m & relevant) continue;                         // a needed predecessor has not published yet
+      u64 c = (lane <= first) ? (sv & OST_MASK) : 0ull;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      excl += c;
+      if (first < 32) break;
+      t -= 32;
+    }
+    if (lane == 0) {
+      if (tile > 0) st_relaxed_u64(&status[tile], OST_INCL | (excl + total));
       s_prefix = excl;
       if (tile == ntiles - 1) {
         const u64 ng = excl + total;
@@ -146,8 +154,8 @@ int launch_mark_heads(const void* sorted_keys, int key_bytes, int group_shift, i
 }
 
 int64_t offsets_num_tiles(int64_t n) {
-  // the smaller tile (8-byte keys: 4 items/thread) bounds the status array
-  const int64_t tile = OFF_THREADS * 4;
+  // the smallest tile (8-byte keys: 16 rows/thread) bounds the status array
+  const int64_t tile = OFF_THREADS * 16;
   return (n + tile - 1) / tile;
 }
 
@@ -164,11 +172,11 @@ int launch_group_offsets(const void* sorted_keys, int key_bytes, int group_shift
     group_offsets_kernel<uint8_t, true><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
         (const uint8_t*)sorted_keys, 0, n, offsets_out, d_ngroups, scratch);
   } else if (key_bytes == 4) {
-    const int64_t tile = OFF_THREADS * 8;
+    const int64_t tile = OFF_THREADS * 32;
     group_offsets_kernel<u32, false><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
         (const u32*)sorted_keys, group_shift, n, offsets_out, d_ngroups, scratch);
   } else {
-    const int64_t tile = OFF_THREADS * 4;
+    const int64_t tile = OFF_THREADS * 16;
     group_offsets_kernel<u64, false><<<(unsigned)((n + tile - 1) / tile), OFF_THREADS, 0, s>>>(
         (const u64*)sorted_keys, group_shift, n, offsets_out, d_ngroups, scratch);
   }

@@ -109,7 +109,7 @@ static int run_hist_raw(const KeyPlan& kp, int64_t n, const PassPlan& pp, int nb
 {
   const KeyNorm& k = kp.k[0];
 #define DTB_CASE(T)                                                                          \
-  { RawSrc<T, KeyT> src; src.p = (const typename RawKey<T>::load_t*)k.data; src.k = k;       \
+  { RawSrc<T, KeyT> src; src.init(k);                                                        \
     return run_hist<KeyT>(src, n, pp, nbins_log2, hist, s); }
   switch (k.stype) {
     case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
@@ -195,48 +195,60 @@ struct PassArgs {
   u32*           tile_counter;
 };
 
-template <typename KeyT, typename Src, int NBINS, int THREADS, int IPT>
-__global__ void __launch_bounds__(THREADS)
-radix_pass_kernel(PassArgs<KeyT, Src> a)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// One tile.  FULL = the tile holds TILE rows (no per-row validity predicates).
+//
+// Shared memory: whist[WARPS][NBINS] u16 | bin_dst[NBINS] u32 | skey[TILE] | sidx[TILE] | ridx[TILE]
+// Registers hold only the 16 keys and their 16-bit ranks; the incoming row ids are
+// prefetched straight into shared memory with cp.async (no register staging), so the
+// kernel fits 4 CTAs = 32 warps per SM.
+template <typename KeyT, typename Src, int NBINS, int THREADS, int IPT, bool FULL>
+__device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, unsigned char* smem_raw,
+                                                u32* s_wsum, const u32 tile)
 {
   constexpr int WARPS = THREADS / 32;
   constexpr int TILE = THREADS * IPT;
-  constexpr int BPT = (NBINS + THREADS - 1) / THREADS;       // bins per thread in the scan phase
-  static_assert(NBINS % 32 == 0, "NBINS must be a multiple of the warp size");
+  static_assert(NBINS == THREADS, "one digit per thread in the scan phase");
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: whist[WARPS][NBINS] u16 | tile_start[NBINS] u32 | bin_dst[NBINS] u32 | skey[TILE] | sidx[TILE]
   unsigned short* whist = reinterpret_cast<unsigned short*>(smem_raw);
-  u32* tile_start = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
-  u32* bin_dst    = tile_start + NBINS;
-  KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);   // +4 words: scan scratch below
+  u32* bin_dst    = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
+  KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);
   int32_t* sidx   = reinterpret_cast<int32_t*>(skey + TILE);
-  u32* s_misc     = bin_dst + NBINS;                                 // [0] = ticket
-  __shared__ u32 s_wsum[32];
+  int32_t* ridx   = sidx + TILE;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if (tid == 0) s_misc[0] = atomicAdd(a.tile_counter, 1u);
-  {
-    u32* z = reinterpret_cast<u32*>(whist);
-    for (int i = tid; i < WARPS * NBINS / 2; i += THREADS) z[i] = 0;
-  }
-  __syncthreads();
-  const u32 tile = s_misc[0];
   const int64_t base = (int64_t)tile * TILE;
-  const int tile_n = (int)((a.n - base) < (int64_t)TILE ? (a.n - base) : (int64_t)TILE);
+  const int tile_n = FULL ? TILE : (int)(a.n - base);
+  const bool have_idx = a.idx_in != nullptr;
 
-  // ---- load (warp-striped: item i of lane l sits at warp_base + i*32 + l) ----
+  // ---- prefetch the incoming row ids into shared memory (consumed in the reorder phase) ----
+  if (have_idx) {
+    const int32_t* g = a.idx_in + base;
+    if (FULL) {
+#pragma unroll
+      for (int j = 0; j < IPT / 4; j++) {
+        const int c = tid + j * THREADS;                       // 16-byte chunk index
+        cp_async16(ridx + 4 * c, g + 4 * c);
+      }
+    } else {
+      for (int p = tid; p < tile_n; p += THREADS) ridx[p] = g[p];
+    }
+  }
+
+  // ---- load keys (warp-striped: item i of lane l sits at warp_base + i*32 + l) ----
   KeyT key[IPT];
-  int32_t idx[IPT];
   const int wbase = warp * 32 * IPT;
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const int lp = wbase + i * 32 + lane;
-    if (lp < tile_n) {
-      key[i] = a.src.load(base + lp);
-      idx[i] = a.idx_in ? a.idx_in[base + lp] : (int32_t)(base + lp);
-    } else { key[i] = 0; idx[i] = 0; }
+    key[i] = (FULL || lp < tile_n) ? a.src.load(base + lp) : (KeyT)0;
   }
 
   // ---- rank inside the warp: rows with equal digits keep (item, lane) order ----
@@ -245,103 +257,85 @@ radix_pass_kernel(PassArgs<KeyT, Src> a)
   const unsigned lt = lanemask_lt();
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
-    const bool valid = (wbase + i * 32 + lane) < tile_n;
+    const bool valid = FULL || (wbase + i * 32 + lane) < tile_n;
     const u32 d = valid ? ((u32)(key[i] >> a.shift) & a.mask) : (u32)NBINS;
     const unsigned peers = __match_any_sync(0xffffffffu, d);
-    const int leader = __ffs(peers) - 1;
-    unsigned short old = 0;
-    if (lane == leader && valid) { old = myhist[d]; myhist[d] = old + (unsigned short)__popc(peers); }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[i] = old + (unsigned short)__popc(peers & lt);
+    const unsigned before = peers & lt;
+    unsigned short cnt = 0;
+    if (valid) cnt = myhist[d];                                 // equal digits -> same address: broadcast
+    rank[i] = cnt + (unsigned short)__popc(before);
+    __syncwarp();                                               // all reads of this round precede the update
+    if (valid && before == 0) myhist[d] = cnt + (unsigned short)__popc(peers);
     __syncwarp();
   }
   __syncthreads();
 
-  // ---- per-digit: prefix over warps, publish tile count, scan over digits, look back ----
-  u32 cnt[BPT];
+  // ---- per digit (thread b owns digit b): prefix over warps, publish, scan over digits, look back ----
+  const int b = tid;
+  u32 run = 0;
 #pragma unroll
-  for (int j = 0; j < BPT; j++) {
-    const int b = tid * BPT + j;
-    u32 run = 0;
-    if (b < NBINS) {
-#pragma unroll
-      for (int w = 0; w < WARPS; w++) {
-        unsigned short c = whist[w * NBINS + b];
-        whist[w * NBINS + b] = (unsigned short)run;
-        run += c;
-      }
-      st_relaxed_u32(&a.status[(size_t)tile * NBINS + b],
-                     (tile == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | run);
-    }
-    cnt[j] = run;
+  for (int w = 0; w < WARPS; w++) {
+    const unsigned short c = whist[w * NBINS + b];
+    whist[w * NBINS + b] = (unsigned short)run;
+    run += c;
   }
-  {
-    // block-wide exclusive scan of the tile's digit counts (thread t owns bins t*BPT..)
-    u32 tsum = 0;
+  st_relaxed_u32(&a.status[(size_t)tile * NBINS + b], (tile == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | run);
+
+  u32 incl = run;
 #pragma unroll
-    for (int j = 0; j < BPT; j++) tsum += cnt[j];
-    u32 incl = tsum;
+  for (int d = 1; d < 32; d <<= 1) {
+    const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const u32 w = lane < WARPS ? s_wsum[lane] : 0;
+    u32 wi = w;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
+      const u32 o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += o;
     }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      u32 w = lane < WARPS ? s_wsum[lane] : 0;
-      u32 wi = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        u32 o = __shfl_up_sync(0xffffffffu, wi, d);
-        if (lane >= d) wi += o;
-      }
-      s_wsum[lane] = wi - w;
-    }
-    __syncthreads();
-    u32 excl = incl - tsum + s_wsum[warp];
-#pragma unroll
-    for (int j = 0; j < BPT; j++) {
-      const int b = tid * BPT + j;
-      if (b < NBINS) tile_start[b] = excl;
-      excl += cnt[j];
-    }
+    s_wsum[lane] = wi - w;
   }
+  __syncthreads();
+  const u32 tstart = incl - run + s_wsum[warp];                  // first slot of digit b inside the tile
 #pragma unroll
-  for (int j = 0; j < BPT; j++) {
-    const int b = tid * BPT + j;
-    if (b < NBINS) {
-      u32 prev = 0;
-      if (tile > 0) {
-        int64_t t = (int64_t)tile - 1;
-        while (true) {
-          u32 sv = ld_relaxed_u32(&a.status[(size_t)t * NBINS + b]);
-          const u32 flag = sv & ~ST_MASK;
-          if (flag == 0) continue;                  // predecessor has a ticket, hence is running
-          prev += sv & ST_MASK;
-          if (flag == ST_FLAG_INCL) break;
-          --t;
-        }
-        st_relaxed_u32(&a.status[(size_t)tile * NBINS + b], ST_FLAG_INCL | ((prev + cnt[j]) & ST_MASK));
-      }
-      bin_dst[b] = a.bin_start[b] + prev - tile_start[b];
+  for (int w = 0; w < WARPS; w++) whist[w * NBINS + b] += (unsigned short)tstart;
+
+  u32 prev = 0;
+  if (tile > 0) {
+    int64_t t = (int64_t)tile - 1;
+    while (true) {
+      const u32 sv = ld_relaxed_u32(&a.status[(size_t)t * NBINS + b]);
+      const u32 flag = sv & ~ST_MASK;
+      if (flag == 0) continue;                                   // predecessor holds a ticket, hence is running
+      prev += sv & ST_MASK;
+      if (flag == ST_FLAG_INCL) break;
+      --t;
     }
+    st_relaxed_u32(&a.status[(size_t)tile * NBINS + b], ST_FLAG_INCL | ((prev + run) & ST_MASK));
   }
+  bin_dst[b] = a.bin_start[b] + prev - tstart;
+  if (have_idx && FULL) cp_async_commit_wait_all();
   __syncthreads();
 
   // ---- reorder the tile in shared memory ----
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
-    if ((wbase + i * 32 + lane) < tile_n) {
+    const int pos = wbase + i * 32 + lane;
+    if (FULL || pos < tile_n) {
       const u32 d = (u32)(key[i] >> a.shift) & a.mask;
-      const u32 lp = tile_start[d] + myhist[d] + rank[i];
+      const u32 lp = (u32)myhist[d] + rank[i];
       skey[lp] = key[i];
-      sidx[lp] = idx[i];
+      sidx[lp] = have_idx ? ridx[pos] : (int32_t)(base + pos);
     }
   }
   __syncthreads();
 
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
+#pragma unroll 4
   for (int p = tid; p < tile_n; p += THREADS) {
     const KeyT k = skey[p];
     const u32 d = (u32)(k >> a.shift) & a.mask;
@@ -351,14 +345,37 @@ radix_pass_kernel(PassArgs<KeyT, Src> a)
   }
 }
 
+template <typename KeyT, typename Src, int NBINS, int THREADS, int IPT, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+radix_pass_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
+{
+  constexpr int TILE = THREADS * IPT;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ u32 s_wsum[32];
+  __shared__ u32 s_ticket;
+
+  if (threadIdx.x == 0) s_ticket = atomicAdd(a.tile_counter, 1u);
+  {
+    u32* z = reinterpret_cast<u32*>(smem_raw);
+    for (int i = threadIdx.x; i < (THREADS / 32) * NBINS / 2; i += THREADS) z[i] = 0;
+  }
+  __syncthreads();
+  const u32 tile = s_ticket;
+  const int64_t base = (int64_t)tile * TILE;
+  if (a.n - base >= (int64_t)TILE)
+    radix_pass_tile<KeyT, Src, NBINS, THREADS, IPT, true>(a, smem_raw, s_wsum, tile);
+  else
+    radix_pass_tile<KeyT, Src, NBINS, THREADS, IPT, false>(a, smem_raw, s_wsum, tile);
+}
+
 template <typename KeyT> struct PassCfg;
-template <> struct PassCfg<u32> { static constexpr int THREADS = 256, IPT = 16; };
-template <> struct PassCfg<u64> { static constexpr int THREADS = 256, IPT = 16; };
+template <> struct PassCfg<u32> { static constexpr int THREADS = 256, IPT = 16, MINB = 4; };
+template <> struct PassCfg<u64> { static constexpr int THREADS = 256, IPT = 16, MINB = 3; };
 
 template <typename KeyT, int NBINS>
 static constexpr size_t pass_smem_bytes() {
-  return sizeof(unsigned short) * (PassCfg<KeyT>::THREADS / 32) * NBINS + sizeof(u32) * (2 * NBINS + 4)
-       + (sizeof(KeyT) + sizeof(int32_t)) * PassCfg<KeyT>::THREADS * PassCfg<KeyT>::IPT;
+  return sizeof(unsigned short) * (PassCfg<KeyT>::THREADS / 32) * NBINS + sizeof(u32) * (NBINS + 4)
+       + (sizeof(KeyT) + 2 * sizeof(int32_t)) * PassCfg<KeyT>::THREADS * PassCfg<KeyT>::IPT;
 }
 
 int radix_pass_tile_rows(int key_bytes, int /*nbins_log2*/) {
@@ -371,15 +388,18 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits,
                     const u32* bin_start, u32* status, u32* tile_counter, cudaStream_t s)
 {
   constexpr int NBINS = 256;
-  constexpr int THREADS = PassCfg<KeyT>::THREADS, IPT = PassCfg<KeyT>::IPT;
+  constexpr int THREADS = PassCfg<KeyT>::THREADS, IPT = PassCfg<KeyT>::IPT, MINB = PassCfg<KeyT>::MINB;
   if (n == 0) return DTB_OK;
+  if (io.idx_in && (reinterpret_cast<uintptr_t>(io.idx_in) & 15)) {
+    set_error("internal: row-id buffer must be 16-byte aligned"); return DTB_EINVAL;
+  }
   PassArgs<KeyT, Src> a;
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
   a.n = n; a.shift = shift; a.mask = (1u << bits) - 1;
   a.bin_start = bin_start; a.status = status; a.tile_counter = tile_counter;
   const int64_t ntiles = (n + THREADS * IPT - 1) / (THREADS * IPT);
   constexpr size_t smem = pass_smem_bytes<KeyT, NBINS>();
-  auto kern = radix_pass_kernel<KeyT, Src, NBINS, THREADS, IPT>;
+  auto kern = radix_pass_kernel<KeyT, Src, NBINS, THREADS, IPT, MINB>;
   static bool configured = false;   // per instantiation
   if (!configured) {
     DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -397,7 +417,7 @@ static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shif
 {
   const KeyNorm& k = kp.k[0];
 #define DTB_CASE(T)                                                                          \
-  { RawSrc<T, KeyT> src; src.p = (const typename RawKey<T>::load_t*)k.data; src.k = k;       \
+  { RawSrc<T, KeyT> src; src.init(k);                                                        \
     return run_pass<KeyT>(src, io, n, shift, bits, bin_start, status, tile_counter, s); }
   switch (k.stype) {
     case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)

@@ -380,7 +380,7 @@ direct_reduce_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load_t* __
       p_add<T, CAT>(part, v[i], true, flag);
     }
     const unsigned peers = __match_any_sync(0xffffffffu, x);
-    if (peers != (1u << lane)) {
+    if (__any_sync(0xffffffffu, peers != (1u << lane))) {        // warp-uniform: the body shuffles
       // rare for spread-out keys: fold the partials of equal keys into the lowest lane
       const int leader = __ffs(peers) - 1;
       unsigned rest = peers & ~(1u << leader);

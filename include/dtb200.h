@@ -197,6 +197,7 @@ DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream st
  *   "radix_bits"   digit width of the LSD passes (default 8)
  *   "verbose"      1 = print the pass plan to stderr
  *   "profile"      1 = bracket every kernel with CUDA events on the call's stream
+ *   "trim_scratch" (set only) release the calling thread's cached HBM scratch slab
  */
 DTB_API int dtb_set_option(const char* name, int64_t value);
 DTB_API int dtb_get_option(const char* name, int64_t* value);
