@@ -252,20 +252,26 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
   }
 
   // ---- rank inside the warp: rows with equal digits keep (item, lane) order ----
+  // The lanes holding the same digit are found with a shared-memory atomicOr on a per-warp
+  // mask table, not MATCH.ANY: on sm_100 MATCH.ANY issues once per ~60 SM cycles and bound
+  // the whole kernel; the atomicOr sequence costs ~7 (scripts/ubench/match_bench.cu).
   unsigned short rank[IPT];
   unsigned short* myhist = whist + warp * NBINS;
+  u32* wmask = reinterpret_cast<u32*>(skey) + warp * NBINS;    // skey/sidx are idle until the reorder phase
   const unsigned lt = lanemask_lt();
+  const unsigned lanebit = 1u << lane;
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const bool valid = FULL || (wbase + i * 32 + lane) < tile_n;
-    const u32 d = valid ? ((u32)(key[i] >> a.shift) & a.mask) : (u32)NBINS;
-    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const u32 d = (u32)(key[i] >> a.shift) & a.mask;
+    if (valid) atomicOr(&wmask[d], lanebit);
+    __syncwarp();
+    unsigned peers = 0; unsigned short cnt = 0;
+    if (valid) { peers = wmask[d]; cnt = myhist[d]; }
     const unsigned before = peers & lt;
-    unsigned short cnt = 0;
-    if (valid) cnt = myhist[d];                                 // equal digits -> same address: broadcast
     rank[i] = cnt + (unsigned short)__popc(before);
     __syncwarp();                                               // all reads of this round precede the update
-    if (valid && before == 0) myhist[d] = cnt + (unsigned short)__popc(peers);
+    if (valid && before == 0) { myhist[d] = cnt + (unsigned short)__popc(peers); wmask[d] = 0; }
     __syncwarp();
   }
   __syncthreads();
@@ -304,16 +310,29 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
 #pragma unroll
   for (int w = 0; w < WARPS; w++) whist[w * NBINS + b] += (unsigned short)tstart;
 
+  // Decoupled look-back, LB_W predecessors per step: the loads of a window are independent, so a
+  // walk of depth D costs ~D/LB_W L2 round trips instead of D.
+  constexpr int LB_W = 4;
   u32 prev = 0;
   if (tile > 0) {
-    int64_t t = (int64_t)tile - 1;
-    while (true) {
-      const u32 sv = ld_relaxed_u32(&a.status[(size_t)t * NBINS + b]);
-      const u32 flag = sv & ~ST_MASK;
-      if (flag == 0) continue;                                   // predecessor holds a ticket, hence is running
-      prev += sv & ST_MASK;
-      if (flag == ST_FLAG_INCL) break;
-      --t;
+    const u32* sp = a.status + (size_t)tile * NBINS + b;         // sp[-j*NBINS] = tile-j
+    int64_t left = (int64_t)tile;                                 // predecessors not yet visited
+    bool done = false;
+    while (!done) {
+      u32 sv[LB_W];
+#pragma unroll
+      for (int j = 0; j < LB_W; j++)
+        sv[j] = (j < left) ? ld_relaxed_u32(sp - (size_t)(j + 1) * NBINS) : ST_FLAG_INCL;
+#pragma unroll
+      for (int j = 0; j < LB_W; j++) {
+        if (!done) {
+          u32 x = sv[j];
+          while ((x & ~ST_MASK) == 0) x = ld_relaxed_u32(sp - (size_t)(j + 1) * NBINS);   // holds a ticket: is running
+          prev += x & ST_MASK;
+          if ((x & ~ST_MASK) == ST_FLAG_INCL) done = true;
+        }
+      }
+      sp -= (size_t)LB_W * NBINS; left -= LB_W;
     }
     st_relaxed_u32(&a.status[(size_t)tile * NBINS + b], ST_FLAG_INCL | ((prev + run) & ST_MASK));
   }
@@ -356,8 +375,11 @@ radix_pass_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
 
   if (threadIdx.x == 0) s_ticket = atomicAdd(a.tile_counter, 1u);
   {
-    u32* z = reinterpret_cast<u32*>(smem_raw);
-    for (int i = threadIdx.x; i < (THREADS / 32) * NBINS / 2; i += THREADS) z[i] = 0;
+    constexpr int WARPS = THREADS / 32;
+    u32* z = reinterpret_cast<u32*>(smem_raw);                              // whist
+    for (int i = threadIdx.x; i < WARPS * NBINS / 2; i += THREADS) z[i] = 0;
+    u32* m = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS) + NBINS + 4;   // = skey
+    for (int i = threadIdx.x; i < WARPS * NBINS; i += THREADS) m[i] = 0;    // per-warp peer masks
   }
   __syncthreads();
   const u32 tile = s_ticket;
