@@ -259,6 +259,7 @@ struct GroupResult {
   int64_t ngroups = -1;
   // direct-address reducer support (small key domains, device-resident key columns)
   bool    direct = false;
+  bool    direct_hot = false;
   KeyPlan direct_kp;
   int64_t direct_table = 0;
   DevBuf  gkeys;         // uint32[ngroups]
@@ -442,6 +443,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   if (nrounds > 2) { DTB_TRY(idxR1.alloc((size_t)n * 4, s)); }
 
   DTB_TL("scratch allocated");
+  u32 h_hmax[MAX_PASSES]; int n_hmax = 0;  // largest digit count per pass (read after the final sync)
   const int32_t* idx_cur = nullptr;        // rows in the order established by the previous rounds
   void* sorted_keys = nullptr;             // last round's sorted composite keys
   int last_key_bytes = 4;
@@ -464,7 +466,12 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       ProfScope ps("histogram", s);
       DTB_TRY(launch_histograms(src_kind, keyA.p, rk, key_bytes, n, pp, nbins_log2, hist.as<u32>(), s));
     }
-    DTB_TRY(launch_scan_histograms(hist.as<u32>(), pp.npasses, nbins_log2, s));
+    DevBuf hmax; DTB_TRY(hmax.alloc(sizeof(u32) * MAX_PASSES, s));
+    DTB_TRY(launch_scan_histograms(hist.as<u32>(), pp.npasses, nbins_log2, hmax.as<u32>(), s));
+    if (want_direct && nrounds == 1) {
+      DTB_CUDA_CHECK(cudaMemcpyAsync(h_hmax, hmax.p, sizeof(u32) * pp.npasses, cudaMemcpyDeviceToHost, s));
+      n_hmax = pp.npasses;
+    }
 
     // look-back state for all passes of the round, zeroed once
     const int64_t tile_rows = radix_pass_tile_rows(key_bytes, nbins_log2);
@@ -545,6 +552,10 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       DTB_TRY(launch_group_keys(sorted_keys, last_key_bytes, offsets, rounds[0].kp.group_shift, res.ngroups,
                                 res.gkeys.as<u32>(), s));
       res.direct = true;
+      // a key owning a share f of the rows puts >= f*n rows into one bin of EVERY digit histogram
+      u32 least = 0xffffffffu;
+      for (int p = 0; p < n_hmax; p++) least = h_hmax[p] < least ? h_hmax[p] : least;
+      res.direct_hot = n_hmax > 0 && (double)least > 0.02 * (double)n;
       res.direct_kp = rounds[0].kp;
       res.direct_table = (int64_t)1 << dbits;
     }
@@ -570,6 +581,7 @@ struct dtb_groupby {
   int64_t nrows = 0;
   // direct-address reducers: valid while the caller keeps the key columns alive and unchanged
   bool direct = false;
+  bool hot = false;
   dtb::KeyPlan kp;
   int64_t table = 0;
   void* gkeys = nullptr;      // device uint32[ngroups]
@@ -689,7 +701,7 @@ int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags, int na_
   g->norder = res.n - res.nskip;
   g->ngroups = res.ngroups;
   g->nrows = res.n;
-  if (res.direct) { g->direct = true; g->kp = res.direct_kp; g->table = res.direct_table; g->gkeys = res.gkeys.detach(); }
+  if (res.direct) { g->direct = true; g->hot = res.direct_hot; g->kp = res.direct_kp; g->table = res.direct_table; g->gkeys = res.gkeys.detach(); }
   if (res.ngroups >= 0) {
     // shrink the worst-case offsets buffer to ngroups+1 entries
     DevBuf exact;
@@ -791,7 +803,7 @@ int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_valu
   DevBuf acc; DTB_TRY(acc.alloc(sizeof(u64) * (size_t)g->table * 2, s));
   {
     ProfScope ps("reduce_direct", s);
-    DTB_TRY(launch_reduce_direct(op, g->kp, value.data, value.stype, g->nrows, g->table,
+    DTB_TRY(launch_reduce_direct(op, g->kp, g->hot, value.data, value.stype, g->nrows, g->table,
                                  (const uint32_t*)g->gkeys, g->ngroups, acc.as<u64>(),
                                  acc.as<u64>() + g->table, d_out.dptr, s));
   }

@@ -95,8 +95,8 @@ int launch_histograms(int src_kind, const void* packed, const KeyPlan& kp, int k
                       int64_t n, const PassPlan& pp, int nbins_log2, uint32_t* hist,
                       cudaStream_t s);
 
-// Exclusive scan of each pass' histogram in place.
-int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, cudaStream_t s);
+// Exclusive scan of each pass' histogram in place; hmax[p] (optional) = largest digit count of pass p.
+int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, uint32_t* hmax, cudaStream_t s);
 
 struct PassIO {
   int         src_kind;     // 0 packed keys + idx_in (idx_in NULL = identity), 1 raw column (identity idx)
@@ -141,7 +141,8 @@ int launch_reduce_impl(int op, const void* value, int stype, int64_t nrows_value
 int reduce_out_stype_host(int op, int stype);
 
 // Direct-address reducers over a small normalised key domain (see dtb_reduce.cu).
-int launch_reduce_direct(int op, const KeyPlan& kp, const void* value, int stype, int64_t n,
+// hot_keys: some key may own a large share of the rows -> combine equal keys inside a warp first.
+int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* value, int stype, int64_t n,
                          int64_t table, const uint32_t* gkeys, int64_t ngroups,
                          unsigned long long* acc0, unsigned long long* acc1, void* out, cudaStream_t s);
 int launch_group_keys(const void* sorted_keys, int key_bytes, const int32_t* offsets, int group_shift,

@@ -135,13 +135,26 @@ int launch_histograms(int src_kind, const void* packed, const KeyPlan& kp, int k
 }
 
 // Exclusive scan of each pass' NBINS counters (one block per pass).
-__global__ void scan_hist_kernel(u32* hist, int nbins)
+__global__ void scan_hist_kernel(u32* hist, int nbins, u32* hmax)
 {
   __shared__ u32 wsum[32];
+  __shared__ u32 wmax[32];
   u32* h = hist + (size_t)blockIdx.x * nbins;
   // nbins <= 1024 = blockDim.x
   const int t = threadIdx.x;
   u32 v = t < nbins ? h[t] : 0;
+  {
+    // largest digit count of this pass (skew detector for the direct-address reducers)
+    u32 m = v;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const u32 o = __shfl_xor_sync(0xffffffffu, m, d); m = o > m ? o : m; }
+    if ((t & 31) == 0) wmax[t >> 5] = m;
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = wmax[w] > m ? wmax[w] : m;
+      if (hmax) hmax[blockIdx.x] = m;
+    }
+  }
   u32 incl = v;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -164,11 +177,11 @@ __global__ void scan_hist_kernel(u32* hist, int nbins)
   if (t < nbins) h[t] = incl - v + wsum[t >> 5];
 }
 
-int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, cudaStream_t s)
+int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, uint32_t* hmax, cudaStream_t s)
 {
   const int nbins = 1 << nbins_log2;
   int threads = nbins < 32 ? 32 : nbins;
-  scan_hist_kernel<<<npasses, threads, 0, s>>>(hist, nbins);
+  scan_hist_kernel<<<npasses, threads, 0, s>>>(hist, nbins, hmax);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;

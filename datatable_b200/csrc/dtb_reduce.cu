@@ -363,7 +363,7 @@ int reduce_out_stype_host(int op, int st) { return reduce_out_stype(op, st); }
 //
 // Bound: L2 atomic throughput (measured 170 G atomics/s on B200), then HBM.
 // Algorithmic bytes per row: key column(s) + value column, read once.
-template <typename T, int CAT, typename KSrc>
+template <typename T, int CAT, typename KSrc, bool HOT>
 __global__ void __launch_bounds__(512)
 direct_reduce_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load_t* __restrict__ v,
                      int64_t n, u64* acc0, u64* acc1, int flag)
@@ -379,8 +379,11 @@ direct_reduce_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load_t* __
       x = (u32)(ksrc.load(i) >> gshift);
       p_add<T, CAT>(part, v[i], true, flag);
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, x);
-    if (__any_sync(0xffffffffu, peers != (1u << lane))) {        // warp-uniform: the body shuffles
+    // HOT: a key may own a large share of the rows (skewed digit histograms): fold equal keys of the
+    // warp before touching L2.  MATCH.ANY is slow on sm_100 (~60 SM cycles per warp), so the
+    // common spread-out case skips it entirely.
+    const unsigned peers = HOT ? __match_any_sync(0xffffffffu, x) : (1u << lane);
+    if (HOT && __any_sync(0xffffffffu, peers != (1u << lane))) {  // warp-uniform: the body shuffles
       // rare for spread-out keys: fold the partials of equal keys into the lowest lane
       const int leader = __ffs(peers) - 1;
       unsigned rest = peers & ~(1u << leader);
@@ -437,11 +440,8 @@ __global__ void finalize_direct_kernel(int op, int in_stype, int out_stype, cons
 // key sources: one raw column normalised on the fly, or the general multi-column composite
 template <typename TK>
 struct DirectRawKey {
-  const typename RawKey<TK>::load_t* p; KeyNorm k;
-  __device__ __forceinline__ u64 load(int64_t i) const {
-    u64 u; bool valid = RawKey<TK>::get(p[i], u);
-    return norm_apply(valid, u, k);
-  }
+  RawSrc<TK, u32> src;                       // the direct path only exists for keys of <= 22 bits
+  __device__ __forceinline__ u64 load(int64_t i) const { return (u64)src.load(i); }
 };
 struct DirectComposite {
   KeyPlan kp;
@@ -452,6 +452,8 @@ struct DirectComposite {
   }
 };
 
+static thread_local bool t_direct_hot = false;
+
 template <typename T, int CAT, typename KSrc>
 static int run_direct(const KSrc& ks, int gshift, const void* v, int64_t n, u64* acc0, u64* acc1, int flag,
                       cudaStream_t s)
@@ -459,7 +461,10 @@ static int run_direct(const KSrc& ks, int gshift, const void* v, int64_t n, u64*
   typedef typename RawKey<T>::load_t L;
   int64_t want = (n + 511) / 512;
   int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
-  direct_reduce_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag);
+  if (t_direct_hot)
+    direct_reduce_kernel<T, CAT, KSrc, true><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag);
+  else
+    direct_reduce_kernel<T, CAT, KSrc, false><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
@@ -505,10 +510,11 @@ static int direct_op(int op, int st, const KSrc& ks, int gshift, const void* v, 
 }
 
 // acc0/acc1: device scratch of `table` u64 each; gkeys: uint32[ng] group key of every group.
-int launch_reduce_direct(int op, const KeyPlan& kp, const void* value, int stype, int64_t n,
+int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* value, int stype, int64_t n,
                          int64_t table, const uint32_t* gkeys, int64_t ng, u64* acc0, u64* acc1,
                          void* out, cudaStream_t s)
 {
+  t_direct_hot = hot_keys;
   const int out_st = reduce_out_stype(op, stype);
   if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
   if (ng == 0) return DTB_OK;
@@ -521,7 +527,7 @@ int launch_reduce_direct(int op, const KeyPlan& kp, const void* value, int stype
     int rc;
     if (kp.nkeys == 1) {
       const KeyNorm& k = kp.k[0];
-#define DTB_CASE(TK) { DirectRawKey<TK> ks; ks.p = (const typename RawKey<TK>::load_t*)k.data; ks.k = k; \
+#define DTB_CASE(TK) { DirectRawKey<TK> ks; ks.src.init(k); \
                        rc = direct_op(op, stype, ks, kp.group_shift, value, n, acc0, acc1, s); break; }
       switch (k.stype) {
         case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
