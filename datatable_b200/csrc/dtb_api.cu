@@ -423,7 +423,6 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   for (auto& r : rounds) if (r.kp.total_bits > max_bits) max_bits = r.kp.total_bits;
   const int buf_key_bytes = max_bits <= 32 ? 4 : 8;
   const int nbins_log2 = 8;
-  const int nbins = 1 << nbins_log2;
   int width = (int)opt_radix_bits; if (width < 1) width = 1; if (width > nbins_log2) width = nbins_log2;
 
   if (opt_verbose) {
@@ -460,26 +459,9 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       DTB_TRY(launch_compose_keys(rk, n, idx_cur, keyA.p, key_bytes, s)); src_kind = 0;
     }
 
-    // histograms -> global digit offsets
-    DevBuf hist; DTB_TRY(hist.alloc(sizeof(u32) * pp.npasses * nbins, s));
-    {
-      ProfScope ps("histogram", s);
-      DTB_TRY(launch_histograms(src_kind, keyA.p, rk, key_bytes, n, pp, nbins_log2, hist.as<u32>(), s));
-    }
+    // per-pass scratch: chunk x digit counts + digit totals/bases; largest digit count per pass
+    DevBuf work; DTB_TRY(work.alloc(radix_pass_work_bytes(n), s));
     DevBuf hmax; DTB_TRY(hmax.alloc(sizeof(u32) * MAX_PASSES, s));
-    DTB_TRY(launch_scan_histograms(hist.as<u32>(), pp.npasses, nbins_log2, hmax.as<u32>(), s));
-    if (want_direct && nrounds == 1) {
-      DTB_CUDA_CHECK(cudaMemcpyAsync(h_hmax, hmax.p, sizeof(u32) * pp.npasses, cudaMemcpyDeviceToHost, s));
-      n_hmax = pp.npasses;
-    }
-
-    // look-back state for all passes of the round, zeroed once
-    const int64_t tile_rows = radix_pass_tile_rows(key_bytes, nbins_log2);
-    const int64_t ntiles = (n + tile_rows - 1) / tile_rows;
-    const size_t status_words = (size_t)ntiles * nbins;
-    DevBuf status; DTB_TRY(status.alloc(sizeof(u32) * (status_words * pp.npasses + pp.npasses), s));
-    DTB_CUDA_CHECK(cudaMemsetAsync(status.p, 0, status.bytes, s));
-    u32* counters = status.as<u32>() + status_words * pp.npasses;
 
     int32_t* round_out = last_round ? order : ((ri & 1) ? idxR1.as<int32_t>() : idxR0.as<int32_t>());
     const bool want_sorted_keys = last_round && do_groups && rounds[ri].has_by;
@@ -496,14 +478,17 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       io.idx_out = iout;
       {
         ProfScope ps("radix_pass", s);
-        DTB_TRY(launch_radix_pass(io, rk, key_bytes, n, pp.shift[p], pp.bits[p], nbins_log2,
-                                  hist.as<u32>() + (size_t)p * nbins,
-                                  status.as<u32>() + status_words * p, counters + p, s));
+        DTB_TRY(launch_radix_pass(io, rk, key_bytes, n, pp.shift[p], pp.bits[p], work.as<u32>(),
+                                  hmax.as<u32>() + p, s));
       }
       if (last && want_sorted_keys) { sorted_keys = kout; last_key_bytes = key_bytes; }
       kin = kout;
       kout = (kout == keyA.p) ? keyB.p : keyA.p;
       iin = iout;
+    }
+    if (want_direct && nrounds == 1) {
+      DTB_CUDA_CHECK(cudaMemcpyAsync(h_hmax, hmax.p, sizeof(u32) * pp.npasses, cudaMemcpyDeviceToHost, s));
+      n_hmax = pp.npasses;
     }
     idx_cur = round_out;
   }

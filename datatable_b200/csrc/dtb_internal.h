@@ -87,17 +87,6 @@ struct PassPlan {
 int launch_compose_keys(const KeyPlan& kp, int64_t n, const int32_t* idx, void* keys_out,
                         int key_bytes, cudaStream_t s);
 
-// Digit histograms of every pass in one read of the key source.
-//   src_kind 0: packed composite keys (key_bytes 4 or 8) at `packed`
-//   src_kind 1: raw single column described by kp.k[0]
-// hist: uint32[npasses][nbins] (zeroed by the callee).
-int launch_histograms(int src_kind, const void* packed, const KeyPlan& kp, int key_bytes,
-                      int64_t n, const PassPlan& pp, int nbins_log2, uint32_t* hist,
-                      cudaStream_t s);
-
-// Exclusive scan of each pass' histogram in place; hmax[p] (optional) = largest digit count of pass p.
-int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, uint32_t* hmax, cudaStream_t s);
-
 struct PassIO {
   int         src_kind;     // 0 packed keys + idx_in (idx_in NULL = identity), 1 raw column (identity idx)
   const void* keys_in;      // packed keys (src_kind 0)
@@ -106,14 +95,11 @@ struct PassIO {
   int32_t*    idx_out;
 };
 
-int radix_pass_tile_rows(int key_bytes, int nbins_log2);
-
-// One stable scatter pass.  status: uint32[ntiles * nbins] zeroed by the caller;
-// tile_counter: uint32 zeroed by the caller.
+// One stable pass = count + scan + scatter kernels.  work: radix_pass_work_bytes(n) of scratch;
+// hmax (optional, device): receives the largest digit count of the pass.
+size_t radix_pass_work_bytes(int64_t n);
 int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
-                      int shift, int bits, int nbins_log2,
-                      const uint32_t* bin_start, uint32_t* status, uint32_t* tile_counter,
-                      cudaStream_t s);
+                      int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // Group offsets (replaces GroupGatherer, sort_groups.cc:34-117): heads where

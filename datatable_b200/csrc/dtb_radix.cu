@@ -3,21 +3,29 @@
 // Replaces SortContext::build_histogram / reorder_data / radix_psort /
 // _radix_recurse (sort.cc:950-1353).  The reference is an MSD recursion over
 // a chunk x radix size_t histogram with insertion-sort leaves -- a CPU idiom.
-// Here every pass is ONE kernel that reads each (key, row) pair once and
-// writes it once ("single sweep"): tiles take ticket numbers from an atomic
-// counter, rank their rows with warp match/ballot histogramming in shared
-// memory, publish per-digit tile counts and resolve the global digit offsets
-// with a decoupled look-back over earlier tiles' status words.  Stability
-// (ties keep ascending row index, sort.cc:27-33) follows from ranking rows in
-// (item, lane) = position order inside a tile and tiles in ticket order.
+// Here every digit is one pass of three kernels:
 //
-// Key normalisation (sort.cc:690-845) is evaluated on the fly in the first
-// pass and in the histogram kernel: no separate `x` array is materialised for
-// single-column keys.
+//   count   : every CTA owns a contiguous CHUNK of 65536 rows and counts its digits
+//             (shared-memory histogram) -> counts[chunk][digit]
+//   scan    : per digit, exclusive prefix over the chunks; exclusive prefix over the digit
+//             totals -> every (chunk, digit) knows its first output slot
+//   scatter : the CTA walks its chunk tile by tile (4096 rows), ranks the rows of a tile with
+//             warp-level peer masks in shared memory, reorders the tile in shared memory and
+//             writes digit runs out coalesced, keeping the running digit offsets in registers.
 //
-// Bound: HBM.  Algorithmic bytes per row per pass = read (key + idx) + write
-// (key + idx); first pass reads the raw column only, last pass of a sort-only
-// call writes idx only.
+// No look-back, no status words, no spinning: a first version used single-sweep tiles with
+// a decoupled look-back; with ~600 tiles in flight the look-back walk was 40 % of the stall
+// samples and 31 % of the instructions of the pass (profiles/r1_ncu_summary.md).  The price
+// is one extra read of the keys per pass (K of 2(K+4) bytes per row).
+//
+// Stability (ties keep ascending row index, sort.cc:27-33): chunks and tiles are in row
+// order and rows of a tile are ranked in (item, lane) = position order.
+//
+// Key normalisation (sort.cc:690-845) is evaluated on the fly in the first pass (count and
+// scatter): no separate `x` array is materialised for single-column keys.
+//
+// Bound: HBM.  Algorithmic bytes per row per pass = read (key + idx) + write (key + idx);
+// first pass reads the raw column only, last pass of a sort-only call writes idx only.
 #include "dtb_common.cuh"
 
 namespace dtb {
@@ -53,147 +61,113 @@ int launch_compose_keys(const KeyPlan& kp, int64_t n, const int32_t* idx, void* 
 }
 
 // ===========================================================================
-// Digit histograms for all passes (one read of the key source)
+// Pass geometry
 // ===========================================================================
-struct HistPlan {
-  int npasses;
-  int shift[MAX_PASSES];
-  u32 mask[MAX_PASSES];
-};
+constexpr int PASS_NBINS = 256;              // digits are at most 8 bits wide
+constexpr int PASS_THREADS = 256;
+constexpr int PASS_IPT = 16;
+constexpr int PASS_TILE = PASS_THREADS * PASS_IPT;            // 4096 rows
+constexpr int CHUNK_TILES = 16;
+constexpr int CHUNK_ROWS = PASS_TILE * CHUNK_TILES;           // 65536 rows per CTA
 
-template <typename KeyT, typename Src, int NBINS>
-__global__ void __launch_bounds__(512)
-histogram_kernel(Src src, int64_t n, HistPlan hp, u32* __restrict__ ghist)
-{
-  extern __shared__ u32 shist[];            // [npasses][NBINS]
-  const int nwords = hp.npasses * NBINS;
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x) shist[i] = 0;
-  __syncthreads();
+int64_t radix_num_chunks(int64_t n) { return (n + CHUNK_ROWS - 1) / CHUNK_ROWS; }
 
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    KeyT x = src.load(i);
-    for (int p = 0; p < hp.npasses; p++) {
-      u32 d = (u32)(x >> hp.shift[p]) & hp.mask[p];
-      atomicAdd(&shist[p * NBINS + d], 1u);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-    u32 c = shist[i];
-    if (c) atomicAdd(&ghist[i], c);
-  }
-}
-
+// ===========================================================================
+// count: counts[chunk][digit]
+// ===========================================================================
 template <typename KeyT, typename Src>
-static int run_hist(Src src, int64_t n, const PassPlan& pp, int nbins_log2, u32* hist, cudaStream_t s)
+__global__ void __launch_bounds__(PASS_THREADS)
+count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u32* __restrict__ counts,
+             unsigned short* __restrict__ tile_counts)
 {
-  HistPlan hp; hp.npasses = pp.npasses;
-  for (int p = 0; p < pp.npasses; p++) { hp.shift[p] = pp.shift[p]; hp.mask[p] = (1u << pp.bits[p]) - 1; }
-  const int nbins = 1 << nbins_log2;
-  DTB_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(u32) * pp.npasses * nbins, s));
-  if (n == 0) return DTB_OK;
-  int64_t want = (n + 512 * 16 - 1) / (512 * 16);
-  int grid = (int)(want < 1 ? 1 : (want > NUM_SMS_B200 * 4 ? NUM_SMS_B200 * 4 : want));
-  size_t smem = sizeof(u32) * pp.npasses * nbins;
-  if (nbins_log2 != 8) { set_error("internal: only 8-bit digit kernels are built"); return DTB_EINVAL; }
-  histogram_kernel<KeyT, Src, 256><<<grid, 512, smem, s>>>(src, n, hp, hist);
-  count_launch();
-  DTB_CUDA_CHECK(cudaGetLastError());
-  return DTB_OK;
-}
-
-template <typename KeyT>
-static int run_hist_raw(const KeyPlan& kp, int64_t n, const PassPlan& pp, int nbins_log2, u32* hist,
-                        cudaStream_t s)
-{
-  const KeyNorm& k = kp.k[0];
-#define DTB_CASE(T)                                                                          \
-  { RawSrc<T, KeyT> src; src.init(k);                                                        \
-    return run_hist<KeyT>(src, n, pp, nbins_log2, hist, s); }
-  switch (k.stype) {
-    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
-    case DTB_STYPE_INT16:                        DTB_CASE(int16_t)
-    case DTB_STYPE_INT32: case DTB_STYPE_DATE32: DTB_CASE(int32_t)
-    case DTB_STYPE_INT64: case DTB_STYPE_TIME64: DTB_CASE(int64_t)
-    case DTB_STYPE_FLOAT32:                      DTB_CASE(float)
-    case DTB_STYPE_FLOAT64:                      DTB_CASE(double)
-  }
-#undef DTB_CASE
-  set_error("internal: bad stype in histogram"); return DTB_EINVAL;
-}
-
-int launch_histograms(int src_kind, const void* packed, const KeyPlan& kp, int key_bytes,
-                      int64_t n, const PassPlan& pp, int nbins_log2, uint32_t* hist, cudaStream_t s)
-{
-  if (src_kind == 0) {
-    if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)packed}; return run_hist<u32>(src, n, pp, nbins_log2, hist, s); }
-    else                { PackedSrc<u64> src{(const u64*)packed}; return run_hist<u64>(src, n, pp, nbins_log2, hist, s); }
-  }
-  return key_bytes == 4 ? run_hist_raw<u32>(kp, n, pp, nbins_log2, hist, s)
-                        : run_hist_raw<u64>(kp, n, pp, nbins_log2, hist, s);
-}
-
-// Exclusive scan of each pass' NBINS counters (one block per pass).
-__global__ void scan_hist_kernel(u32* hist, int nbins, u32* hmax)
-{
-  __shared__ u32 wsum[32];
-  __shared__ u32 wmax[32];
-  u32* h = hist + (size_t)blockIdx.x * nbins;
-  // nbins <= 1024 = blockDim.x
-  const int t = threadIdx.x;
-  u32 v = t < nbins ? h[t] : 0;
-  {
-    // largest digit count of this pass (skew detector for the direct-address reducers)
-    u32 m = v;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { const u32 o = __shfl_xor_sync(0xffffffffu, m, d); m = o > m ? o : m; }
-    if ((t & 31) == 0) wmax[t >> 5] = m;
+  __shared__ u32 h[PASS_NBINS];
+  const int64_t cbase = (int64_t)blockIdx.x * CHUNK_ROWS;
+  const int64_t cend = (cbase + CHUNK_ROWS < n) ? cbase + CHUNK_ROWS : n;
+  u32 total = 0;                                           // thread b: rows of digit b in this chunk
+  for (int64_t base = cbase; base < cend; base += PASS_TILE) {
+    h[threadIdx.x] = 0;
     __syncthreads();
-    if (t == 0) {
-      for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = wmax[w] > m ? wmax[w] : m;
-      if (hmax) hmax[blockIdx.x] = m;
-    }
-  }
-  u32 incl = v;
+    const int64_t end = (base + PASS_TILE < cend) ? base + PASS_TILE : cend;
+    if (end - base == PASS_TILE) {
+      // coalesced: consecutive threads read consecutive rows; 16 independent loads in flight per thread
+      KeyT k[PASS_IPT];
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    u32 o = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((t & 31) >= d) incl += o;
-  }
-  if ((t & 31) == 31) wsum[t >> 5] = incl;
-  __syncthreads();
-  if (t < 32) {
-    u32 w = t < (blockDim.x >> 5) ? wsum[t] : 0;
-    u32 wi = w;
+      for (int j = 0; j < PASS_IPT; j++) k[j] = src.load(base + threadIdx.x + j * PASS_THREADS);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      u32 o = __shfl_up_sync(0xffffffffu, wi, d);
-      if (t >= d) wi += o;
+      for (int j = 0; j < PASS_IPT; j++) atomicAdd(&h[(u32)(k[j] >> shift) & mask], 1u);
+    } else {
+      for (int64_t i = base + threadIdx.x; i < end; i += PASS_THREADS)
+        atomicAdd(&h[(u32)(src.load(i) >> shift) & mask], 1u);
     }
-    wsum[t] = wi - w;
+    __syncthreads();
+    const u32 c = h[threadIdx.x];
+    tile_counts[(size_t)(base / PASS_TILE) * PASS_NBINS + threadIdx.x] = (unsigned short)c;   // <= 4096
+    total += c;
   }
-  __syncthreads();
-  if (t < nbins) h[t] = incl - v + wsum[t >> 5];
+  counts[(size_t)blockIdx.x * PASS_NBINS + threadIdx.x] = total;
 }
 
-int launch_scan_histograms(uint32_t* hist, int npasses, int nbins_log2, uint32_t* hmax, cudaStream_t s)
+// ===========================================================================
+// scan: offs[chunk][digit] = sum over earlier chunks (in place); total[digit]
+// then base[digit] = exclusive scan of total[]; hmax = largest total (skew detector)
+// ===========================================================================
+__global__ void __launch_bounds__(256)
+chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, u32* __restrict__ total)
 {
-  const int nbins = 1 << nbins_log2;
-  int threads = nbins < 32 ? 32 : nbins;
-  scan_hist_kernel<<<npasses, threads, 0, s>>>(hist, nbins, hmax);
-  count_launch();
-  DTB_CUDA_CHECK(cudaGetLastError());
-  return DTB_OK;
+  __shared__ u32 wsum[8];
+  __shared__ u32 s_carry;
+  const int d = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t c0 = 0; c0 < nchunks; c0 += 256) {
+    const int64_t c = c0 + t;
+    const u32 v = (c < nchunks) ? counts[(size_t)c * PASS_NBINS + d] : 0;
+    u32 incl = v;
+#pragma unroll
+    for (int k = 1; k < 32; k <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += o; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    u32 wpre = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) if (w < warp) wpre += wsum[w];
+    const u32 carry = s_carry;
+    if (c < nchunks) counts[(size_t)c * PASS_NBINS + d] = carry + wpre + incl - v;
+    __syncthreads();
+    if (t == 255) s_carry = carry + wpre + incl;
+    __syncthreads();
+  }
+  if (t == 0) total[d] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+digit_base_kernel(const u32* __restrict__ total, u32* __restrict__ base, u32* __restrict__ hmax)
+{
+  __shared__ u32 wsum[8];
+  __shared__ u32 wmax[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const u32 v = total[t];
+  u32 incl = v, m = v;
+#pragma unroll
+  for (int k = 1; k < 32; k <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += o; }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) { const u32 o = __shfl_xor_sync(0xffffffffu, m, k); m = o > m ? o : m; }
+  if (lane == 31) wsum[warp] = incl;
+  if (lane == 0) wmax[warp] = m;
+  __syncthreads();
+  u32 wpre = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) if (w < warp) wpre += wsum[w];
+  base[t] = wpre + incl - v;
+  if (t == 0 && hmax) {
+    u32 mm = 0;
+    for (int w = 0; w < 8; w++) mm = wmax[w] > mm ? wmax[w] : mm;
+    *hmax = mm;
+  }
 }
 
 // ===========================================================================
-// The single-sweep scatter pass
+// scatter
 // ===========================================================================
-constexpr u32 ST_FLAG_AGG  = 1u << 30;     // tile count published
-constexpr u32 ST_FLAG_INCL = 2u << 30;     // inclusive prefix published
-constexpr u32 ST_MASK      = (1u << 30) - 1;
-
 template <typename KeyT, typename Src>
 struct PassArgs {
   Src            src;
@@ -203,55 +177,54 @@ struct PassArgs {
   int64_t        n;
   int            shift;
   u32            mask;
-  const u32*     bin_start;     // [NBINS] global exclusive digit offsets
-  u32*           status;        // [ntiles][NBINS]
-  u32*           tile_counter;
+  const u32*     chunk_offs;    // [nchunks][NBINS] rows of this digit in earlier chunks
+  const u32*     digit_base;    // [NBINS] first output slot of every digit
+  const unsigned short* tile_counts;   // [ntiles][NBINS] rows of this digit in every tile
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// One tile.  FULL = the tile holds TILE rows (no per-row validity predicates).
-//
 // Shared memory: whist[WARPS][NBINS] u16 | bin_dst[NBINS] u32 | skey[TILE] | sidx[TILE] | ridx[TILE]
-// Registers hold only the 16 keys and their 16-bit ranks; the incoming row ids are
-// prefetched straight into shared memory with cp.async (no register staging), so the
-// kernel fits 4 CTAs = 32 warps per SM.
-template <typename KeyT, typename Src, int NBINS, int THREADS, int IPT, bool FULL>
-__device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, unsigned char* smem_raw,
-                                                u32* s_wsum, const u32 tile)
+// (the per-warp peer-mask table of the rank phase aliases skey, idle until the reorder phase).
+// Registers hold the 16 keys of the thread, their 16-bit ranks and the running output offset of
+// the thread's digit; 64 registers / 53 KB -> 4 CTAs = 32 warps per SM.
+template <typename KeyT, typename Src, bool FULL>
+__device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsigned char* smem_raw, u32* s_wsum,
+                                             const int64_t base, const int tile_n, const bool prefetched)
 {
+  constexpr int NBINS = PASS_NBINS, THREADS = PASS_THREADS, IPT = PASS_IPT, TILE = PASS_TILE;
   constexpr int WARPS = THREADS / 32;
-  constexpr int TILE = THREADS * IPT;
-  static_assert(NBINS == THREADS, "one digit per thread in the scan phase");
-
   unsigned short* whist = reinterpret_cast<unsigned short*>(smem_raw);
   u32* bin_dst    = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
   KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);
   int32_t* sidx   = reinterpret_cast<int32_t*>(skey + TILE);
   int32_t* ridx   = sidx + TILE;
+  u32* wmask_all  = reinterpret_cast<u32*>(skey);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t base = (int64_t)tile * TILE;
-  const int tile_n = FULL ? TILE : (int)(a.n - base);
   const bool have_idx = a.idx_in != nullptr;
 
-  // ---- prefetch the incoming row ids into shared memory (consumed in the reorder phase) ----
-  if (have_idx) {
-    const int32_t* g = a.idx_in + base;
-    if (FULL) {
+  // ---- clear the per-warp digit counters and peer masks; fetch the row ids of a partial tile ----
+  {
+    u32* z = reinterpret_cast<u32*>(whist);
 #pragma unroll
-      for (int j = 0; j < IPT / 4; j++) {
-        const int c = tid + j * THREADS;                       // 16-byte chunk index
-        cp_async16(ridx + 4 * c, g + 4 * c);
+    for (int j = 0; j < WARPS * NBINS / 2 / THREADS; j++) z[tid + j * THREADS] = 0;
+#pragma unroll
+    for (int j = 0; j < WARPS * NBINS / THREADS; j++) wmask_all[tid + j * THREADS] = 0;
+    if (have_idx && !prefetched) {
+      const int32_t* g = a.idx_in + base;
+      if (FULL) {
+#pragma unroll
+        for (int j = 0; j < IPT / 4; j++) { const int c = tid + j * THREADS; cp_async16(ridx + 4 * c, g + 4 * c); }
+        cp_async_commit();
+      } else {
+        for (int p = tid; p < tile_n; p += THREADS) ridx[p] = g[p];
       }
-    } else {
-      for (int p = tid; p < tile_n; p += THREADS) ridx[p] = g[p];
     }
   }
 
@@ -263,14 +236,15 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
     const int lp = wbase + i * 32 + lane;
     key[i] = (FULL || lp < tile_n) ? a.src.load(base + lp) : (KeyT)0;
   }
+  __syncthreads();
 
   // ---- rank inside the warp: rows with equal digits keep (item, lane) order ----
   // The lanes holding the same digit are found with a shared-memory atomicOr on a per-warp
   // mask table, not MATCH.ANY: on sm_100 MATCH.ANY issues once per ~60 SM cycles and bound
   // the whole kernel; the atomicOr sequence costs ~7 (scripts/ubench/match_bench.cu).
-  unsigned short rank[IPT];
+  u32 rank2[IPT / 2];                                         // two 16-bit ranks per register
   unsigned short* myhist = whist + warp * NBINS;
-  u32* wmask = reinterpret_cast<u32*>(skey) + warp * NBINS;    // skey/sidx are idle until the reorder phase
+  u32* wmask = wmask_all + warp * NBINS;
   const unsigned lt = lanemask_lt();
   const unsigned lanebit = 1u << lane;
 #pragma unroll
@@ -282,14 +256,15 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
     unsigned peers = 0; unsigned short cnt = 0;
     if (valid) { peers = wmask[d]; cnt = myhist[d]; }
     const unsigned before = peers & lt;
-    rank[i] = cnt + (unsigned short)__popc(before);
+    const u32 r = (u32)cnt + (u32)__popc(before);
+    if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
     __syncwarp();                                               // all reads of this round precede the update
     if (valid && before == 0) { myhist[d] = cnt + (unsigned short)__popc(peers); wmask[d] = 0; }
     __syncwarp();
   }
   __syncthreads();
 
-  // ---- per digit (thread b owns digit b): prefix over warps, publish, scan over digits, look back ----
+  // ---- per digit (thread b owns digit b): prefix over warps, scan over digits, output offsets ----
   const int b = tid;
   u32 run = 0;
 #pragma unroll
@@ -298,8 +273,6 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
     whist[w * NBINS + b] = (unsigned short)run;
     run += c;
   }
-  st_relaxed_u32(&a.status[(size_t)tile * NBINS + b], (tile == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | run);
-
   u32 incl = run;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -308,49 +281,14 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
   }
   if (lane == 31) s_wsum[warp] = incl;
   __syncthreads();
-  if (warp == 0) {
-    const u32 w = lane < WARPS ? s_wsum[lane] : 0;
-    u32 wi = w;
+  u32 wpre = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const u32 o = __shfl_up_sync(0xffffffffu, wi, d);
-      if (lane >= d) wi += o;
-    }
-    s_wsum[lane] = wi - w;
-  }
-  __syncthreads();
-  const u32 tstart = incl - run + s_wsum[warp];                  // first slot of digit b inside the tile
+  for (int w = 0; w < WARPS; w++) if (w < warp) wpre += s_wsum[w];
+  const u32 tstart = incl - run + wpre;                          // first slot of digit b inside the tile
 #pragma unroll
   for (int w = 0; w < WARPS; w++) whist[w * NBINS + b] += (unsigned short)tstart;
-
-  // Decoupled look-back, LB_W predecessors per step: the loads of a window are independent, so a
-  // walk of depth D costs ~D/LB_W L2 round trips instead of D.
-  constexpr int LB_W = 4;
-  u32 prev = 0;
-  if (tile > 0) {
-    const u32* sp = a.status + (size_t)tile * NBINS + b;         // sp[-j*NBINS] = tile-j
-    int64_t left = (int64_t)tile;                                 // predecessors not yet visited
-    bool done = false;
-    while (!done) {
-      u32 sv[LB_W];
-#pragma unroll
-      for (int j = 0; j < LB_W; j++)
-        sv[j] = (j < left) ? ld_relaxed_u32(sp - (size_t)(j + 1) * NBINS) : ST_FLAG_INCL;
-#pragma unroll
-      for (int j = 0; j < LB_W; j++) {
-        if (!done) {
-          u32 x = sv[j];
-          while ((x & ~ST_MASK) == 0) x = ld_relaxed_u32(sp - (size_t)(j + 1) * NBINS);   // holds a ticket: is running
-          prev += x & ST_MASK;
-          if ((x & ~ST_MASK) == ST_FLAG_INCL) done = true;
-        }
-      }
-      sp -= (size_t)LB_W * NBINS; left -= LB_W;
-    }
-    st_relaxed_u32(&a.status[(size_t)tile * NBINS + b], ST_FLAG_INCL | ((prev + run) & ST_MASK));
-  }
-  bin_dst[b] = a.bin_start[b] + prev - tstart;
-  if (have_idx && FULL) cp_async_commit_wait_all();
+  bin_dst[b] -= tstart;                                         // holds the digit's first output slot (set by the caller)
+  if (have_idx && (FULL || prefetched)) cp_async_wait_all();
   __syncthreads();
 
   // ---- reorder the tile in shared memory ----
@@ -359,12 +297,46 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
     const int pos = wbase + i * 32 + lane;
     if (FULL || pos < tile_n) {
       const u32 d = (u32)(key[i] >> a.shift) & a.mask;
-      const u32 lp = (u32)myhist[d] + rank[i];
+      const u32 lp = (u32)myhist[d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
       skey[lp] = key[i];
       sidx[lp] = have_idx ? ridx[pos] : (int32_t)(base + pos);
     }
   }
   __syncthreads();
+}
+
+template <typename KeyT, typename Src, int MINB>
+__global__ void __launch_bounds__(PASS_THREADS, MINB)
+scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
+{
+  constexpr int NBINS = PASS_NBINS, THREADS = PASS_THREADS, TILE = PASS_TILE;
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ u32 s_wsum[WARPS];
+  u32* bin_dst    = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
+  KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);
+  int32_t* sidx   = reinterpret_cast<int32_t*>(skey + TILE);
+
+  // One tile per CTA: neighbouring tiles run at the same time on different SMs, so the partial
+  // sectors at the ends of their digit runs meet in L2 before they are evicted.
+  const int tid = threadIdx.x;
+  const int64_t tile = blockIdx.x;
+  const int64_t base = tile * TILE;
+  const int tile_n = (int)((a.n - base) < (int64_t)TILE ? (a.n - base) : (int64_t)TILE);
+  const int64_t chunk = tile / CHUNK_TILES;
+  const int jt = (int)(tile % CHUNK_TILES);
+
+  // first output slot of digit `tid` for this tile: digit base + earlier chunks + earlier tiles of the chunk
+  u32 bin_run = a.digit_base[tid] + a.chunk_offs[(size_t)chunk * NBINS + tid];
+  {
+    const unsigned short* tc = a.tile_counts + (size_t)(chunk * CHUNK_TILES) * NBINS + tid;
+#pragma unroll 4
+    for (int t = 0; t < jt; t++) bin_run += (u32)tc[(size_t)t * NBINS];
+  }
+  bin_dst[tid] = bin_run;                                       // parked in shared memory until the scan phase
+
+  if (tile_n == TILE) scatter_tile<KeyT, Src, true >(a, smem_raw, s_wsum, base, tile_n, false);
+  else                scatter_tile<KeyT, Src, false>(a, smem_raw, s_wsum, base, tile_n, false);
 
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
 #pragma unroll 4
@@ -377,70 +349,49 @@ __device__ __forceinline__ void radix_pass_tile(const PassArgs<KeyT, Src>& a, un
   }
 }
 
-template <typename KeyT, typename Src, int NBINS, int THREADS, int IPT, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-radix_pass_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
-{
-  constexpr int TILE = THREADS * IPT;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ u32 s_wsum[32];
-  __shared__ u32 s_ticket;
-
-  if (threadIdx.x == 0) s_ticket = atomicAdd(a.tile_counter, 1u);
-  {
-    constexpr int WARPS = THREADS / 32;
-    u32* z = reinterpret_cast<u32*>(smem_raw);                              // whist
-    for (int i = threadIdx.x; i < WARPS * NBINS / 2; i += THREADS) z[i] = 0;
-    u32* m = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS) + NBINS + 4;   // = skey
-    for (int i = threadIdx.x; i < WARPS * NBINS; i += THREADS) m[i] = 0;    // per-warp peer masks
-  }
-  __syncthreads();
-  const u32 tile = s_ticket;
-  const int64_t base = (int64_t)tile * TILE;
-  if (a.n - base >= (int64_t)TILE)
-    radix_pass_tile<KeyT, Src, NBINS, THREADS, IPT, true>(a, smem_raw, s_wsum, tile);
-  else
-    radix_pass_tile<KeyT, Src, NBINS, THREADS, IPT, false>(a, smem_raw, s_wsum, tile);
-}
-
 template <typename KeyT> struct PassCfg;
-template <> struct PassCfg<u32> { static constexpr int THREADS = 256, IPT = 16, MINB = 4; };
-template <> struct PassCfg<u64> { static constexpr int THREADS = 256, IPT = 16, MINB = 3; };
+template <> struct PassCfg<u32> { static constexpr int MINB = 4; };
+template <> struct PassCfg<u64> { static constexpr int MINB = 3; };
 
-template <typename KeyT, int NBINS>
+template <typename KeyT>
 static constexpr size_t pass_smem_bytes() {
-  return sizeof(unsigned short) * (PassCfg<KeyT>::THREADS / 32) * NBINS + sizeof(u32) * (NBINS + 4)
-       + (sizeof(KeyT) + 2 * sizeof(int32_t)) * PassCfg<KeyT>::THREADS * PassCfg<KeyT>::IPT;
-}
-
-int radix_pass_tile_rows(int key_bytes, int /*nbins_log2*/) {
-  return key_bytes == 4 ? PassCfg<u32>::THREADS * PassCfg<u32>::IPT
-                        : PassCfg<u64>::THREADS * PassCfg<u64>::IPT;
+  return sizeof(unsigned short) * (PASS_THREADS / 32) * PASS_NBINS + sizeof(u32) * (PASS_NBINS + 4)
+       + (sizeof(KeyT) + 2 * sizeof(int32_t)) * PASS_TILE;
 }
 
 template <typename KeyT, typename Src>
-static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits,
-                    const u32* bin_start, u32* status, u32* tile_counter, cudaStream_t s)
+static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax, cudaStream_t s)
 {
-  constexpr int NBINS = 256;
-  constexpr int THREADS = PassCfg<KeyT>::THREADS, IPT = PassCfg<KeyT>::IPT, MINB = PassCfg<KeyT>::MINB;
+  constexpr int MINB = PassCfg<KeyT>::MINB;
   if (n == 0) return DTB_OK;
   if (io.idx_in && (reinterpret_cast<uintptr_t>(io.idx_in) & 15)) {
     set_error("internal: row-id buffer must be 16-byte aligned"); return DTB_EINVAL;
   }
+  const int64_t nchunks = radix_num_chunks(n);
+  const int64_t ntiles = (n + PASS_TILE - 1) / PASS_TILE;
+  u32* counts = work;                                   // [nchunks][NBINS], becomes chunk_offs in place
+  u32* total  = work + (size_t)nchunks * PASS_NBINS;    // [NBINS]
+  u32* base   = total + PASS_NBINS;                     // [NBINS]
+  unsigned short* tile_counts = reinterpret_cast<unsigned short*>(base + PASS_NBINS);   // [ntiles][NBINS]
+  const u32 mask = (1u << bits) - 1;
+
+  count_kernel<KeyT, Src><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts);
+  chunk_scan_kernel<<<PASS_NBINS, 256, 0, s>>>(counts, nchunks, total);
+  digit_base_kernel<<<1, 256, 0, s>>>(total, base, hmax);
+  count_launch(3);
+
   PassArgs<KeyT, Src> a;
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
-  a.n = n; a.shift = shift; a.mask = (1u << bits) - 1;
-  a.bin_start = bin_start; a.status = status; a.tile_counter = tile_counter;
-  const int64_t ntiles = (n + THREADS * IPT - 1) / (THREADS * IPT);
-  constexpr size_t smem = pass_smem_bytes<KeyT, NBINS>();
-  auto kern = radix_pass_kernel<KeyT, Src, NBINS, THREADS, IPT, MINB>;
+  a.n = n; a.shift = shift; a.mask = mask; a.chunk_offs = counts; a.digit_base = base;
+  a.tile_counts = tile_counts;
+  constexpr size_t smem = pass_smem_bytes<KeyT>();
+  auto kern = scatter_kernel<KeyT, Src, MINB>;
   static bool configured = false;   // per instantiation
   if (!configured) {
     DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  kern<<<(unsigned)ntiles, THREADS, smem, s>>>(a);
+  kern<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
@@ -448,12 +399,12 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits,
 
 template <typename KeyT>
 static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shift, int bits,
-                        const u32* bin_start, u32* status, u32* tile_counter, cudaStream_t s)
+                        u32* work, u32* hmax, cudaStream_t s)
 {
   const KeyNorm& k = kp.k[0];
 #define DTB_CASE(T)                                                                          \
   { RawSrc<T, KeyT> src; src.init(k);                                                        \
-    return run_pass<KeyT>(src, io, n, shift, bits, bin_start, status, tile_counter, s); }
+    return run_pass<KeyT>(src, io, n, shift, bits, work, hmax, s); }
   switch (k.stype) {
     case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
     case DTB_STYPE_INT16:                        DTB_CASE(int16_t)
@@ -466,21 +417,24 @@ static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shif
   set_error("internal: bad stype in radix pass"); return DTB_EINVAL;
 }
 
+size_t radix_pass_work_bytes(int64_t n) {
+  const size_t ntiles = (size_t)((n + PASS_TILE - 1) / PASS_TILE);
+  return sizeof(u32) * ((size_t)radix_num_chunks(n) * PASS_NBINS + 2 * PASS_NBINS)
+       + sizeof(unsigned short) * (ntiles + CHUNK_TILES) * PASS_NBINS;
+}
+
 int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
-                      int shift, int bits, int nbins_log2,
-                      const uint32_t* bin_start, uint32_t* status, uint32_t* tile_counter,
-                      cudaStream_t s)
+                      int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s)
 {
-  if (nbins_log2 != 8) { set_error("internal: only 8-bit digit kernels are built"); return DTB_EINVAL; }
-  if (n >= (int64_t)ST_MASK) { set_error("nrows too large for 30-bit look-back words"); return DTB_ENOTIMPL; }
+  if (bits < 1 || bits > 8) { set_error("internal: digit width must be 1..8 bits"); return DTB_EINVAL; }
   if (io.src_kind == 0) {
     if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)io.keys_in};
-      return run_pass<u32>(src, io, n, shift, bits, bin_start, status, tile_counter, s); }
+      return run_pass<u32>(src, io, n, shift, bits, work, hmax, s); }
     else { PackedSrc<u64> src{(const u64*)io.keys_in};
-      return run_pass<u64>(src, io, n, shift, bits, bin_start, status, tile_counter, s); }
+      return run_pass<u64>(src, io, n, shift, bits, work, hmax, s); }
   }
-  return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, bin_start, status, tile_counter, s)
-                        : run_pass_raw<u64>(io, kp, n, shift, bits, bin_start, status, tile_counter, s);
+  return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, work, hmax, s)
+                        : run_pass_raw<u64>(io, kp, n, shift, bits, work, hmax, s);
 }
 
 __global__ void iota32_kernel(int32_t* out, int64_t n) {
