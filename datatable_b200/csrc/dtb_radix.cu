@@ -191,6 +191,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Shared memory: whist[WARPS][NBINS] u16 | bin_dst[NBINS] u32 | skey[TILE] | sidx[TILE] | ridx[TILE]
 // (the per-warp peer-mask table of the rank phase aliases skey, idle until the reorder phase).
+// With 32-bit keys the sorted tile is staged as interleaved (key, row id) pairs so that the
+// scattered shared-memory write of the reorder phase is ONE 8-byte store per row, not two
+// 4-byte stores: shared-memory wavefronts, not HBM, bound this kernel.
 // Registers hold the 16 keys of the thread, their 16-bit ranks and the running output offset of
 // the thread's digit; 64 registers / 53 KB -> 4 CTAs = 32 warps per SM.
 template <typename KeyT, typename Src, bool FULL>
@@ -267,10 +270,11 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
   // ---- per digit (thread b owns digit b): prefix over warps, scan over digits, output offsets ----
   const int b = tid;
   u32 run = 0;
+  u32 cw[WARPS / 2];                                            // the warps' counts of digit b, two per register
 #pragma unroll
   for (int w = 0; w < WARPS; w++) {
-    const unsigned short c = whist[w * NBINS + b];
-    whist[w * NBINS + b] = (unsigned short)run;
+    const u32 c = whist[w * NBINS + b];
+    if (w & 1) cw[w >> 1] |= c << 16; else cw[w >> 1] = c;
     run += c;
   }
   u32 incl = run;
@@ -285,8 +289,14 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
 #pragma unroll
   for (int w = 0; w < WARPS; w++) if (w < warp) wpre += s_wsum[w];
   const u32 tstart = incl - run + wpre;                          // first slot of digit b inside the tile
+  {
+    u32 pre = tstart;                                            // tile slot of warp w's first row of digit b
 #pragma unroll
-  for (int w = 0; w < WARPS; w++) whist[w * NBINS + b] += (unsigned short)tstart;
+    for (int w = 0; w < WARPS; w++) {
+      whist[w * NBINS + b] = (unsigned short)pre;
+      pre += (cw[w >> 1] >> (16 * (w & 1))) & 0xffffu;
+    }
+  }
   bin_dst[b] -= tstart;                                         // holds the digit's first output slot (set by the caller)
   if (have_idx && (FULL || prefetched)) cp_async_wait_all();
   __syncthreads();
@@ -298,8 +308,13 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
     if (FULL || pos < tile_n) {
       const u32 d = (u32)(key[i] >> a.shift) & a.mask;
       const u32 lp = (u32)myhist[d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-      skey[lp] = key[i];
-      sidx[lp] = have_idx ? ridx[pos] : (int32_t)(base + pos);
+      const int32_t rid = have_idx ? ridx[pos] : (int32_t)(base + pos);
+      if constexpr (sizeof(KeyT) == 4) {
+        reinterpret_cast<uint2*>(skey)[lp] = make_uint2((u32)key[i], (u32)rid);      // pairs span skey+sidx
+      } else {
+        skey[lp] = key[i];
+        sidx[lp] = rid;
+      }
     }
   }
   __syncthreads();
@@ -341,11 +356,17 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
 #pragma unroll 4
   for (int p = tid; p < tile_n; p += THREADS) {
-    const KeyT k = skey[p];
+    KeyT k; int32_t rid;
+    if constexpr (sizeof(KeyT) == 4) {
+      const uint2 kv = reinterpret_cast<const uint2*>(skey)[p];
+      k = (KeyT)kv.x; rid = (int32_t)kv.y;
+    } else {
+      k = skey[p]; rid = sidx[p];
+    }
     const u32 d = (u32)(k >> a.shift) & a.mask;
     const u32 dst = bin_dst[d] + (u32)p;
     if (a.keys_out) a.keys_out[dst] = k;
-    a.idx_out[dst] = sidx[p];
+    a.idx_out[dst] = rid;
   }
 }
 

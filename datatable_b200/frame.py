@@ -248,13 +248,44 @@ def _evaluate(DT, j, by_, sort_):
         raise _lib.DtbCudaError("no usable CUDA device: datatable_b200 has no CPU fallback")
     host_frame = not any(engine.is_tensor(c) and c.is_cuda for c in DT._cols.values())
     cache = {}
+    names, exprs = _resolve_j(DT, j)
+
+    # Host columns: start every upload the query needs on a copy stream, key columns first, so
+    # that the PCIe transfer of the value columns overlaps the sort of the keys; each column is
+    # awaited (stream event) only where it is first used.
+    needed = []
+    for m in (by_, sort_):
+        if m is not None:
+            needed += [r.name for r in m.cols]
+    for e in exprs:
+        nm = e.arg.name if isinstance(e, Reducer) and e.arg is not None else getattr(e, "name", None)
+        if nm is not None:
+            needed.append(nm)
+    copy_stream = None
+    pending = {}
+    for nm in dict.fromkeys(needed):
+        c = DT._col(nm)
+        t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
+        if t.is_cuda:
+            continue
+        if copy_stream is None:
+            copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(copy_stream):
+            d = t.cuda(non_blocking=True)                           # pinned host memory -> async DMA
+            ev = torch.cuda.Event(); ev.record(copy_stream)
+        pending[nm] = (engine.Col(d, c.stype), ev)
 
     def dcol(name):
         if name not in cache:
-            c = DT._col(name)
-            t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
-            if not t.is_cuda:
-                c = engine.Col(t.cuda(non_blocking=True), c.stype)      # pinned host memory -> async DMA
+            if name in pending:
+                c, ev = pending[name]
+                torch.cuda.current_stream().wait_event(ev)
+                c.data.record_stream(torch.cuda.current_stream())
+            else:
+                c = DT._col(name)
+                t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
+                if not t.is_cuda:
+                    c = engine.Col(t.cuda(non_blocking=True), c.stype)
             cache[name] = c
         return cache[name]
 
@@ -274,7 +305,6 @@ def _evaluate(DT, j, by_, sort_):
     order = offsets = None
     ngroups = None
     gb = None
-    names, exprs = _resolve_j(DT, j)
     has_reducer = any(isinstance(e, Reducer) for e in exprs)
     if keycols:
         if by_ is not None and has_reducer:
