@@ -250,9 +250,9 @@ def run_b200(args, rank, local_rank, world):
     fam = {}
     for name, ms in prof:
         fam.setdefault(name, []).append(ms)
-    passes = fam.get("radix_pass", [])
+    passes = fam.get("radix_scatter", [])
     npass_step = len(passes) // max(1, args.steps)
-    # algorithmic bytes of one pass launch over n rows (32-bit keys, int32 row ids):
+    # algorithmic bytes of one scatter launch over n rows (32-bit keys, int32 row ids):
     #   first pass : read raw key 4            + write (key 4 + idx 4)  = 12 B/row
     #   later pass : read (key 4 + idx 4)      + write (key 4 + idx 4)  = 16 B/row
     pass_bytes = [12.0 * n] + [16.0 * n] * max(0, npass_step - 1)
@@ -260,13 +260,13 @@ def run_b200(args, rank, local_rank, world):
     pass_ms = sum(passes) / max(1, len(passes))
     achieved = alg_bytes_launch / (pass_ms / 1e3) / 1e9 if passes else None
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "radix_pass_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "scatter_kernel_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"kernel": "radix_pass_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "scatter_kernel (radix pass)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src, "launches_per_step": npass_step, "avg_launch_ms": pass_ms,
                 "alg_bytes_per_launch": alg_bytes_launch}

@@ -46,6 +46,22 @@ struct ProfScope {
   ~ProfScope() { if (on) { cudaEventRecord(r.b, s); t_prof_open.push_back(r); } }
 };
 
+static thread_local ProfRec t_prof_cur;
+static thread_local bool t_prof_cur_on = false;
+void prof_begin(const char* name, cudaStream_t s) {
+  if (!opt_profile) return;
+  t_prof_cur.name = name;
+  cudaEventCreate(&t_prof_cur.a); cudaEventCreate(&t_prof_cur.b);
+  cudaEventRecord(t_prof_cur.a, s);
+  t_prof_cur_on = true;
+}
+void prof_end(cudaStream_t s) {
+  if (!t_prof_cur_on) return;
+  cudaEventRecord(t_prof_cur.b, s);
+  t_prof_open.push_back(t_prof_cur);
+  t_prof_cur_on = false;
+}
+
 // call after the stream has been synchronised
 static void prof_collect() {
   for (auto& r : t_prof_open) {
@@ -476,11 +492,8 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       io.keys_out = (last && !want_sorted_keys) ? nullptr : kout;
       int32_t* iout = last ? round_out : ((p & 1) ? idxB.as<int32_t>() : idxA.as<int32_t>());
       io.idx_out = iout;
-      {
-        ProfScope ps("radix_pass", s);
-        DTB_TRY(launch_radix_pass(io, rk, key_bytes, n, pp.shift[p], pp.bits[p], work.as<u32>(),
-                                  hmax.as<u32>() + p, s));
-      }
+      DTB_TRY(launch_radix_pass(io, rk, key_bytes, n, pp.shift[p], pp.bits[p], work.as<u32>(),
+                                hmax.as<u32>() + p, s));
       if (last && want_sorted_keys) { sorted_keys = kout; last_key_bytes = key_bytes; }
       kin = kout;
       kout = (kout == keyA.p) ? keyB.p : keyA.p;

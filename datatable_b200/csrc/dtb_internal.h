@@ -15,6 +15,9 @@ constexpr int MAX_PASSES = 16;
 // Thread-local error slot + launch counter (dtb_api.cu)
 void set_error(const std::string& msg);
 void count_launch(int n = 1);
+// Optional CUDA-event timing of a kernel family (option "profile"); no-ops otherwise.
+void prof_begin(const char* name, cudaStream_t s);
+void prof_end(cudaStream_t s);
 
 #define DTB_CUDA_CHECK(expr)                                                     \
   do {                                                                           \

@@ -396,7 +396,9 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
   unsigned short* tile_counts = reinterpret_cast<unsigned short*>(base + PASS_NBINS);   // [ntiles][NBINS]
   const u32 mask = (1u << bits) - 1;
 
+  prof_begin("radix_count", s);
   count_kernel<KeyT, Src><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts);
+  prof_end(s);
   chunk_scan_kernel<<<PASS_NBINS, 256, 0, s>>>(counts, nchunks, total);
   digit_base_kernel<<<1, 256, 0, s>>>(total, base, hmax);
   count_launch(3);
@@ -412,7 +414,9 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
     DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  prof_begin("radix_scatter", s);
   kern<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
+  prof_end(s);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
