@@ -20,7 +20,7 @@ OK, EINVAL, ENOTIMPL, ECUDA, ENOMEM, ENOSPACE = 0, -1, -2, -3, -4, -5
 
 EXPORTS = [
     "dtb_last_error", "dtb_abi_version", "dtb_stype_size", "dtb_reduce_out_stype", "dtb_init",
-    "dtb_group", "dtb_groupby_create", "dtb_groupby_norder", "dtb_groupby_ngroups",
+    "dtb_group", "dtb_groupby_create", "dtb_groupby_create_reduce", "dtb_groupby_reduced", "dtb_groupby_norder", "dtb_groupby_ngroups",
     "dtb_groupby_order", "dtb_groupby_offsets", "dtb_groupby_destroy", "dtb_groupby_reduce", "dtb_reduce",
     "dtb_gather", "dtb_memcpy", "dtb_set_option", "dtb_get_option", "dtb_last_call_stats",
     "dtb_profile_count", "dtb_profile_get", "dtb_profile_reset",
@@ -29,6 +29,10 @@ EXPORTS = [
 
 class dtb_col(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("stype", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class dtb_reduce_spec(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_int32), ("reserved", ctypes.c_int32), ("value", dtb_col)]
 
 
 class dtb_call_stats(ctypes.Structure):
@@ -80,6 +84,11 @@ def _load():
                               c.POINTER(c.c_int64), c.POINTER(c.c_int64)]
     lib.dtb_groupby_create.argtypes = [c.POINTER(dtb_col), c.c_int, c.POINTER(c.c_int), c.c_int,
                                        c.c_int64, c.c_void_p, c.POINTER(c.c_void_p)]
+    lib.dtb_groupby_create_reduce.argtypes = [c.POINTER(dtb_col), c.c_int, c.POINTER(c.c_int), c.c_int,
+                                              c.c_int64, c.c_void_p, c.POINTER(dtb_reduce_spec), c.c_int,
+                                              c.POINTER(c.c_void_p)]
+    lib.dtb_groupby_reduced.restype = c.c_void_p
+    lib.dtb_groupby_reduced.argtypes = [c.c_void_p, c.c_int]
     for fn in ("dtb_groupby_norder", "dtb_groupby_ngroups"):
         getattr(lib, fn).restype = c.c_int64
         getattr(lib, fn).argtypes = [c.c_void_p]

@@ -267,6 +267,29 @@ static bool stype_is_float(int st) { return st == DTB_STYPE_FLOAT32 || st == DTB
 // ---------------------------------------------------------------------------
 // group(): plan + launch
 // ---------------------------------------------------------------------------
+// Reducers evaluated inside the group() call (dtb_groupby_create_reduce).
+struct FusedReducers {
+  const dtb_reduce_spec* spec = nullptr;
+  int n = 0;
+  std::vector<void*> out;       // owned device buffers, ngroups elements each
+};
+
+// Side stream on which the direct-address reducers run while the sort passes occupy `s`.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int ensure() {
+    if (stream) return DTB_OK;
+    int lo = 0, hi = 0;
+    DTB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    DTB_CUDA_CHECK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi));
+    DTB_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    DTB_CUDA_CHECK(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+    return DTB_OK;
+  }
+};
+static thread_local SideStream t_side;
+
 struct GroupResult {
   DevBuf order;          // int32[n]
   DevBuf offsets;        // int32[ng+1] (capacity n+1) when groups were requested
@@ -338,7 +361,7 @@ static void plan_passes(int total_bits, int width, PassPlan& pp) {
 static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t n,
                       cudaStream_t s, int32_t* order_dev /*optional caller buffer*/,
                       int32_t* offsets_dev /*optional caller buffer, n+1*/, GroupResult& res,
-                      bool want_direct = false)
+                      bool want_direct = false, FusedReducers* fr = nullptr)
 {
   // want_direct == the handle path: the RowIndex outlives the call and must be an owned allocation
   t_stats = dtb_call_stats{0, 0, 0, 0, 0};
@@ -459,6 +482,24 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
 
   DTB_TL("scratch allocated");
   u32 h_hmax[MAX_PASSES]; int n_hmax = 0;  // largest digit count per pass (read after the final sync)
+
+  // ---- fused reducers: when the group key domain is small the reducers only need the key
+  //      columns, so they run on a side stream WHILE the sort passes run on `s`
+  //      (the passes are shared-memory bound, the reducers L2-atomic bound) -----------------------
+  bool staged_keys = false;
+  for (int c = 0; c < nkeys; c++) staged_keys = staged_keys || (in[c].buf.p != nullptr);
+  const int dbits0 = (nrounds == 1) ? rounds[0].kp.total_bits - rounds[0].kp.group_shift : 99;
+  bool fused_direct = fr && fr->n > 0 && do_groups && nrounds == 1 && !staged_keys && dbits0 <= 22 &&
+                      na_pos != DTB_NA_REMOVE;
+  if (fused_direct)
+    for (int i = 0; i < fr->n; i++)
+      fused_direct = fused_direct && (fr->spec[i].op == DTB_OP_NROWS || is_device_ptr(fr->spec[i].value.data));
+  DevBuf facc;
+  const int64_t ftable = fused_direct ? ((int64_t)1 << dbits0) : 0;
+  if (fused_direct) {
+    DTB_TRY(t_side.ensure());
+    DTB_TRY(facc.alloc(sizeof(u64) * (size_t)ftable * 2 * (size_t)fr->n, s));
+  }
   const int32_t* idx_cur = nullptr;        // rows in the order established by the previous rounds
   void* sorted_keys = nullptr;             // last round's sorted composite keys
   int last_key_bytes = 4;
@@ -492,8 +533,22 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       io.keys_out = (last && !want_sorted_keys) ? nullptr : kout;
       int32_t* iout = last ? round_out : ((p & 1) ? idxB.as<int32_t>() : idxA.as<int32_t>());
       io.idx_out = iout;
+      const bool fork_here = fused_direct && ri == 0 && p == 0;
       DTB_TRY(launch_radix_pass(io, rk, key_bytes, n, pp.shift[p], pp.bits[p], work.as<u32>(),
-                                hmax.as<u32>() + p, s));
+                                hmax.as<u32>() + p, s, fork_here ? t_side.fork : nullptr));
+      if (fork_here) {
+        // the digit totals of pass 0 exist: the reducers can decide about hot keys on the device
+        DTB_CUDA_CHECK(cudaStreamWaitEvent(t_side.stream, t_side.fork, 0));
+        for (int i = 0; i < fr->n; i++) {
+          if (fr->spec[i].op == DTB_OP_NROWS) continue;
+          ProfScope ps("reduce_direct_overlapped", t_side.stream);
+          DTB_TRY(launch_direct_accumulate(fr->spec[i].op, rk, 0, hmax.as<u32>(), fr->spec[i].value.data,
+                                           fr->spec[i].value.stype, n, ftable,
+                                           facc.as<u64>() + (size_t)ftable * 2 * i,
+                                           facc.as<u64>() + (size_t)ftable * (2 * i + 1), t_side.stream));
+        }
+        DTB_CUDA_CHECK(cudaEventRecord(t_side.join, t_side.stream));
+      }
       if (last && want_sorted_keys) { sorted_keys = kout; last_key_bytes = key_bytes; }
       kin = kout;
       kout = (kout == keyA.p) ? keyB.p : keyA.p;
@@ -545,7 +600,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     bool staged = false;
     for (int c = 0; c < nkeys; c++) staged = staged || (in[c].buf.p != nullptr);
     const int dbits = (nrounds == 1) ? rounds[0].kp.total_bits - rounds[0].kp.group_shift : 99;
-    if (want_direct && nrounds == 1 && !staged && dbits <= 22 && na_pos != DTB_NA_REMOVE) {
+    if ((want_direct || fused_direct) && nrounds == 1 && !staged && dbits <= 22 && na_pos != DTB_NA_REMOVE) {
       DTB_TRY(res.gkeys.alloc_owned(sizeof(u32) * (size_t)(res.ngroups + 1), s));
       DTB_TRY(launch_group_keys(sorted_keys, last_key_bytes, offsets, rounds[0].kp.group_shift, res.ngroups,
                                 res.gkeys.as<u32>(), s));
@@ -559,6 +614,36 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     }
   }
   DTB_TL("offsets synced");
+
+  // ---- fused reducers: finalize (direct) or evaluate through the RowIndex (general) ------------
+  if (fr && fr->n > 0 && do_groups) {
+    const int64_t ng = res.ngroups;
+    fr->out.assign(fr->n, nullptr);
+    if (fused_direct) DTB_CUDA_CHECK(cudaStreamWaitEvent(s, t_side.join, 0));
+    DevBuf gacc;
+    if (!fused_direct) DTB_TRY(gacc.alloc(sizeof(u64) * (size_t)(ng > 0 ? ng : 1) * 2, s));
+    for (int i = 0; i < fr->n; i++) {
+      const dtb_reduce_spec& sp = fr->spec[i];
+      const int out_st = (sp.op == DTB_OP_NROWS) ? DTB_STYPE_INT64 : reduce_out_stype_host(sp.op, sp.value.stype);
+      if (!out_st) {
+        set_error("Invalid column of stype " + std::to_string(sp.value.stype) + " in reducer " + std::to_string(sp.op));
+        return stype_supported(sp.value.stype) ? DTB_EINVAL : DTB_ENOTIMPL;
+      }
+      DevBuf ob; DTB_TRY(ob.alloc_owned((size_t)(ng > 0 ? ng : 1) * stype_bytes(out_st), s));
+      if (sp.op == DTB_OP_NROWS) {
+        DTB_TRY(launch_nrows(offsets, ng, ob.p, s));
+      } else if (fused_direct) {
+        DTB_TRY(launch_direct_finalize(sp.op, sp.value.stype, facc.as<u64>() + (size_t)ftable * 2 * i,
+                                       facc.as<u64>() + (size_t)ftable * (2 * i + 1), res.gkeys.as<u32>(), ng, ob.p, s));
+      } else {
+        DevIn dv; DTB_TRY(dv.bind(sp.value.data, (size_t)n * stype_bytes(sp.value.stype), s));
+        ProfScope ps("reduce", s);
+        DTB_TRY(launch_reduce_impl(sp.op, dv.dptr, sp.value.stype, n, order + res.nskip, 0, offsets, ng,
+                                   ng > 0 ? (int64_t)(n - res.nskip) : 0, gacc.as<u64>(), gacc.as<u64>() + ng, ob.p, s));
+      }
+      fr->out[i] = ob.detach();
+    }
+  }
   if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   return DTB_OK;
 }
@@ -583,6 +668,7 @@ struct dtb_groupby {
   dtb::KeyPlan kp;
   int64_t table = 0;
   void* gkeys = nullptr;      // device uint32[ngroups]
+  std::vector<void*> reduced; // outputs of the reducers evaluated by dtb_groupby_create_reduce
 };
 
 extern "C" {
@@ -688,14 +774,27 @@ int dtb_group(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int6
 int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t nrows,
                        dtb_stream stream, dtb_groupby** out)
 {
+  return dtb_groupby_create_reduce(keys, nkeys, flags, na_pos, nrows, stream, nullptr, 0, out);
+}
+
+int dtb_groupby_create_reduce(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t nrows,
+                              dtb_stream stream, const dtb_reduce_spec* reducers, int nreducers,
+                              dtb_groupby** out)
+{
   cudaStream_t s = (cudaStream_t)stream;
   if (!out) { set_error("out is NULL"); return DTB_EINVAL; }
   *out = nullptr;
+  if (nreducers < 0 || (nreducers > 0 && !reducers)) { set_error("bad reducer list"); return DTB_EINVAL; }
+  if (nreducers > 0 && flags && nkeys > 0 && (flags[0] & DTB_FLAG_SORT_ONLY)) {
+    set_error("reducers need a Groupby: the first key column must not be SORT_ONLY"); return DTB_EINVAL;
+  }
   ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   GroupResult res;
-  int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, nullptr, nullptr, res, true);
-  if (rc != DTB_OK) return rc;
+  FusedReducers fr; fr.spec = reducers; fr.n = nreducers;
+  int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, nullptr, nullptr, res, true, nreducers ? &fr : nullptr);
+  if (rc != DTB_OK) { for (void* p : fr.out) if (p) cudaFreeAsync(p, s); return rc; }
   dtb_groupby* g = new dtb_groupby();
+  g->reduced = fr.out;
   g->norder = res.n - res.nskip;
   g->ngroups = res.ngroups;
   g->nrows = res.n;
@@ -720,6 +819,9 @@ int64_t dtb_groupby_norder(const dtb_groupby* g) { return g ? g->norder : 0; }
 int64_t dtb_groupby_ngroups(const dtb_groupby* g) { return g ? g->ngroups : -1; }
 const void* dtb_groupby_order(const dtb_groupby* g) { return g ? g->order : nullptr; }
 const void* dtb_groupby_offsets(const dtb_groupby* g) { return g ? g->offsets : nullptr; }
+const void* dtb_groupby_reduced(const dtb_groupby* g, int i) {
+  return (g && i >= 0 && i < (int)g->reduced.size()) ? g->reduced[i] : nullptr;
+}
 
 int dtb_groupby_destroy(dtb_groupby* g, dtb_stream stream) {
   if (!g) return DTB_OK;
@@ -727,6 +829,7 @@ int dtb_groupby_destroy(dtb_groupby* g, dtb_stream stream) {
   if (g->order_base) cudaFreeAsync(g->order_base, s);
   if (g->offsets) cudaFreeAsync(g->offsets, s);
   if (g->gkeys) cudaFreeAsync(g->gkeys, s);
+  for (void* p : g->reduced) if (p) cudaFreeAsync(p, s);
   delete g;
   return DTB_OK;
 }

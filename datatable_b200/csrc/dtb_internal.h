@@ -101,8 +101,10 @@ struct PassIO {
 // One stable pass = count + scan + scatter kernels.  work: radix_pass_work_bytes(n) of scratch;
 // hmax (optional, device): receives the largest digit count of the pass.
 size_t radix_pass_work_bytes(int64_t n);
+// after_counts (optional): recorded on `s` once the digit totals of the pass (hmax) are final.
 int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
-                      int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s);
+                      int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s,
+                      cudaEvent_t after_counts = nullptr);
 
 // ---------------------------------------------------------------------------
 // Group offsets (replaces GroupGatherer, sort_groups.cc:34-117): heads where
@@ -134,6 +136,12 @@ int reduce_out_stype_host(int op, int stype);
 int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* value, int stype, int64_t n,
                          int64_t table, const uint32_t* gkeys, int64_t ngroups,
                          unsigned long long* acc0, unsigned long long* acc1, void* out, cudaStream_t s);
+int launch_direct_accumulate(int op, const KeyPlan& kp, int hot_value, const uint32_t* hot_count,
+                             const void* value, int stype, int64_t n, int64_t table,
+                             unsigned long long* acc0, unsigned long long* acc1, cudaStream_t s);
+int launch_direct_finalize(int op, int stype, const unsigned long long* acc0, const unsigned long long* acc1,
+                           const uint32_t* gkeys, int64_t ngroups, void* out, cudaStream_t s);
+int launch_nrows(const int32_t* offsets, int64_t ngroups, void* out, cudaStream_t s);
 int launch_group_keys(const void* sorted_keys, int key_bytes, const int32_t* offsets, int group_shift,
                       int64_t ngroups, uint32_t* gkeys, cudaStream_t s);
 

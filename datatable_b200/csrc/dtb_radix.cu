@@ -381,7 +381,8 @@ static constexpr size_t pass_smem_bytes() {
 }
 
 template <typename KeyT, typename Src>
-static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax, cudaStream_t s)
+static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax, cudaStream_t s,
+                    cudaEvent_t after_counts)
 {
   constexpr int MINB = PassCfg<KeyT>::MINB;
   if (n == 0) return DTB_OK;
@@ -402,6 +403,7 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
   chunk_scan_kernel<<<PASS_NBINS, 256, 0, s>>>(counts, nchunks, total);
   digit_base_kernel<<<1, 256, 0, s>>>(total, base, hmax);
   count_launch(3);
+  if (after_counts) DTB_CUDA_CHECK(cudaEventRecord(after_counts, s));
 
   PassArgs<KeyT, Src> a;
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
@@ -424,12 +426,12 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
 
 template <typename KeyT>
 static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shift, int bits,
-                        u32* work, u32* hmax, cudaStream_t s)
+                        u32* work, u32* hmax, cudaStream_t s, cudaEvent_t after_counts)
 {
   const KeyNorm& k = kp.k[0];
 #define DTB_CASE(T)                                                                          \
   { RawSrc<T, KeyT> src; src.init(k);                                                        \
-    return run_pass<KeyT>(src, io, n, shift, bits, work, hmax, s); }
+    return run_pass<KeyT>(src, io, n, shift, bits, work, hmax, s, after_counts); }
   switch (k.stype) {
     case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
     case DTB_STYPE_INT16:                        DTB_CASE(int16_t)
@@ -449,17 +451,18 @@ size_t radix_pass_work_bytes(int64_t n) {
 }
 
 int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
-                      int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s)
+                      int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s,
+                      cudaEvent_t after_counts)
 {
   if (bits < 1 || bits > 8) { set_error("internal: digit width must be 1..8 bits"); return DTB_EINVAL; }
   if (io.src_kind == 0) {
     if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)io.keys_in};
-      return run_pass<u32>(src, io, n, shift, bits, work, hmax, s); }
+      return run_pass<u32>(src, io, n, shift, bits, work, hmax, s, after_counts); }
     else { PackedSrc<u64> src{(const u64*)io.keys_in};
-      return run_pass<u64>(src, io, n, shift, bits, work, hmax, s); }
+      return run_pass<u64>(src, io, n, shift, bits, work, hmax, s, after_counts); }
   }
-  return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, work, hmax, s)
-                        : run_pass_raw<u64>(io, kp, n, shift, bits, work, hmax, s);
+  return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, work, hmax, s, after_counts)
+                        : run_pass_raw<u64>(io, kp, n, shift, bits, work, hmax, s, after_counts);
 }
 
 __global__ void iota32_kernel(int32_t* out, int64_t n) {

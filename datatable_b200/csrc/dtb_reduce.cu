@@ -350,6 +350,15 @@ int launch_reduce_impl(int op, const void* value, int stype, int64_t nv, const v
 
 int reduce_out_stype_host(int op, int st) { return reduce_out_stype(op, st); }
 
+int launch_nrows(const int32_t* offsets, int64_t ng, void* out, cudaStream_t s) {
+  if (ng == 0) return DTB_OK;
+  const int fgrid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+  nrows_kernel<<<fgrid, 256, 0, s>>>(offsets, ng, (int64_t*)out);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
 // ===========================================================================
 // Direct-address reducers (small key domains)
 // ===========================================================================
@@ -363,11 +372,18 @@ int reduce_out_stype_host(int op, int st) { return reduce_out_stype(op, st); }
 //
 // Bound: L2 atomic throughput (measured 170 G atomics/s on B200), then HBM.
 // Algorithmic bytes per row: key column(s) + value column, read once.
-template <typename T, int CAT, typename KSrc, bool HOT>
+struct HotSpec {            // "may one key own a large share of the rows?"
+  const u32* count;         // device: largest digit count of the first pass (NULL = use `value`)
+  u32 thresh;
+  int value;
+};
+
+template <typename T, int CAT, typename KSrc>
 __global__ void __launch_bounds__(512)
 direct_reduce_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load_t* __restrict__ v,
-                     int64_t n, u64* acc0, u64* acc1, int flag)
+                     int64_t n, u64* acc0, u64* acc1, int flag, HotSpec hs)
 {
+  const bool HOT = hs.count ? (*hs.count > hs.thresh) : (hs.value != 0);      // warp-uniform
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nround = ((n + 31) / 32) * 32;                // keep whole warps in the loop
@@ -452,7 +468,7 @@ struct DirectComposite {
   }
 };
 
-static thread_local bool t_direct_hot = false;
+static thread_local HotSpec t_hot = {nullptr, 0, 0};
 
 template <typename T, int CAT, typename KSrc>
 static int run_direct(const KSrc& ks, int gshift, const void* v, int64_t n, u64* acc0, u64* acc1, int flag,
@@ -461,10 +477,7 @@ static int run_direct(const KSrc& ks, int gshift, const void* v, int64_t n, u64*
   typedef typename RawKey<T>::load_t L;
   int64_t want = (n + 511) / 512;
   int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
-  if (t_direct_hot)
-    direct_reduce_kernel<T, CAT, KSrc, true><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag);
-  else
-    direct_reduce_kernel<T, CAT, KSrc, false><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag);
+  direct_reduce_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag, t_hot);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
@@ -509,15 +522,17 @@ static int direct_op(int op, int st, const KSrc& ks, int gshift, const void* v, 
   set_error("unknown reducer"); return DTB_EINVAL;
 }
 
-// acc0/acc1: device scratch of `table` u64 each; gkeys: uint32[ng] group key of every group.
-int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* value, int stype, int64_t n,
-                         int64_t table, const uint32_t* gkeys, int64_t ng, u64* acc0, u64* acc1,
-                         void* out, cudaStream_t s)
+// Stage 1: stream every row into acc[x].  acc0/acc1: device scratch of `table` u64 each.
+// hot_count (device, optional): largest digit count of the first radix pass; a key owning more
+// than 2 % of the rows switches on the intra-warp pre-aggregation (decided on the device so that the
+// accumulation can run on a side stream while the sort is still in flight).
+int launch_direct_accumulate(int op, const KeyPlan& kp, int hot_value, const uint32_t* hot_count,
+                             const void* value, int stype, int64_t n, int64_t table,
+                             u64* acc0, u64* acc1, cudaStream_t s)
 {
-  t_direct_hot = hot_keys;
   const int out_st = reduce_out_stype(op, stype);
   if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
-  if (ng == 0) return DTB_OK;
+  t_hot.count = hot_count; t_hot.thresh = (u32)(0.02 * (double)n); t_hot.value = hot_value;
   const int tgrid = (int)((table + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (table + 255) / 256);
   fill_u64_kernel<<<tgrid, 256, 0, s>>>(acc0, table, (op == DTB_OP_MIN) ? ~0ull : 0ull);
   count_launch();
@@ -545,11 +560,30 @@ int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* v
     }
     if (rc != DTB_OK) return rc;
   }
+  return DTB_OK;
+}
+
+// Stage 2: out[g] = finalize(acc[gkeys[g]]) in the reference's output stype / NA rules.
+int launch_direct_finalize(int op, int stype, const u64* acc0, const u64* acc1, const uint32_t* gkeys,
+                           int64_t ng, void* out, cudaStream_t s)
+{
+  const int out_st = reduce_out_stype(op, stype);
+  if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
+  if (ng == 0) return DTB_OK;
   const int fgrid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
   finalize_direct_kernel<<<fgrid, 256, 0, s>>>(op, stype, out_st, acc0, acc1, gkeys, ng, out);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
+}
+
+int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* value, int stype, int64_t n,
+                         int64_t table, const uint32_t* gkeys, int64_t ng, u64* acc0, u64* acc1,
+                         void* out, cudaStream_t s)
+{
+  if (ng == 0) return DTB_OK;
+  DTB_TRY(launch_direct_accumulate(op, kp, hot_keys ? 1 : 0, nullptr, value, stype, n, table, acc0, acc1, s));
+  return launch_direct_finalize(op, stype, acc0, acc1, gkeys, ng, out, s);
 }
 
 // gkeys[g] = sorted_keys[offsets[g]] >> gshift  (the normalised key of every group)

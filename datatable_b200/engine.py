@@ -130,7 +130,9 @@ class Groupby:
     (dtb_groupby handle).  Mirrors the pair the reference keeps in EvalContext
     (src/core/expr/eval_context.cc:278-280)."""
 
-    def __init__(self, cols, flags=None, na_pos=NA_FIRST):
+    def __init__(self, cols, flags=None, na_pos=NA_FIRST, reducers=None):
+        """reducers: optional [(op, value column or None), ...] evaluated inside the same call
+        (dtb_groupby_create_reduce): with a small key domain they overlap the sort on a side stream."""
         cols = [Col(c) for c in cols]
         nk = len(cols)
         n = cols[0].nrows
@@ -138,7 +140,25 @@ class Groupby:
         ckeys = (dtb_col * nk)(*[c.c() for c in cols])
         cflags = (ctypes.c_int * nk)(*flags)
         h = ctypes.c_void_p(0)
-        check(lib.dtb_groupby_create(ckeys, nk, cflags, na_pos, n, _stream(), ctypes.byref(h)))
+        self._red = []
+        if reducers:
+            specs = (_lib.dtb_reduce_spec * len(reducers))()
+            for i, (op, val) in enumerate(reducers):
+                if op == _lib.OP_NROWS or val is None:
+                    v = None
+                    specs[i] = _lib.dtb_reduce_spec(_lib.OP_NROWS, 0, dtb_col(None, INT8, 0))
+                    self._red.append((_lib.OP_NROWS, INT64, None))
+                else:
+                    v = Col(val)
+                    out_st = lib.dtb_reduce_out_stype(op, v.stype)
+                    if not out_st:
+                        raise _lib.DtbValueError(f"Invalid column of stype {v.stype} in reducer {op}")
+                    specs[i] = _lib.dtb_reduce_spec(op, 0, v.c())
+                    self._red.append((op, out_st, v))
+            check(lib.dtb_groupby_create_reduce(ckeys, nk, cflags, na_pos, n, _stream(), specs, len(reducers),
+                                                ctypes.byref(h)))
+        else:
+            check(lib.dtb_groupby_create(ckeys, nk, cflags, na_pos, n, _stream(), ctypes.byref(h)))
         self._h = h
         self._keys = cols            # the handle may re-read the key columns (direct-address reducers)
         self.norder = lib.dtb_groupby_norder(h)
@@ -162,6 +182,14 @@ class Groupby:
             optr = out.data_ptr() if is_tensor(out) else out.ctypes.data
         check(lib.dtb_groupby_reduce(self._h, op, v.c(), v.nrows, _stream(), ctypes.c_void_p(optr)))
         return out
+
+    def reduced(self, i):
+        """Result of the i-th reducer passed to the constructor (CUDA tensor, ngroups elements)."""
+        op, out_st, _ = self._red[i]
+        t = torch.empty(max(self.ngroups, 0), dtype=_torch_dtype(out_st), device="cuda")
+        if self.ngroups > 0:
+            _memcpy_d2d(t.data_ptr(), lib.dtb_groupby_reduced(self._h, i), t.numel() * t.element_size())
+        return t
 
     def order_col(self):
         """The RowIndex as a zero-copy column view (valid while the handle lives)."""

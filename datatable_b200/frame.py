@@ -309,7 +309,10 @@ def _evaluate(DT, j, by_, sort_):
     if keycols:
         if by_ is not None and has_reducer:
             # RowIndex + Groupby stay in HBM behind a handle; reducers go through it
-            gb = engine.Groupby(keycols, flags, na_pos)
+            # the reducers of j are known before group() runs: hand them over so that the engine can
+            # overlap them with the sort (dtb_groupby_create_reduce)
+            reds = [(e.op, None if e.arg is None else dcol(e.arg.name)) for e in exprs if isinstance(e, Reducer)]
+            gb = engine.Groupby(keycols, flags, na_pos, reducers=reds)
             ngroups = gb.ngroups
         else:
             order, offsets, ngroups = engine.group(keycols, flags, na_pos)
@@ -334,9 +337,11 @@ def _evaluate(DT, j, by_, sort_):
             for ref in by_.cols:
                 c = dcol(ref.name)
                 add(ref.name, engine.gather(c, first), c.stype)
+            ired = 0
             for name, e in zip(names, exprs):
                 if isinstance(e, Reducer):
-                    add(name, gb.reduce(e.op, None if e.arg is None else dcol(e.arg.name)), None)
+                    add(name, gb.reduced(ired), None)
+                    ired += 1
                 else:
                     raise NotImplementedError("mixing reducers and plain columns under by() is outside the hot path")
             for n_ in out._cols:

@@ -142,6 +142,25 @@ typedef struct dtb_groupby dtb_groupby;
 DTB_API int dtb_groupby_create(const dtb_col* keys, int nkeys, const int* flags,
                        int na_pos, int64_t nrows, dtb_stream stream,
                        dtb_groupby** out);
+/*
+ * Fused variant: group() plus `nreducers` per-group reducers in one call (the j-expressions of
+ * DT[:, {sum(f.v), ...}, by(f.k)] are known before group() runs, expr/eval_context.cc:144-172).
+ * When the group-key domain is small the reducers only need the key columns, so they run on an
+ * engine-owned side stream concurrently with the sort passes.  Results are owned by the handle:
+ * dtb_groupby_reduced(g, i) = device buffer of ngroups elements of stype
+ * dtb_reduce_out_stype(op, value.stype).  Equivalent to dtb_groupby_create + dtb_groupby_reduce.
+ */
+typedef struct dtb_reduce_spec {
+  int32_t op;          /* DTB_OP_* */
+  int32_t reserved;
+  dtb_col value;       /* ignored for DTB_OP_NROWS */
+} dtb_reduce_spec;
+
+DTB_API int dtb_groupby_create_reduce(const dtb_col* keys, int nkeys, const int* flags,
+                       int na_pos, int64_t nrows, dtb_stream stream,
+                       const dtb_reduce_spec* reducers, int nreducers, dtb_groupby** out);
+DTB_API const void* dtb_groupby_reduced(const dtb_groupby* g, int i);
+
 DTB_API int64_t     dtb_groupby_norder(const dtb_groupby* g);    /* RowIndex length               */
 DTB_API int64_t     dtb_groupby_ngroups(const dtb_groupby* g);   /* -1 = no Groupby (sort only)   */
 DTB_API const void* dtb_groupby_order(const dtb_groupby* g);     /* device int32[norder]          */

@@ -221,3 +221,33 @@ def test_groupby_handle_multikey_direct():
         got = gb.reduce(OPS[op], vd).cpu().numpy()
         assert_reducer_equal(got, want, op, FLOAT64, ctx=f"multikey direct {op}")
     gb.close()
+
+
+@pytest.mark.parametrize("small_domain", [True, False])
+def test_fused_create_reduce_vs_oracle(small_domain):
+    """dtb_groupby_create_reduce: reducers evaluated inside the group() call (side-stream overlap for
+    small key domains, RowIndex path otherwise) must equal separate group + reduce."""
+    import torch
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    n = 600_000
+    rng = np.random.default_rng(5 + small_domain)
+    k = make_col(rng, INT32, n, "few" if small_domain else "wide", 0.03)
+    v1 = make_col(rng, FLOAT64, n, "unit", 0.1)
+    v2 = make_col(rng, INT16, n, "unit", 0.1)
+    want_o, want_f, want_ng = orc.group([k], [0], 1)
+    reds = [("sum", v1, FLOAT64), ("mean", v2, INT16), ("min", v1, FLOAT64), ("max", v2, INT16),
+            ("count", v1, FLOAT64), ("nrows", None, None), ("sum", v2, INT16)]
+    gb = engine.Groupby([torch.from_numpy(k).cuda()], [0], 1,
+                        reducers=[(OPS[op], None if v is None else torch.from_numpy(v).cuda()) for op, v, _ in reds])
+    assert gb.ngroups == want_ng
+    assert np.array_equal(gb.order().cpu().numpy(), want_o)
+    assert np.array_equal(gb.offsets().cpu().numpy(), want_f)
+    for i, (op, v, vst) in enumerate(reds):
+        got = gb.reduced(i).cpu().numpy()
+        if op == "nrows":
+            assert np.array_equal(got, np.diff(want_f).astype(np.int64))
+        else:
+            want = orc.reduce(OPS[op], v, want_o, want_f, stype=vst)
+            assert_reducer_equal(got, want, op, vst, ctx=f"fused {op} small={small_domain}")
+    gb.close()
