@@ -494,6 +494,17 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   if (fused_direct)
     for (int i = 0; i < fr->n; i++)
       fused_direct = fused_direct && (fr->spec[i].op == DTB_OP_NROWS || is_device_ptr(fr->spec[i].value.data));
+  // Small key domain + handle path: the last pass counts rows per group key instead of writing
+  // the sorted keys, and the offsets come from a scan over that table.
+  const bool count_table = want_direct && do_groups && nrounds == 1 && !staged_keys && dbits0 <= 22 &&
+                           na_pos != DTB_NA_REMOVE;
+  int64_t ctable = 0;
+  DevBuf gcount;
+  if (count_table) {
+    ctable = (int64_t)1 << (dbits0 < 10 ? 10 : dbits0);
+    DTB_TRY(gcount.alloc(sizeof(u32) * (size_t)ctable, s));
+    DTB_CUDA_CHECK(cudaMemsetAsync(gcount.p, 0, sizeof(u32) * (size_t)ctable, s));
+  }
   DevBuf facc;
   const int64_t ftable = fused_direct ? ((int64_t)1 << dbits0) : 0;
   if (fused_direct) {
@@ -521,7 +532,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     DevBuf hmax; DTB_TRY(hmax.alloc(sizeof(u32) * MAX_PASSES, s));
 
     int32_t* round_out = last_round ? order : ((ri & 1) ? idxR1.as<int32_t>() : idxR0.as<int32_t>());
-    const bool want_sorted_keys = last_round && do_groups && rounds[ri].has_by;
+    const bool want_sorted_keys = last_round && do_groups && rounds[ri].has_by && !count_table;
     void* kin = keyA.p; void* kout = fused_raw ? keyA.p : keyB.p;
     const int32_t* iin = idx_cur;
     for (int p = 0; p < pp.npasses; p++) {
@@ -535,7 +546,8 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       io.idx_out = iout;
       const bool fork_here = fused_direct && ri == 0 && p == 0;
       DTB_TRY(launch_radix_pass(io, rk, key_bytes, n, pp.shift[p], pp.bits[p], work.as<u32>(),
-                                hmax.as<u32>() + p, s, fork_here ? t_side.fork : nullptr));
+                                hmax.as<u32>() + p, s, fork_here ? t_side.fork : nullptr,
+                                (count_table && last) ? gcount.as<u32>() : nullptr, rk.group_shift));
       if (fork_here) {
         // the digit totals of pass 0 exist: the reducers can decide about hot keys on the device
         DTB_CUDA_CHECK(cudaStreamWaitEvent(t_side.stream, t_side.fork, 0));
@@ -569,7 +581,13 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     DTB_CUDA_CHECK(cudaMemsetAsync(oscr.p, 0, oscr.bytes, s));
     u64* d_ng = oscr.as<u64>() + otiles + 2;
     DevBuf headflags;
-    if (nrounds == 1) {
+    if (count_table) {
+      ProfScope ps("group_offsets_from_counts", s);
+      DTB_TRY(res.gkeys.alloc_owned(sizeof(u32) * (size_t)(ctable + 1), s));   // trimmed by the handle's lifetime
+      DevBuf cscr; DTB_TRY(cscr.alloc(sizeof(u64) * (size_t)(2 * ctable / 1024 + 2), s));
+      DTB_TRY(launch_offsets_from_counts(gcount.as<u32>(), ctable, n, offsets, res.gkeys.as<u32>(), d_ng,
+                                         cscr.as<u64>(), s));
+    } else if (nrounds == 1) {
       ProfScope ps("group_offsets", s);
       DTB_TRY(launch_group_offsets(sorted_keys, last_key_bytes, rounds[0].kp.group_shift, n, offsets, d_ng,
                                    oscr.as<u64>(), s));
@@ -601,9 +619,11 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     for (int c = 0; c < nkeys; c++) staged = staged || (in[c].buf.p != nullptr);
     const int dbits = (nrounds == 1) ? rounds[0].kp.total_bits - rounds[0].kp.group_shift : 99;
     if ((want_direct || fused_direct) && nrounds == 1 && !staged && dbits <= 22 && na_pos != DTB_NA_REMOVE) {
-      DTB_TRY(res.gkeys.alloc_owned(sizeof(u32) * (size_t)(res.ngroups + 1), s));
-      DTB_TRY(launch_group_keys(sorted_keys, last_key_bytes, offsets, rounds[0].kp.group_shift, res.ngroups,
-                                res.gkeys.as<u32>(), s));
+      if (!count_table) {
+        DTB_TRY(res.gkeys.alloc_owned(sizeof(u32) * (size_t)(res.ngroups + 1), s));
+        DTB_TRY(launch_group_keys(sorted_keys, last_key_bytes, offsets, rounds[0].kp.group_shift, res.ngroups,
+                                  res.gkeys.as<u32>(), s));
+      }
       res.direct = true;
       // a key owning a share f of the rows puts >= f*n rows into one bin of EVERY digit histogram
       u32 least = 0xffffffffu;

@@ -153,6 +153,110 @@ int launch_mark_heads(const void* sorted_keys, int key_bytes, int group_shift, i
   return DTB_OK;
 }
 
+// ===========================================================================
+// Offsets from a count table (small key domains)
+// ===========================================================================
+// count[x] = rows whose group key is x (filled by the last radix pass).  Three tiny kernels over the
+// table (<= 4M entries): block sums, scan of the block sums, local scan + compaction.
+constexpr int CT_BLOCK = 1024;                 // table entries per block (256 threads x 4)
+
+__global__ void __launch_bounds__(256)
+count_block_sums_kernel(const u32* __restrict__ count, u64* __restrict__ bsum /*[nb][2]*/)
+{
+  __shared__ u64 wr[8], wg[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint4 c = reinterpret_cast<const uint4*>(count)[(size_t)blockIdx.x * 256 + t];
+  u64 rows = (u64)c.x + c.y + c.z + c.w;
+  u64 grp = (c.x != 0) + (c.y != 0) + (c.z != 0) + (c.w != 0);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { rows += __shfl_xor_sync(0xffffffffu, rows, d); grp += __shfl_xor_sync(0xffffffffu, grp, d); }
+  if (lane == 0) { wr[warp] = rows; wg[warp] = grp; }
+  __syncthreads();
+  if (t == 0) {
+    u64 r = 0, g = 0;
+    for (int w = 0; w < 8; w++) { r += wr[w]; g += wg[w]; }
+    bsum[2 * (size_t)blockIdx.x] = r; bsum[2 * (size_t)blockIdx.x + 1] = g;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+count_scan_sums_kernel(u64* bsum, int nb)          // in place: exclusive prefixes; nb <= 4096
+{
+  __shared__ u64 sr[1024], sg[1024];
+  const int t = threadIdx.x;
+  u64 r[4], g[4], tr = 0, tg = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int b = t * 4 + j;
+    r[j] = b < nb ? bsum[2 * b] : 0; g[j] = b < nb ? bsum[2 * b + 1] : 0;
+    tr += r[j]; tg += g[j];
+  }
+  sr[t] = tr; sg[t] = tg;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    u64 ar = 0, ag = 0;
+    if (t >= d) { ar = sr[t - d]; ag = sg[t - d]; }
+    __syncthreads();
+    sr[t] += ar; sg[t] += ag;
+    __syncthreads();
+  }
+  u64 er = sr[t] - tr, eg = sg[t] - tg;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int b = t * 4 + j;
+    if (b < nb) { bsum[2 * b] = er; bsum[2 * b + 1] = eg; }
+    er += r[j]; eg += g[j];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+count_compact_kernel(const u32* __restrict__ count, const u64* __restrict__ bsum, int64_t n, int nb,
+                     int32_t* __restrict__ offsets, u32* __restrict__ gkeys, u64* d_ngroups)
+{
+  __shared__ u64 wr[8], wg[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const uint4 cv = reinterpret_cast<const uint4*>(count)[(size_t)blockIdx.x * 256 + t];
+  const u32 c[4] = {cv.x, cv.y, cv.z, cv.w};
+  u64 rows = (u64)c[0] + c[1] + c[2] + c[3];
+  u64 grp = (c[0] != 0) + (c[1] != 0) + (c[2] != 0) + (c[3] != 0);
+  u64 ir = rows, ig = grp;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 a = __shfl_up_sync(0xffffffffu, ir, d), b = __shfl_up_sync(0xffffffffu, ig, d);
+    if (lane >= d) { ir += a; ig += b; }
+  }
+  if (lane == 31) { wr[warp] = ir; wg[warp] = ig; }
+  __syncthreads();
+  u64 pr = 0, pg = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) if (w < warp) { pr += wr[w]; pg += wg[w]; }
+  u64 r = bsum[2 * (size_t)blockIdx.x] + pr + ir - rows;          // rows before this thread's entries
+  u64 g = bsum[2 * (size_t)blockIdx.x + 1] + pg + ig - grp;       // groups before this thread's entries
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (c[j]) {
+      offsets[g] = (int32_t)r;
+      gkeys[g] = (u32)(((size_t)blockIdx.x * 256 + t) * 4 + j);
+      g++; r += c[j];
+    }
+  }
+  if (blockIdx.x == nb - 1 && t == 255) { *d_ngroups = g; offsets[g] = (int32_t)n; }
+}
+
+int launch_offsets_from_counts(const uint32_t* count, int64_t table, int64_t n, int32_t* offsets,
+                               uint32_t* gkeys, unsigned long long* d_ngroups, unsigned long long* scratch,
+                               cudaStream_t s)
+{
+  const int nb = (int)(table / CT_BLOCK);
+  if (nb < 1 || nb > 4096 || table % CT_BLOCK) { set_error("internal: bad count table size"); return DTB_EINVAL; }
+  count_block_sums_kernel<<<nb, 256, 0, s>>>(count, scratch);
+  count_scan_sums_kernel<<<1, 1024, 0, s>>>(scratch, nb);
+  count_compact_kernel<<<nb, 256, 0, s>>>(count, scratch, n, nb, offsets, gkeys, d_ngroups);
+  count_launch(3);
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
 int64_t offsets_num_tiles(int64_t n) {
   // the smallest tile (8-byte keys: 16 rows/thread) bounds the status array
   const int64_t tile = OFF_THREADS * 16;

@@ -102,9 +102,18 @@ struct PassIO {
 // hmax (optional, device): receives the largest digit count of the pass.
 size_t radix_pass_work_bytes(int64_t n);
 // after_counts (optional): recorded on `s` once the digit totals of the pass (hmax) are final.
+// group_count (optional, last pass only): uint32 table indexed by (key >> group_shift), zeroed by the
+// caller; receives the number of rows of every group key (see launch_offsets_from_counts).
 int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
                       int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s,
-                      cudaEvent_t after_counts = nullptr);
+                      cudaEvent_t after_counts = nullptr, uint32_t* group_count = nullptr, int group_shift = 0);
+
+// Groupby offsets from a per-group-key row count table (small key domains): offsets[] = exclusive
+// scan of the non-zero counts, gkeys[g] = key of group g, *d_ngroups = number of groups.
+// table must be a multiple of 1024 entries and at most 2^22; scratch: uint64[2 * table / 1024 + 2].
+int launch_offsets_from_counts(const uint32_t* count, int64_t table, int64_t n, int32_t* offsets,
+                               uint32_t* gkeys, unsigned long long* d_ngroups, unsigned long long* scratch,
+                               cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // Group offsets (replaces GroupGatherer, sort_groups.cc:34-117): heads where

@@ -180,6 +180,8 @@ struct PassArgs {
   const u32*     chunk_offs;    // [nchunks][NBINS] rows of this digit in earlier chunks
   const u32*     digit_base;    // [NBINS] first output slot of every digit
   const unsigned short* tile_counts;   // [ntiles][NBINS] rows of this digit in every tile
+  u32*           group_count;   // optional (last pass, small key domains): rows per group key
+  int            group_shift;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -354,19 +356,42 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
   else                scatter_tile<KeyT, Src, false>(a, smem_raw, s_wsum, base, tile_n, false);
 
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
+  const int lane = tid & 31;
 #pragma unroll 4
-  for (int p = tid; p < tile_n; p += THREADS) {
-    KeyT k; int32_t rid;
-    if constexpr (sizeof(KeyT) == 4) {
-      const uint2 kv = reinterpret_cast<const uint2*>(skey)[p];
-      k = (KeyT)kv.x; rid = (int32_t)kv.y;
-    } else {
-      k = skey[p]; rid = sidx[p];
+  for (int p0 = 0; p0 < tile_n; p0 += THREADS) {
+    const int p = p0 + tid;
+    const bool valid = p < tile_n;
+    KeyT k = 0; int32_t rid = 0;
+    if (valid) {
+      if constexpr (sizeof(KeyT) == 4) {
+        const uint2 kv = reinterpret_cast<const uint2*>(skey)[p];
+        k = (KeyT)kv.x; rid = (int32_t)kv.y;
+      } else {
+        k = skey[p]; rid = sidx[p];
+      }
     }
-    const u32 d = (u32)(k >> a.shift) & a.mask;
-    const u32 dst = bin_dst[d] + (u32)p;
-    if (a.keys_out) a.keys_out[dst] = k;
-    a.idx_out[dst] = rid;
+    if (a.group_count) {
+      // Last pass: the tile is sorted by the full composite key (its rows arrive sorted by the lower
+      // digits), so equal group keys are adjacent.  Every warp adds the lengths of the runs it sees
+      // to count[group key]; the Groupby offsets are then a scan over that L2-resident table
+      // instead of a pass over 4n bytes of sorted keys.
+      const u32 x = valid ? (u32)(k >> a.group_shift) : 0xffffffffu;
+      const u32 xprev = __shfl_up_sync(0xffffffffu, x, 1);
+      const bool head = valid && (lane == 0 || xprev != x);
+      const unsigned hm = __ballot_sync(0xffffffffu, head);
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
+      if (head) {
+        const unsigned above = hm & ~((2u << lane) - 1u);           // heads in higher lanes
+        const int end = above ? (__ffs(above) - 1) : __popc(vm);    // valid lanes form a prefix
+        atomicAdd(&a.group_count[x], (u32)(end - lane));
+      }
+    }
+    if (valid) {
+      const u32 d = (u32)(k >> a.shift) & a.mask;
+      const u32 dst = bin_dst[d] + (u32)p;
+      if (a.keys_out) a.keys_out[dst] = k;
+      a.idx_out[dst] = rid;
+    }
   }
 }
 
@@ -382,7 +407,7 @@ static constexpr size_t pass_smem_bytes() {
 
 template <typename KeyT, typename Src>
 static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax, cudaStream_t s,
-                    cudaEvent_t after_counts)
+                    cudaEvent_t after_counts, u32* group_count, int group_shift)
 {
   constexpr int MINB = PassCfg<KeyT>::MINB;
   if (n == 0) return DTB_OK;
@@ -408,7 +433,7 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
   PassArgs<KeyT, Src> a;
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
   a.n = n; a.shift = shift; a.mask = mask; a.chunk_offs = counts; a.digit_base = base;
-  a.tile_counts = tile_counts;
+  a.tile_counts = tile_counts; a.group_count = group_count; a.group_shift = group_shift;
   constexpr size_t smem = pass_smem_bytes<KeyT>();
   auto kern = scatter_kernel<KeyT, Src, MINB>;
   static bool configured = false;   // per instantiation
@@ -426,12 +451,13 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
 
 template <typename KeyT>
 static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shift, int bits,
-                        u32* work, u32* hmax, cudaStream_t s, cudaEvent_t after_counts)
+                        u32* work, u32* hmax, cudaStream_t s, cudaEvent_t after_counts,
+                        u32* group_count, int group_shift)
 {
   const KeyNorm& k = kp.k[0];
 #define DTB_CASE(T)                                                                          \
   { RawSrc<T, KeyT> src; src.init(k);                                                        \
-    return run_pass<KeyT>(src, io, n, shift, bits, work, hmax, s, after_counts); }
+    return run_pass<KeyT>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift); }
   switch (k.stype) {
     case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
     case DTB_STYPE_INT16:                        DTB_CASE(int16_t)
@@ -452,17 +478,17 @@ size_t radix_pass_work_bytes(int64_t n) {
 
 int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
                       int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s,
-                      cudaEvent_t after_counts)
+                      cudaEvent_t after_counts, uint32_t* group_count, int group_shift)
 {
   if (bits < 1 || bits > 8) { set_error("internal: digit width must be 1..8 bits"); return DTB_EINVAL; }
   if (io.src_kind == 0) {
     if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)io.keys_in};
-      return run_pass<u32>(src, io, n, shift, bits, work, hmax, s, after_counts); }
+      return run_pass<u32>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift); }
     else { PackedSrc<u64> src{(const u64*)io.keys_in};
-      return run_pass<u64>(src, io, n, shift, bits, work, hmax, s, after_counts); }
+      return run_pass<u64>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift); }
   }
-  return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, work, hmax, s, after_counts)
-                        : run_pass_raw<u64>(io, kp, n, shift, bits, work, hmax, s, after_counts);
+  return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift)
+                        : run_pass_raw<u64>(io, kp, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift);
 }
 
 __global__ void iota32_kernel(int32_t* out, int64_t n) {
