@@ -533,13 +533,15 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
 
     int32_t* round_out = last_round ? order : ((ri & 1) ? idxR1.as<int32_t>() : idxR0.as<int32_t>());
     const bool want_sorted_keys = last_round && do_groups && rounds[ri].has_by && !count_table;
-    void* kin = keyA.p; void* kout = fused_raw ? keyA.p : keyB.p;
+    // raw single column: the first count kernel materialises the normalised keys into keyA
+    void* kin = keyA.p; void* kout = keyB.p;
     const int32_t* iin = idx_cur;
     for (int p = 0; p < pp.npasses; p++) {
       const bool last = (p == pp.npasses - 1);
       PassIO io;
       io.src_kind = (p == 0) ? src_kind : 0;
       io.keys_in = kin;
+      io.keys_stage = (p == 0 && src_kind == 1) ? keyA.p : nullptr;
       io.idx_in = iin;
       io.keys_out = (last && !want_sorted_keys) ? nullptr : kout;
       int32_t* iout = last ? round_out : ((p & 1) ? idxB.as<int32_t>() : idxA.as<int32_t>());

@@ -96,6 +96,8 @@ struct PassIO {
   const int32_t* idx_in;
   void*       keys_out;     // may be NULL on the last pass of a sort-only call
   int32_t*    idx_out;
+  void*       keys_stage;   // src_kind 1 only, optional: buffer that receives the normalised keys in the
+                            // count kernel; the scatter kernel of the pass then reads them from there
 };
 
 // One stable pass = count + scan + scatter kernels.  work: radix_pass_work_bytes(n) of scratch;

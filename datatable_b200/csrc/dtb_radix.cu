@@ -78,8 +78,10 @@ int64_t radix_num_chunks(int64_t n) { return (n + CHUNK_ROWS - 1) / CHUNK_ROWS; 
 template <typename KeyT, typename Src>
 __global__ void __launch_bounds__(PASS_THREADS)
 count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u32* __restrict__ counts,
-             unsigned short* __restrict__ tile_counts)
+             unsigned short* __restrict__ tile_counts, KeyT* __restrict__ keys_out)
 {
+  // keys_out (first pass over a raw column): also store the normalised keys, so that the scatter
+  // kernel of this pass streams 32/64-bit keys like every later pass instead of re-normalising.
   __shared__ u32 h[PASS_NBINS];
   const int64_t cbase = (int64_t)blockIdx.x * CHUNK_ROWS;
   const int64_t cend = (cbase + CHUNK_ROWS < n) ? cbase + CHUNK_ROWS : n;
@@ -93,11 +95,18 @@ count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u3
       KeyT k[PASS_IPT];
 #pragma unroll
       for (int j = 0; j < PASS_IPT; j++) k[j] = src.load(base + threadIdx.x + j * PASS_THREADS);
+      if (keys_out) {
+#pragma unroll
+        for (int j = 0; j < PASS_IPT; j++) keys_out[base + threadIdx.x + j * PASS_THREADS] = k[j];
+      }
 #pragma unroll
       for (int j = 0; j < PASS_IPT; j++) atomicAdd(&h[(u32)(k[j] >> shift) & mask], 1u);
     } else {
-      for (int64_t i = base + threadIdx.x; i < end; i += PASS_THREADS)
-        atomicAdd(&h[(u32)(src.load(i) >> shift) & mask], 1u);
+      for (int64_t i = base + threadIdx.x; i < end; i += PASS_THREADS) {
+        const KeyT kk = src.load(i);
+        if (keys_out) keys_out[i] = kk;
+        atomicAdd(&h[(u32)(kk >> shift) & mask], 1u);
+      }
     }
     __syncthreads();
     const u32 c = h[threadIdx.x];
@@ -406,30 +415,11 @@ static constexpr size_t pass_smem_bytes() {
 }
 
 template <typename KeyT, typename Src>
-static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax, cudaStream_t s,
-                    cudaEvent_t after_counts, u32* group_count, int group_shift)
+static int run_scatter(Src src, const PassIO& io, int64_t n, int shift, u32 mask, int64_t ntiles,
+                       const u32* counts, const u32* base, const unsigned short* tile_counts,
+                       u32* group_count, int group_shift, cudaStream_t s)
 {
   constexpr int MINB = PassCfg<KeyT>::MINB;
-  if (n == 0) return DTB_OK;
-  if (io.idx_in && (reinterpret_cast<uintptr_t>(io.idx_in) & 15)) {
-    set_error("internal: row-id buffer must be 16-byte aligned"); return DTB_EINVAL;
-  }
-  const int64_t nchunks = radix_num_chunks(n);
-  const int64_t ntiles = (n + PASS_TILE - 1) / PASS_TILE;
-  u32* counts = work;                                   // [nchunks][NBINS], becomes chunk_offs in place
-  u32* total  = work + (size_t)nchunks * PASS_NBINS;    // [NBINS]
-  u32* base   = total + PASS_NBINS;                     // [NBINS]
-  unsigned short* tile_counts = reinterpret_cast<unsigned short*>(base + PASS_NBINS);   // [ntiles][NBINS]
-  const u32 mask = (1u << bits) - 1;
-
-  prof_begin("radix_count", s);
-  count_kernel<KeyT, Src><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts);
-  prof_end(s);
-  chunk_scan_kernel<<<PASS_NBINS, 256, 0, s>>>(counts, nchunks, total);
-  digit_base_kernel<<<1, 256, 0, s>>>(total, base, hmax);
-  count_launch(3);
-  if (after_counts) DTB_CUDA_CHECK(cudaEventRecord(after_counts, s));
-
   PassArgs<KeyT, Src> a;
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
   a.n = n; a.shift = shift; a.mask = mask; a.chunk_offs = counts; a.digit_base = base;
@@ -447,6 +437,41 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
+}
+
+template <typename KeyT, typename Src>
+static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax, cudaStream_t s,
+                    cudaEvent_t after_counts, u32* group_count, int group_shift)
+{
+  if (n == 0) return DTB_OK;
+  if (io.idx_in && (reinterpret_cast<uintptr_t>(io.idx_in) & 15)) {
+    set_error("internal: row-id buffer must be 16-byte aligned"); return DTB_EINVAL;
+  }
+  const int64_t nchunks = radix_num_chunks(n);
+  const int64_t ntiles = (n + PASS_TILE - 1) / PASS_TILE;
+  u32* counts = work;                                   // [nchunks][NBINS], becomes chunk_offs in place
+  u32* total  = work + (size_t)nchunks * PASS_NBINS;    // [NBINS]
+  u32* base   = total + PASS_NBINS;                     // [NBINS]
+  unsigned short* tile_counts = reinterpret_cast<unsigned short*>(base + PASS_NBINS);   // [ntiles][NBINS]
+  const u32 mask = (1u << bits) - 1;
+
+  prof_begin("radix_count", s);
+  count_kernel<KeyT, Src><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts,
+                                                                      (KeyT*)io.keys_stage);
+  prof_end(s);
+  chunk_scan_kernel<<<PASS_NBINS, 256, 0, s>>>(counts, nchunks, total);
+  digit_base_kernel<<<1, 256, 0, s>>>(total, base, hmax);
+  count_launch(3);
+  if (after_counts) DTB_CUDA_CHECK(cudaEventRecord(after_counts, s));
+
+  if (io.keys_stage) {
+    // the count kernel materialised the normalised keys: scatter from them
+    PassIO io2 = io; io2.src_kind = 0; io2.keys_in = io.keys_stage; io2.keys_stage = nullptr;
+    PackedSrc<KeyT> psrc{(const KeyT*)io.keys_stage};
+    return run_scatter<KeyT, PackedSrc<KeyT>>(psrc, io2, n, shift, mask, ntiles, counts, base, tile_counts,
+                                              group_count, group_shift, s);
+  }
+  return run_scatter<KeyT, Src>(src, io, n, shift, mask, ntiles, counts, base, tile_counts, group_count, group_shift, s);
 }
 
 template <typename KeyT>
