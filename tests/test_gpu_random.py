@@ -251,3 +251,34 @@ def test_fused_create_reduce_vs_oracle(small_domain):
             want = orc.reduce(OPS[op], v, want_o, want_f, stype=vst)
             assert_reducer_equal(got, want, op, vst, ctx=f"fused {op} small={small_domain}")
     gb.close()
+
+
+def test_rows_beyond_2_pow_30():
+    """n > 2^30 rows (the first look-back design was limited to 2^30): permutation + sortedness + group
+    count + sum total on device-resident data, checked with engine kernels and cheap torch reductions."""
+    import torch
+    from datatable_b200 import engine
+    free, _ = torch.cuda.mem_get_info()
+    n = 1_200_000_000
+    if free < 80e9:
+        pytest.skip("needs ~60 GB of free HBM")
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    k = torch.randint(-50_000, 50_000, (n,), generator=g, device="cuda", dtype=torch.int32)
+    v = torch.ones(n, device="cuda", dtype=torch.float64)
+    gb = engine.Groupby([k], [0], 1, reducers=[(OPS["sum"], v), (OPS["nrows"], None)])
+    assert gb.ngroups == 100_000
+    sums, cnt = gb.reduced(0), gb.reduced(1)
+    assert torch.equal(sums.long(), cnt) and int(cnt.sum()) == n
+    ks = engine.gather(k, gb.order_col())                     # keys in RowIndex order
+    assert bool((ks[1:] >= ks[:-1]).all())
+    offs = gb.offsets()
+    assert int(offs[-1]) == n and bool((offs[1:] > offs[:-1]).all())
+    heads = ks[offs[:-1].long()]
+    assert torch.equal(heads, torch.arange(-50_000, 50_000, device="cuda", dtype=torch.int32))
+    # stability: inside the first and the last group the row ids ascend
+    o = gb.order()
+    for a, b in ((0, int(offs[1])), (int(offs[-2]), n)):
+        seg = o[a:b]
+        assert bool((seg[1:] > seg[:-1]).all())
+    del o, ks
+    gb.close()
