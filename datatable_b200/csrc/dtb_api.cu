@@ -23,7 +23,7 @@ void count_launch(int n) { t_stats.kernels_launched += n; }
 // ---------------------------------------------------------------------------
 // options (analogue of dt.options.sort.*, sort.cc:259-349)
 // ---------------------------------------------------------------------------
-static int64_t opt_radix_bits = 8;
+static int64_t opt_radix_bits = 0;     // 0 = automatic (8, or 10 when that saves a pass)
 static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
 
@@ -461,8 +461,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   int max_bits = 0;
   for (auto& r : rounds) if (r.kp.total_bits > max_bits) max_bits = r.kp.total_bits;
   const int buf_key_bytes = max_bits <= 32 ? 4 : 8;
-  const int nbins_log2 = 8;
-  int width = (int)opt_radix_bits; if (width < 1) width = 1; if (width > nbins_log2) width = nbins_log2;
+  // digit width: 8 bits, or 10 bits when that saves a whole pass (option "radix_bits" overrides)
 
   if (opt_verbose) {
     fprintf(stderr, "[dtb200] group: n=%lld keys=%d bits=%d rounds=%d\n", (long long)n, nkeys, kp.total_bits, nrounds);
@@ -518,6 +517,12 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     const KeyPlan& rk = rounds[ri].kp;
     const bool last_round = (ri == nrounds - 1);
     const int key_bytes = rk.total_bits <= 32 ? 4 : 8;
+    int width = (int)opt_radix_bits;
+    if (width <= 0) {
+      const int p8 = (rk.total_bits + 7) / 8, p10 = (rk.total_bits + 9) / 10;
+      width = (p10 < p8) ? 10 : 8;
+    }
+    if (width > 10) width = 10;
     PassPlan pp; plan_passes(rk.total_bits, width, pp);
     t_stats.radix_passes += pp.npasses;
 
@@ -721,7 +726,7 @@ int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream stream) {
 int dtb_set_option(const char* name, int64_t value) {
   if (!name) { set_error("option name is NULL"); return DTB_EINVAL; }
   if (!strcmp(name, "radix_bits")) {
-    if (value < 1 || value > 8) { set_error("radix_bits must be in 1..8"); return DTB_EINVAL; }
+    if (value < 0 || value > 10) { set_error("radix_bits must be in 0..10 (0 = automatic)"); return DTB_EINVAL; }
     opt_radix_bits = value; return DTB_OK;
   }
   if (!strcmp(name, "verbose")) { opt_verbose = value; return DTB_OK; }

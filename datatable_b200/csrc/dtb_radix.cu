@@ -63,31 +63,37 @@ int launch_compose_keys(const KeyPlan& kp, int64_t n, const int32_t* idx, void* 
 // ===========================================================================
 // Pass geometry
 // ===========================================================================
-constexpr int PASS_NBINS = 256;              // digits are at most 8 bits wide
+// Two digit widths are built: 8 bits (256 bins) and 10 bits (1024 bins).  The planner takes 10-bit
+// digits when that saves a whole pass (20-bit keys: 2 passes instead of 3; 62-64-bit keys: 7 instead
+// of 8); a 10-bit pass costs ~20 % more shared-memory work per row than an 8-bit one.
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_IPT = 16;
 constexpr int PASS_TILE = PASS_THREADS * PASS_IPT;            // 4096 rows
 constexpr int CHUNK_TILES = 16;
-constexpr int CHUNK_ROWS = PASS_TILE * CHUNK_TILES;           // 65536 rows per CTA
+constexpr int CHUNK_ROWS = PASS_TILE * CHUNK_TILES;           // 65536 rows per count CTA
 
 int64_t radix_num_chunks(int64_t n) { return (n + CHUNK_ROWS - 1) / CHUNK_ROWS; }
 
 // ===========================================================================
-// count: counts[chunk][digit]
+// count: tile_counts[tile][digit] (u16) and counts[chunk][digit]
 // ===========================================================================
-template <typename KeyT, typename Src>
+template <typename KeyT, typename Src, int NBINS>
 __global__ void __launch_bounds__(PASS_THREADS)
 count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u32* __restrict__ counts,
              unsigned short* __restrict__ tile_counts, KeyT* __restrict__ keys_out)
 {
   // keys_out (first pass over a raw column): also store the normalised keys, so that the scatter
   // kernel of this pass streams 32/64-bit keys like every later pass instead of re-normalising.
-  __shared__ u32 h[PASS_NBINS];
+  constexpr int BPT = NBINS / PASS_THREADS;
+  __shared__ u32 h[NBINS];
   const int64_t cbase = (int64_t)blockIdx.x * CHUNK_ROWS;
   const int64_t cend = (cbase + CHUNK_ROWS < n) ? cbase + CHUNK_ROWS : n;
-  u32 total = 0;                                           // thread b: rows of digit b in this chunk
+  u32 total[BPT];                                          // rows of digit tid + j*THREADS in this chunk
+#pragma unroll
+  for (int j = 0; j < BPT; j++) total[j] = 0;
   for (int64_t base = cbase; base < cend; base += PASS_TILE) {
-    h[threadIdx.x] = 0;
+#pragma unroll
+    for (int j = 0; j < BPT; j++) h[threadIdx.x + j * PASS_THREADS] = 0;
     __syncthreads();
     const int64_t end = (base + PASS_TILE < cend) ? base + PASS_TILE : cend;
     if (end - base == PASS_TILE) {
@@ -109,11 +115,15 @@ count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u3
       }
     }
     __syncthreads();
-    const u32 c = h[threadIdx.x];
-    tile_counts[(size_t)(base / PASS_TILE) * PASS_NBINS + threadIdx.x] = (unsigned short)c;   // <= 4096
-    total += c;
+#pragma unroll
+    for (int j = 0; j < BPT; j++) {
+      const u32 c = h[threadIdx.x + j * PASS_THREADS];
+      tile_counts[(size_t)(base / PASS_TILE) * NBINS + threadIdx.x + j * PASS_THREADS] = (unsigned short)c;   // <= 4096
+      total[j] += c;
+    }
   }
-  counts[(size_t)blockIdx.x * PASS_NBINS + threadIdx.x] = total;
+#pragma unroll
+  for (int j = 0; j < BPT; j++) counts[(size_t)blockIdx.x * NBINS + threadIdx.x + j * PASS_THREADS] = total[j];
 }
 
 // ===========================================================================
@@ -121,7 +131,7 @@ count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u3
 // then base[digit] = exclusive scan of total[]; hmax = largest total (skew detector)
 // ===========================================================================
 __global__ void __launch_bounds__(256)
-chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, u32* __restrict__ total)
+chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, int nbins, u32* __restrict__ total)
 {
   __shared__ u32 wsum[8];
   __shared__ u32 s_carry;
@@ -130,7 +140,7 @@ chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, u32* __restrict__ t
   __syncthreads();
   for (int64_t c0 = 0; c0 < nchunks; c0 += 256) {
     const int64_t c = c0 + t;
-    const u32 v = (c < nchunks) ? counts[(size_t)c * PASS_NBINS + d] : 0;
+    const u32 v = (c < nchunks) ? counts[(size_t)c * nbins + d] : 0;
     u32 incl = v;
 #pragma unroll
     for (int k = 1; k < 32; k <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += o; }
@@ -140,7 +150,7 @@ chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, u32* __restrict__ t
 #pragma unroll
     for (int w = 0; w < 8; w++) if (w < warp) wpre += wsum[w];
     const u32 carry = s_carry;
-    if (c < nchunks) counts[(size_t)c * PASS_NBINS + d] = carry + wpre + incl - v;
+    if (c < nchunks) counts[(size_t)c * nbins + d] = carry + wpre + incl - v;
     __syncthreads();
     if (t == 255) s_carry = carry + wpre + incl;
     __syncthreads();
@@ -148,14 +158,18 @@ chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, u32* __restrict__ t
   if (t == 0) total[d] = s_carry;
 }
 
+template <int NBINS>
 __global__ void __launch_bounds__(256)
 digit_base_kernel(const u32* __restrict__ total, u32* __restrict__ base, u32* __restrict__ hmax)
 {
+  constexpr int BPT = NBINS / 256;                        // thread t owns digits t*BPT .. t*BPT+BPT-1
   __shared__ u32 wsum[8];
   __shared__ u32 wmax[8];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const u32 v = total[t];
-  u32 incl = v, m = v;
+  u32 v[BPT], tsum = 0, m = 0;
+#pragma unroll
+  for (int j = 0; j < BPT; j++) { v[j] = total[t * BPT + j]; tsum += v[j]; m = v[j] > m ? v[j] : m; }
+  u32 incl = tsum;
 #pragma unroll
   for (int k = 1; k < 32; k <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += o; }
 #pragma unroll
@@ -166,7 +180,9 @@ digit_base_kernel(const u32* __restrict__ total, u32* __restrict__ base, u32* __
   u32 wpre = 0;
 #pragma unroll
   for (int w = 0; w < 8; w++) if (w < warp) wpre += wsum[w];
-  base[t] = wpre + incl - v;
+  u32 e = wpre + incl - tsum;
+#pragma unroll
+  for (int j = 0; j < BPT; j++) { base[t * BPT + j] = e; e += v[j]; }
   if (t == 0 && hmax) {
     u32 mm = 0;
     for (int w = 0; w < 8; w++) mm = wmax[w] > mm ? wmax[w] : mm;
@@ -200,19 +216,33 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+template <typename KeyT, int NBINS> struct PassCfg {
+  static constexpr int WARPS = PASS_THREADS / 32;
+  // 256 bins: row ids are prefetched into shared memory with cp.async; 1024 bins: the tables take that
+  // space and the row ids are read straight from global memory in the reorder phase.
+  static constexpr bool USE_RIDX = (NBINS == 256);
+  static constexpr int MINB = (sizeof(KeyT) == 4) ? 4 : 3;
+  static constexpr size_t SMEM = sizeof(unsigned short) * WARPS * NBINS + sizeof(u32) * (NBINS + 4)
+                               + (sizeof(KeyT) + sizeof(int32_t)) * PASS_TILE
+                               + (USE_RIDX ? sizeof(int32_t) * PASS_TILE : 0);
+};
+
+// One tile per CTA.
 // Shared memory: whist[WARPS][NBINS] u16 | bin_dst[NBINS] u32 | skey[TILE] | sidx[TILE] | ridx[TILE]
-// (the per-warp peer-mask table of the rank phase aliases skey, idle until the reorder phase).
+// (the per-warp peer-mask table of the rank phase aliases skey/sidx, idle until the reorder phase).
 // With 32-bit keys the sorted tile is staged as interleaved (key, row id) pairs so that the
 // scattered shared-memory write of the reorder phase is ONE 8-byte store per row, not two
 // 4-byte stores: shared-memory wavefronts, not HBM, bound this kernel.
-// Registers hold the 16 keys of the thread, their 16-bit ranks and the running output offset of
-// the thread's digit; 64 registers / 53 KB -> 4 CTAs = 32 warps per SM.
-template <typename KeyT, typename Src, bool FULL>
+// Thread t owns the BPT = NBINS/256 consecutive digits t*BPT.. in the scan phase.
+template <typename KeyT, typename Src, int NBINS, bool FULL>
 __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsigned char* smem_raw, u32* s_wsum,
-                                             const int64_t base, const int tile_n, const bool prefetched)
+                                             const int64_t base, const int tile_n)
 {
-  constexpr int NBINS = PASS_NBINS, THREADS = PASS_THREADS, IPT = PASS_IPT, TILE = PASS_TILE;
+  constexpr int THREADS = PASS_THREADS, IPT = PASS_IPT, TILE = PASS_TILE;
   constexpr int WARPS = THREADS / 32;
+  constexpr int BPT = NBINS / THREADS;
+  constexpr bool USE_RIDX = PassCfg<KeyT, NBINS>::USE_RIDX;
+  static_assert(sizeof(u32) * WARPS * NBINS <= (sizeof(KeyT) + sizeof(int32_t)) * TILE, "mask table must fit the staging area");
   unsigned short* whist = reinterpret_cast<unsigned short*>(smem_raw);
   u32* bin_dst    = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
   KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);
@@ -223,14 +253,14 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool have_idx = a.idx_in != nullptr;
 
-  // ---- clear the per-warp digit counters and peer masks; fetch the row ids of a partial tile ----
+  // ---- clear the per-warp digit counters and peer masks; prefetch the row ids ----
   {
     u32* z = reinterpret_cast<u32*>(whist);
 #pragma unroll
     for (int j = 0; j < WARPS * NBINS / 2 / THREADS; j++) z[tid + j * THREADS] = 0;
 #pragma unroll
     for (int j = 0; j < WARPS * NBINS / THREADS; j++) wmask_all[tid + j * THREADS] = 0;
-    if (have_idx && !prefetched) {
+    if (USE_RIDX && have_idx) {
       const int32_t* g = a.idx_in + base;
       if (FULL) {
 #pragma unroll
@@ -278,17 +308,20 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
   }
   __syncthreads();
 
-  // ---- per digit (thread b owns digit b): prefix over warps, scan over digits, output offsets ----
-  const int b = tid;
-  u32 run = 0;
-  u32 cw[WARPS / 2];                                            // the warps' counts of digit b, two per register
+  // ---- per digit: prefix over warps, scan over digits, output offsets ----
+  const int b0 = tid * BPT;                                     // first of the thread's BPT consecutive digits
+  u32 run[BPT];
+#pragma unroll
+  for (int j = 0; j < BPT; j++) run[j] = 0;
 #pragma unroll
   for (int w = 0; w < WARPS; w++) {
-    const u32 c = whist[w * NBINS + b];
-    if (w & 1) cw[w >> 1] |= c << 16; else cw[w >> 1] = c;
-    run += c;
+#pragma unroll
+    for (int j = 0; j < BPT; j++) run[j] += whist[w * NBINS + b0 + j];
   }
-  u32 incl = run;
+  u32 tsum = 0;
+#pragma unroll
+  for (int j = 0; j < BPT; j++) tsum += run[j];
+  u32 incl = tsum;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const u32 o = __shfl_up_sync(0xffffffffu, incl, d);
@@ -299,17 +332,20 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
   u32 wpre = 0;
 #pragma unroll
   for (int w = 0; w < WARPS; w++) if (w < warp) wpre += s_wsum[w];
-  const u32 tstart = incl - run + wpre;                          // first slot of digit b inside the tile
-  {
-    u32 pre = tstart;                                            // tile slot of warp w's first row of digit b
+  u32 tstart = incl - tsum + wpre;                               // first tile slot of digit b0
+#pragma unroll
+  for (int j = 0; j < BPT; j++) {
+    u32 pre = tstart;                                            // tile slot of warp w's first row of digit b0+j
 #pragma unroll
     for (int w = 0; w < WARPS; w++) {
-      whist[w * NBINS + b] = (unsigned short)pre;
-      pre += (cw[w >> 1] >> (16 * (w & 1))) & 0xffffu;
+      const u32 c = whist[w * NBINS + b0 + j];
+      whist[w * NBINS + b0 + j] = (unsigned short)pre;
+      pre += c;
     }
+    bin_dst[b0 + j] -= tstart;                                   // was: the digit's first output slot (set by the caller)
+    tstart += run[j];
   }
-  bin_dst[b] -= tstart;                                         // holds the digit's first output slot (set by the caller)
-  if (have_idx && (FULL || prefetched)) cp_async_wait_all();
+  if (USE_RIDX && have_idx && FULL) cp_async_wait_all();
   __syncthreads();
 
   // ---- reorder the tile in shared memory ----
@@ -319,24 +355,25 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
     if (FULL || pos < tile_n) {
       const u32 d = (u32)(key[i] >> a.shift) & a.mask;
       const u32 lp = (u32)myhist[d] + ((rank2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-      const int32_t rid = have_idx ? ridx[pos] : (int32_t)(base + pos);
+      const int32_t r = !have_idx ? (int32_t)(base + pos) : (USE_RIDX ? ridx[pos] : a.idx_in[base + pos]);
       if constexpr (sizeof(KeyT) == 4) {
-        reinterpret_cast<uint2*>(skey)[lp] = make_uint2((u32)key[i], (u32)rid);      // pairs span skey+sidx
+        reinterpret_cast<uint2*>(skey)[lp] = make_uint2((u32)key[i], (u32)r);      // pairs span skey+sidx
       } else {
         skey[lp] = key[i];
-        sidx[lp] = rid;
+        sidx[lp] = r;
       }
     }
   }
   __syncthreads();
 }
 
-template <typename KeyT, typename Src, int MINB>
+template <typename KeyT, typename Src, int NBINS, int MINB>
 __global__ void __launch_bounds__(PASS_THREADS, MINB)
 scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
 {
-  constexpr int NBINS = PASS_NBINS, THREADS = PASS_THREADS, TILE = PASS_TILE;
+  constexpr int THREADS = PASS_THREADS, TILE = PASS_TILE;
   constexpr int WARPS = THREADS / 32;
+  constexpr int BPT = NBINS / THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ u32 s_wsum[WARPS];
   u32* bin_dst    = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
@@ -352,17 +389,20 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
   const int64_t chunk = tile / CHUNK_TILES;
   const int jt = (int)(tile % CHUNK_TILES);
 
-  // first output slot of digit `tid` for this tile: digit base + earlier chunks + earlier tiles of the chunk
-  u32 bin_run = a.digit_base[tid] + a.chunk_offs[(size_t)chunk * NBINS + tid];
-  {
-    const unsigned short* tc = a.tile_counts + (size_t)(chunk * CHUNK_TILES) * NBINS + tid;
+  // first output slot of the thread's digits for this tile: digit base + earlier chunks + earlier
+  // tiles of the chunk; parked in shared memory until the scan phase
+#pragma unroll
+  for (int j = 0; j < BPT; j++) {
+    const int b = tid * BPT + j;
+    u32 bin_run = a.digit_base[b] + a.chunk_offs[(size_t)chunk * NBINS + b];
+    const unsigned short* tc = a.tile_counts + (size_t)(chunk * CHUNK_TILES) * NBINS + b;
 #pragma unroll 4
     for (int t = 0; t < jt; t++) bin_run += (u32)tc[(size_t)t * NBINS];
+    bin_dst[b] = bin_run;
   }
-  bin_dst[tid] = bin_run;                                       // parked in shared memory until the scan phase
 
-  if (tile_n == TILE) scatter_tile<KeyT, Src, true >(a, smem_raw, s_wsum, base, tile_n, false);
-  else                scatter_tile<KeyT, Src, false>(a, smem_raw, s_wsum, base, tile_n, false);
+  if (tile_n == TILE) scatter_tile<KeyT, Src, NBINS, true >(a, smem_raw, s_wsum, base, tile_n);
+  else                scatter_tile<KeyT, Src, NBINS, false>(a, smem_raw, s_wsum, base, tile_n);
 
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
   const int lane = tid & 31;
@@ -404,28 +444,18 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
   }
 }
 
-template <typename KeyT> struct PassCfg;
-template <> struct PassCfg<u32> { static constexpr int MINB = 4; };
-template <> struct PassCfg<u64> { static constexpr int MINB = 3; };
-
-template <typename KeyT>
-static constexpr size_t pass_smem_bytes() {
-  return sizeof(unsigned short) * (PASS_THREADS / 32) * PASS_NBINS + sizeof(u32) * (PASS_NBINS + 4)
-       + (sizeof(KeyT) + 2 * sizeof(int32_t)) * PASS_TILE;
-}
-
-template <typename KeyT, typename Src>
+template <typename KeyT, typename Src, int NBINS>
 static int run_scatter(Src src, const PassIO& io, int64_t n, int shift, u32 mask, int64_t ntiles,
                        const u32* counts, const u32* base, const unsigned short* tile_counts,
                        u32* group_count, int group_shift, cudaStream_t s)
 {
-  constexpr int MINB = PassCfg<KeyT>::MINB;
+  constexpr int MINB = PassCfg<KeyT, NBINS>::MINB;
   PassArgs<KeyT, Src> a;
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
   a.n = n; a.shift = shift; a.mask = mask; a.chunk_offs = counts; a.digit_base = base;
   a.tile_counts = tile_counts; a.group_count = group_count; a.group_shift = group_shift;
-  constexpr size_t smem = pass_smem_bytes<KeyT>();
-  auto kern = scatter_kernel<KeyT, Src, MINB>;
+  constexpr size_t smem = PassCfg<KeyT, NBINS>::SMEM;
+  auto kern = scatter_kernel<KeyT, Src, NBINS, MINB>;
   static bool configured = false;   // per instantiation
   if (!configured) {
     DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -439,6 +469,38 @@ static int run_scatter(Src src, const PassIO& io, int64_t n, int shift, u32 mask
   return DTB_OK;
 }
 
+template <typename KeyT, typename Src, int NBINS>
+static int run_pass_nb(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax,
+                       cudaStream_t s, cudaEvent_t after_counts, u32* group_count, int group_shift)
+{
+  const int64_t nchunks = radix_num_chunks(n);
+  const int64_t ntiles = (n + PASS_TILE - 1) / PASS_TILE;
+  u32* counts = work;                                   // [nchunks][NBINS], becomes chunk_offs in place
+  u32* total  = work + (size_t)nchunks * NBINS;         // [NBINS]
+  u32* base   = total + NBINS;                          // [NBINS]
+  unsigned short* tile_counts = reinterpret_cast<unsigned short*>(base + NBINS);   // [ntiles][NBINS]
+  const u32 mask = (1u << bits) - 1;
+
+  prof_begin("radix_count", s);
+  count_kernel<KeyT, Src, NBINS><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts,
+                                                                             (KeyT*)io.keys_stage);
+  prof_end(s);
+  chunk_scan_kernel<<<NBINS, 256, 0, s>>>(counts, nchunks, NBINS, total);
+  digit_base_kernel<NBINS><<<1, 256, 0, s>>>(total, base, hmax);
+  count_launch(3);
+  if (after_counts) DTB_CUDA_CHECK(cudaEventRecord(after_counts, s));
+
+  if (io.keys_stage) {
+    // the count kernel materialised the normalised keys: scatter from them
+    PassIO io2 = io; io2.src_kind = 0; io2.keys_in = io.keys_stage; io2.keys_stage = nullptr;
+    PackedSrc<KeyT> psrc{(const KeyT*)io.keys_stage};
+    return run_scatter<KeyT, PackedSrc<KeyT>, NBINS>(psrc, io2, n, shift, mask, ntiles, counts, base, tile_counts,
+                                                     group_count, group_shift, s);
+  }
+  return run_scatter<KeyT, Src, NBINS>(src, io, n, shift, mask, ntiles, counts, base, tile_counts,
+                                       group_count, group_shift, s);
+}
+
 template <typename KeyT, typename Src>
 static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u32* work, u32* hmax, cudaStream_t s,
                     cudaEvent_t after_counts, u32* group_count, int group_shift)
@@ -447,31 +509,8 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
   if (io.idx_in && (reinterpret_cast<uintptr_t>(io.idx_in) & 15)) {
     set_error("internal: row-id buffer must be 16-byte aligned"); return DTB_EINVAL;
   }
-  const int64_t nchunks = radix_num_chunks(n);
-  const int64_t ntiles = (n + PASS_TILE - 1) / PASS_TILE;
-  u32* counts = work;                                   // [nchunks][NBINS], becomes chunk_offs in place
-  u32* total  = work + (size_t)nchunks * PASS_NBINS;    // [NBINS]
-  u32* base   = total + PASS_NBINS;                     // [NBINS]
-  unsigned short* tile_counts = reinterpret_cast<unsigned short*>(base + PASS_NBINS);   // [ntiles][NBINS]
-  const u32 mask = (1u << bits) - 1;
-
-  prof_begin("radix_count", s);
-  count_kernel<KeyT, Src><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts,
-                                                                      (KeyT*)io.keys_stage);
-  prof_end(s);
-  chunk_scan_kernel<<<PASS_NBINS, 256, 0, s>>>(counts, nchunks, total);
-  digit_base_kernel<<<1, 256, 0, s>>>(total, base, hmax);
-  count_launch(3);
-  if (after_counts) DTB_CUDA_CHECK(cudaEventRecord(after_counts, s));
-
-  if (io.keys_stage) {
-    // the count kernel materialised the normalised keys: scatter from them
-    PassIO io2 = io; io2.src_kind = 0; io2.keys_in = io.keys_stage; io2.keys_stage = nullptr;
-    PackedSrc<KeyT> psrc{(const KeyT*)io.keys_stage};
-    return run_scatter<KeyT, PackedSrc<KeyT>>(psrc, io2, n, shift, mask, ntiles, counts, base, tile_counts,
-                                              group_count, group_shift, s);
-  }
-  return run_scatter<KeyT, Src>(src, io, n, shift, mask, ntiles, counts, base, tile_counts, group_count, group_shift, s);
+  if (bits <= 8) return run_pass_nb<KeyT, Src, 256>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift);
+  return run_pass_nb<KeyT, Src, 1024>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift);
 }
 
 template <typename KeyT>
@@ -497,15 +536,16 @@ static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shif
 
 size_t radix_pass_work_bytes(int64_t n) {
   const size_t ntiles = (size_t)((n + PASS_TILE - 1) / PASS_TILE);
-  return sizeof(u32) * ((size_t)radix_num_chunks(n) * PASS_NBINS + 2 * PASS_NBINS)
-       + sizeof(unsigned short) * (ntiles + CHUNK_TILES) * PASS_NBINS;
+  const size_t nbins = 1024;                            // sized for the wider digit
+  return sizeof(u32) * ((size_t)radix_num_chunks(n) * nbins + 2 * nbins)
+       + sizeof(unsigned short) * (ntiles + CHUNK_TILES) * nbins;
 }
 
 int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_t n,
                       int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s,
                       cudaEvent_t after_counts, uint32_t* group_count, int group_shift)
 {
-  if (bits < 1 || bits > 8) { set_error("internal: digit width must be 1..8 bits"); return DTB_EINVAL; }
+  if (bits < 1 || bits > 10) { set_error("internal: digit width must be 1..10 bits"); return DTB_EINVAL; }
   if (io.src_kind == 0) {
     if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)io.keys_in};
       return run_pass<u32>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift); }

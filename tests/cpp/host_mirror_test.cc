@@ -1,0 +1,52 @@
+// C++ host mirror (include/dtb200.hpp) exercised the way the reference's group() is used
+// (src/core/expr/eval_context.cc:249-288): built by __graft_entry__.build(), run by
+// tests/test_gpu_cpp.py on the GPU box.  Prints "OK" on success.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <vector>
+#include "dtb200.hpp"
+
+int main() {
+  const size_t n = 200000;
+  std::vector<int32_t> k(n); std::vector<double> v(n);
+  uint64_t x = 88172645463325252ull;
+  for (size_t i = 0; i < n; i++) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    k[i] = (x % 97 == 0) ? INT32_MIN : int32_t(x % 1000) - 500;      // NA keys form the first group
+    v[i] = double((x >> 20) % 1000) / 8.0;
+  }
+  try {
+    dtb::Column kc(k.data(), dtb::SType::INT32, n), vc(v.data(), dtb::SType::FLOAT64, n);
+    dtb::RiGb rg = dtb::group({kc}, {dtb::SortFlag::NONE});
+    const dtb::RowIndex& ri = rg.first; const dtb::Groupby& gb = rg.second;
+    if (!gb || ri.size() != n) { printf("FAIL: no groupby\n"); return 1; }
+    // reference semantics: NA first, ascending keys, stable inside groups
+    std::map<int64_t, std::pair<double, int64_t>> want;             // key -> (sum, count); NA as INT64_MIN
+    for (size_t i = 0; i < n; i++) { auto& w = want[k[i] == INT32_MIN ? INT64_MIN : k[i]]; w.first += v[i]; w.second++; }
+    if (gb.size() != want.size()) { printf("FAIL: ngroups %zu vs %zu\n", gb.size(), want.size()); return 1; }
+    std::vector<double> sums = dtb::reduce<double>(DTB_OP_SUM, vc, ri, gb);
+    std::vector<int64_t> cnts = dtb::reduce<int64_t>(DTB_OP_NROWS, vc, ri, gb);
+    size_t g = 0;
+    for (auto& kv : want) {
+      size_t i0, i1; gb.get_group(g, &i0, &i1);
+      for (size_t p = i0; p < i1; p++) {
+        const int32_t kk = k[size_t(ri[p])];
+        if ((kk == INT32_MIN ? INT64_MIN : int64_t(kk)) != kv.first) { printf("FAIL: key order at group %zu\n", g); return 1; }
+        if (p > i0 && ri[p] <= ri[p - 1]) { printf("FAIL: stability at group %zu\n", g); return 1; }
+      }
+      if (cnts[g] != kv.second.second || std::fabs(sums[g] - kv.second.first) > 1e-9 * std::fabs(kv.second.first) + 1e-9) {
+        printf("FAIL: reducer at group %zu\n", g); return 1;
+      }
+      g++;
+    }
+    // unsupported stype -> NotImplError, like sort.cc:673
+    bool threw = false;
+    try { dtb::Column sc(k.data(), static_cast<dtb::SType>(11), n); dtb::group({sc}, {dtb::SortFlag::NONE}); }
+    catch (const dtb::NotImplError&) { threw = true; }
+    if (!threw) { printf("FAIL: str32 key did not raise NotImplError\n"); return 1; }
+  } catch (const dtb::Error& e) { printf("FAIL: %s\n", e.what()); return 1; }
+  printf("OK\n");
+  return 0;
+}

@@ -47,10 +47,10 @@ def test_pure_host_queries():
 
 def test_options_roundtrip():
     from datatable_b200 import engine
-    assert engine.get_option("radix_bits") == 8
+    assert engine.get_option("radix_bits") == 0
     engine.set_option("radix_bits", 7)
     assert engine.get_option("radix_bits") == 7
-    engine.set_option("radix_bits", 8)
+    engine.set_option("radix_bits", 0)
     with pytest.raises(ValueError):
         engine.set_option("radix_bits", 99)
     with pytest.raises(ValueError):

@@ -282,3 +282,22 @@ def test_rows_beyond_2_pow_30():
         assert bool((seg[1:] > seg[:-1]).all())
     del o, ks
     gb.close()
+
+
+@pytest.mark.parametrize("bits", [3, 8, 10])
+def test_digit_width_option_gives_identical_results(bits):
+    """The RowIndex / offsets must not depend on the digit width of the passes (256- and 1024-bin kernels)."""
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    rng = np.random.default_rng(bits)
+    n = 300_000
+    cases = [(make_col(rng, INT32, n, "unit", 0.02), INT32), (make_col(rng, FLOAT64, n, "wide", 0.02), FLOAT64),
+             (make_col(rng, INT64, n, "wide", 0.0), INT64)]
+    engine.set_option("radix_bits", bits)
+    try:
+        for k, st in cases:
+            want_o, want_f, want_ng = orc.group([k], [0], 1, stypes=[st])
+            got_o, got_f, got_ng = engine.group([engine.Col(k, st)], [0], 1)
+            assert np.array_equal(got_o, want_o) and np.array_equal(got_f, want_f) and got_ng == want_ng
+    finally:
+        engine.set_option("radix_bits", 0)
