@@ -237,8 +237,11 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- sanity: the sums are the column total (cheap size-independent check, not timed) ----
     tot = float(out[3].sum().item())
-    ref_tot = float(v.sum().item()) if world == 1 else None
-    if ref_tot is not None and abs(tot - ref_tot) > 1e-6 * abs(ref_tot):
+    vsum = v.sum()
+    if world > 1:
+        dist.all_reduce(vsum)                   # the merged sums cover every rank's partition
+    ref_tot = float(vsum.item())
+    if abs(tot - ref_tot) > 1e-6 * abs(ref_tot):
         raise SystemExit(f"bench.py: group sums do not add up: {tot} vs {ref_tot}")
 
     # ---- roofline of the dominant kernel: the radix scatter passes --------------------------
@@ -300,6 +303,11 @@ def run_b200(args, rank, local_rank, world):
 
         def e2e_step():
             R = DT[:, dtb.sum(f.v), by(f.k)]
+            if world > 1:                                   # merge the per-rank result frames over NCCL
+                gk = torch.from_numpy(R.to_numpy("k")).cuda()
+                gs = torch.from_numpy(R.to_numpy("v")).cuda()
+                gk, gs = ddist.merge_partials(gk, gs, _lib.OP_SUM)
+                gs.cpu()
             return R
         e2e_step()
         barrier()

@@ -213,8 +213,8 @@ DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream st
 
 /*
  * Engine options, the analogue of dt.options.sort.* (sort.cc:259-349).
- *   "radix_bits"   largest digit width of the LSD passes: 1..10, or 0 (default) = automatic:
- *                  8 bits, or 10 bits when that saves a whole pass
+ *   "radix_bits"   largest digit width of the LSD passes: 4..10, or 0 (default) = 8 bits
+ *                  (9-10 bits use the 1024-bin kernels: fewer passes, each ~2x as expensive)
  *   "verbose"      1 = print the pass plan to stderr
  *   "profile"      1 = bracket every kernel with CUDA events on the call's stream
  *   "trim_scratch" (set only) release the calling thread's cached HBM scratch slab

@@ -284,7 +284,7 @@ def test_rows_beyond_2_pow_30():
     gb.close()
 
 
-@pytest.mark.parametrize("bits", [3, 8, 10])
+@pytest.mark.parametrize("bits", [4, 8, 10])
 def test_digit_width_option_gives_identical_results(bits):
     """The RowIndex / offsets must not depend on the digit width of the passes (256- and 1024-bin kernels)."""
     from datatable_b200 import engine
