@@ -8,9 +8,16 @@ one NCCL all-gather, and the same group()/reduce() kernels merge them.  Sums,
 counts, minima and maxima are associative, so the merged result equals the
 single-GPU result on the concatenated rows (float sums up to association).
 
-No row ever crosses NVLink: the exchange moves 12-16 bytes per *group*.
-The global RowIndex of a partitioned frame needs the radix-bucket all-to-all
-(north star, config 5) and is not built yet.
+Two exchanges are built on the same kernels:
+
+* `merge_partials`           all-gather of (key, partial) lists; every rank ends with the full result.
+                             Moves 12-16 bytes per *group*; right when ngroups is small (C2).
+* `merge_partials_alltoall`  key-range all-to-all of the partial lists: rank r ends with the r-th key
+                             range of the result (nothing is replicated); right when ngroups is large (C5).
+* `sort_partitioned`         global ordering of a row-partitioned key column: local sort, sample
+                             splitters, NCCL all-to-all of (key, global row id) runs, local merge-sort.
+                             Rank r ends with the r-th key range of the global RowIndex (int64 row ids,
+                             the ARR64 case the reference cannot represent, SURVEY.md mismatch 3).
 """
 import torch
 import torch.distributed as dist
@@ -34,6 +41,7 @@ class _EngineKernels:
     """The product path: libdtb200.so kernels.  (tests/ swap in an oracle-backed object to run the
     exchange logic under gloo on CPU.)"""
     group = staticmethod(lambda keys: engine.group([keys], [0], _lib.NA_FIRST))
+    sort = staticmethod(lambda keys: engine.group([keys], [_lib.FLAG_SORT_ONLY], _lib.NA_FIRST)[0])
     reduce = staticmethod(lambda op, v, order, offsets: engine.reduce(op, v, order, offsets))
     take = staticmethod(lambda src, idx: engine.gather(src, idx))
 
@@ -63,9 +71,92 @@ def merge_partials(gkeys, part, op, group=None, kernels=_EngineKernels):
     return kernels.take(kall, first), merged
 
 
-def groupby_partitioned(k, v, op=_lib.OP_SUM, group=None):
-    """DT[:, op(f.v), by(f.k)] over a frame row-partitioned across the ranks of `group`."""
+def groupby_partitioned(k, v, op=_lib.OP_SUM, group=None, exchange="allgather"):
+    """DT[:, op(f.v), by(f.k)] over a frame row-partitioned across the ranks of `group`.
+    exchange="allgather": every rank gets all groups; "alltoall": rank r gets the r-th key range."""
     gkeys, part = local_groupby(k, v, op)
     if dist.is_available() and dist.is_initialized():
+        if exchange == "alltoall":
+            return merge_partials_alltoall(gkeys, part, op, group)
         return merge_partials(gkeys, part, op, group)
     return gkeys, part
+
+
+# ---------------------------------------------------------------------------
+# key-range all-to-all
+# ---------------------------------------------------------------------------
+def _splitters(sorted_keys, world, group=None):
+    """world-1 global splitters from evenly spaced samples of every rank's sorted keys."""
+    n = sorted_keys.numel()
+    nsamp = 4 * world
+    if n > 0:
+        pos = torch.linspace(0, n - 1, nsamp, device=sorted_keys.device).long()
+        samp = sorted_keys[pos]
+    else:
+        samp = torch.zeros(nsamp, dtype=sorted_keys.dtype, device=sorted_keys.device)
+    have = torch.tensor([1 if n > 0 else 0], dtype=torch.int64, device=sorted_keys.device)
+    allsamp = torch.empty(world * nsamp, dtype=sorted_keys.dtype, device=sorted_keys.device)
+    allhave = torch.empty(world, dtype=torch.int64, device=sorted_keys.device)
+    dist.all_gather_into_tensor(allsamp, samp, group=group)
+    dist.all_gather_into_tensor(allhave, have, group=group)
+    keep = allhave.repeat_interleave(nsamp).bool()
+    pool = torch.sort(allsamp[keep]).values                  # <= 4*world^2 values: plumbing, not the hot path
+    if pool.numel() == 0:
+        return torch.zeros(world - 1, dtype=sorted_keys.dtype, device=sorted_keys.device)
+    q = (torch.arange(1, world, device=pool.device) * pool.numel()) // world
+    return pool[q]
+
+
+def _exchange(sorted_keys, payloads, world, group=None):
+    """Cut the locally sorted run at the global splitters and all-to-all the pieces.
+    Returns (received keys, received payloads): source-rank-major, each piece still sorted."""
+    spl = _splitters(sorted_keys, world, group)
+    cuts = torch.searchsorted(sorted_keys, spl, right=False)      # rows with key < splitter go left
+    bounds = torch.cat([torch.zeros(1, dtype=cuts.dtype, device=cuts.device), cuts,
+                        torch.tensor([sorted_keys.numel()], dtype=cuts.dtype, device=cuts.device)])
+    send = (bounds[1:] - bounds[:-1]).to(torch.int64)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = send.tolist(), recv.tolist()
+    nrecv = sum(recv_l)
+
+    def a2a(x):
+        out = torch.empty(nrecv, dtype=x.dtype, device=x.device)
+        dist.all_to_all_single(out, x.contiguous(), output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+        return out
+    return a2a(sorted_keys), [a2a(p) for p in payloads]
+
+
+def merge_partials_alltoall(gkeys, part, op, group=None, kernels=_EngineKernels):
+    """Key-range all-to-all of per-group partials; `gkeys` must be ascending (as group() returns them).
+    Rank r ends with the groups whose keys fall into the r-th global key range."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return gkeys, part
+    rk, (rp,) = _exchange(gkeys, [part], world, group)
+    if rk.numel() == 0:
+        return rk, rp
+    order, offsets, ng = kernels.group(rk)
+    merged = kernels.reduce(_MERGE_OP[op], rp, order, offsets)
+    first = kernels.take(order, offsets[:-1])
+    return kernels.take(rk, first), merged
+
+
+def sort_partitioned(k, row_offset, group=None, kernels=_EngineKernels):
+    """Global stable ordering of an integer key column row-partitioned over the ranks
+    (rank r holds global rows [row_offset, row_offset + len(k))).
+
+    Returns (keys, row_ids): this rank's slice of the globally sorted sequence -- rank 0 holds the
+    smallest keys -- with int64 GLOBAL row ids; concatenated over ranks this is the ARR64 RowIndex.
+    Ties keep ascending global row id (local sorts are stable, the exchange is source-rank-major)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    order = kernels.sort(k)
+    ks = kernels.take(k, order)
+    ids = order.to(torch.int64) + int(row_offset)
+    if world == 1:
+        return ks, ids
+    rk, (rid,) = _exchange(ks, [ids], world, group)
+    if rk.numel() == 0:
+        return rk, rid
+    order2 = kernels.sort(rk)
+    return kernels.take(rk, order2), kernels.take(rid, order2)

@@ -19,6 +19,11 @@ class OracleKernels:
         return torch.from_numpy(o), torch.from_numpy(f), ng
 
     @staticmethod
+    def sort(keys):
+        from oracle import oracle as orc
+        return torch.from_numpy(orc.group([keys.numpy()], [orc.SORT_ONLY], orc.NA_FIRST)[0])
+
+    @staticmethod
     def reduce(op, v, order, offsets):
         from oracle import oracle as orc
         return torch.from_numpy(orc.reduce(op, v.numpy(), order.numpy(), offsets.numpy()))
@@ -44,7 +49,13 @@ def _worker(rank, world, port, q):
         gkeys = k[o[f[:-1]]]
         mk, mv = ddist.merge_partials(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
                                       kernels=OracleKernels)
-        q.put((rank, k, v, mk.numpy(), mv.numpy()))
+        ak, av = ddist.merge_partials_alltoall(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
+                                               kernels=OracleKernels)
+        k64 = rng.integers(-10**12, 10**12, n).astype(np.int64)
+        k64[::9] = k64[0]                             # ties across ranks: stability must hold globally
+        row0 = 0 if rank == 0 else 5000
+        sk, sid = ddist.sort_partitioned(torch.from_numpy(k64), row0, kernels=OracleKernels)
+        q.put((rank, k, v, mk.numpy(), mv.numpy(), ak.numpy(), av.numpy(), k64, sk.numpy(), sid.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -67,3 +78,13 @@ def test_merge_partials_world2():
     for r in res:                                   # every rank holds the full merged result
         assert np.array_equal(r[3], uk)
         assert np.allclose(r[4], want, rtol=1e-12)
+    # all-to-all variant: the ranks hold disjoint ascending key ranges that concatenate to the result
+    ak = np.concatenate([r[5] for r in res]); av = np.concatenate([r[6] for r in res])
+    assert np.array_equal(ak, uk) and np.allclose(av, want, rtol=1e-12)
+    assert len(res[0][5]) > 0 and len(res[1][5]) > 0
+    # distributed sort: concatenated slices == stable argsort of the concatenated column (global row ids)
+    kcat = np.concatenate([r[7] for r in res])
+    want_ids = np.argsort(kcat, kind="stable")
+    got_ids = np.concatenate([r[9] for r in res]); got_keys = np.concatenate([r[8] for r in res])
+    assert got_ids.dtype == np.int64
+    assert np.array_equal(got_ids, want_ids) and np.array_equal(got_keys, kcat[want_ids])
