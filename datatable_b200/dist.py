@@ -90,7 +90,7 @@ def _splitters(sorted_keys, world, group=None):
     n = sorted_keys.numel()
     nsamp = 4 * world
     if n > 0:
-        pos = torch.linspace(0, n - 1, nsamp, device=sorted_keys.device).long()
+        pos = (torch.arange(nsamp, device=sorted_keys.device, dtype=torch.int64) * (n - 1)) // (nsamp - 1)
         samp = sorted_keys[pos]
     else:
         samp = torch.zeros(nsamp, dtype=sorted_keys.dtype, device=sorted_keys.device)
