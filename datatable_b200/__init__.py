@@ -8,6 +8,6 @@ library has not been built.  There is no CPU fallback.
 from . import _lib
 from ._lib import (DtbError, DtbValueError, DtbNotImplError, DtbCudaError, DtbMemoryError)
 from . import engine
-from .frame import Frame, f, by, sort, sum, mean, min, max, count, countna   # noqa: A004
+from .frame import Frame, f, by, sort, sum, mean, min, max, count, countna, unique, nunique   # noqa: A004
 
-__all__ = ["engine", "Frame", "f", "by", "sort", "sum", "mean", "min", "max", "count", "countna", "DtbError", "DtbValueError", "DtbNotImplError", "DtbCudaError", "DtbMemoryError"]
+__all__ = ["engine", "Frame", "f", "by", "sort", "sum", "mean", "min", "max", "count", "countna", "unique", "nunique", "DtbError", "DtbValueError", "DtbNotImplError", "DtbCudaError", "DtbMemoryError"]

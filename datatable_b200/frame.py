@@ -426,3 +426,43 @@ def _reduce(dcol, e, order, offsets):
     if e.op == _lib.OP_NROWS:
         return engine.reduce(e.op, None, order, offsets)
     return engine.reduce(e.op, dcol(e.arg.name), order, offsets)
+
+
+# ---------------------------------------------------------------------------
+# First consumers of group() beyond DT[i, j, by, sort]
+# ---------------------------------------------------------------------------
+def unique(frame):
+    """dt.unique(frame): the sorted unique values (NA first) of a single-column frame --
+    group() + first row of every group, as src/core/set_funcs.cc:100-140 does."""
+    if frame.ncols != 1:
+        raise NotImplementedError("unique() of a multi-column frame (set union) is outside the GPU hot path")
+    name = frame.names[0]
+    c = frame._col(name)
+    host = not (engine.is_tensor(c.data) and c.data.is_cuda)
+    t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
+    cd = engine.Col(t if t.is_cuda else t.cuda(), c.stype)
+    gb = engine.Groupby([cd], [0], NA_FIRST)
+    vals = engine.gather(cd, gb.first_rows())
+    gb.close()
+    out = Frame()
+    out._cols[name] = vals.cpu().numpy() if host else vals
+    out._stypes[name] = c.stype
+    out._nrows = int(vals.shape[0])
+    return out
+
+
+def nunique(frame):
+    """Frame.nunique(): number of distinct non-NA values per column (stats.cc:949-1010 via group())."""
+    out = Frame()
+    for name in frame.names:
+        c = frame._col(name)
+        t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
+        cd = engine.Col(t if t.is_cuda else t.cuda(), c.stype)
+        gb = engine.Groupby([cd], [0], NA_FIRST, reducers=[(_lib.OP_COUNT, cd)])
+        valid = gb.reduced(0)                      # groups whose key is NA have count(key) == 0
+        n = int((valid > 0).sum().item()) if gb.ngroups > 0 else 0
+        gb.close()
+        out._cols[name] = np.array([n], dtype=np.int64)
+        out._stypes[name] = INT64
+    out._nrows = 1
+    return out

@@ -155,3 +155,11 @@ def test_device_frame_stays_on_device():
 def engine_is_cuda(x):
     import torch
     return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def test_unique_and_nunique():               # tests/test-sets.py (unique), tests/test-dt-stats.py (nunique)
+    dt = dtmod()
+    DT = dt.Frame(A=[3, 1, None, 3, 2, None, 1, 7])
+    assert dt.unique(DT).to_list() == [[None, 1, 2, 3, 7]]
+    DF = dt.Frame(A=[3, 1, None, 3, 2, None, 1, 7], B=[0.5, float("nan"), 0.5, -0.0, 0.0, 1.5, 1.5, 0.5])
+    assert dt.nunique(DF).to_list() == [[4], [4]]       # -0.0 and +0.0 are distinct keys (bit pattern order)
