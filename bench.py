@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -256,9 +256,11 @@ def run_b200(args, rank, local_rank, world):
     passes = fam.get("radix_scatter", [])
     npass_step = len(passes) // max(1, args.steps)
     # algorithmic bytes of one scatter launch over n rows (32-bit keys, int32 row ids):
-    #   first pass : read raw key 4            + write (key 4 + idx 4)  = 12 B/row
-    #   later pass : read (key 4 + idx 4)      + write (key 4 + idx 4)  = 16 B/row
-    pass_bytes = [12.0 * n] + [16.0 * n] * max(0, npass_step - 1)
+    #   first pass : read key 4 (row id = position) + write (key 4 + idx 4)  = 12 B/row
+    #   middle pass: read (key 4 + idx 4)           + write (key 4 + idx 4)  = 16 B/row
+    #   last pass  : read (key 4 + idx 4)           + write idx 4            = 12 B/row
+    #                (small key domain: group sizes go to the count table, the sorted keys are not written)
+    pass_bytes = ([12.0 * n] + [16.0 * n] * max(0, npass_step - 2) + [12.0 * n]) if npass_step >= 2 else [8.0 * n]
     alg_bytes_launch = sum(pass_bytes) / max(1, npass_step)
     pass_ms = sum(passes) / max(1, len(passes))
     achieved = alg_bytes_launch / (pass_ms / 1e3) / 1e9 if passes else None

@@ -217,6 +217,8 @@ DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream st
  *                  (9-10 bits use the 1024-bin kernels: fewer passes, each ~2x as expensive)
  *   "verbose"      1 = print the pass plan to stderr
  *   "profile"      1 = bracket every kernel with CUDA events on the call's stream
+ *   "overlap_reducers" 1 = dtb_groupby_create_reduce runs the direct-address reducers on a side stream
+ *                  concurrently with the sort passes (default 0: same stream, measured equally fast)
  *   "trim_scratch" (set only) release the calling thread's cached HBM scratch slab
  */
 DTB_API int dtb_set_option(const char* name, int64_t value);

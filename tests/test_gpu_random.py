@@ -223,14 +223,16 @@ def test_groupby_handle_multikey_direct():
     gb.close()
 
 
+@pytest.mark.parametrize("overlap", [0, 1])
 @pytest.mark.parametrize("small_domain", [True, False])
-def test_fused_create_reduce_vs_oracle(small_domain):
+def test_fused_create_reduce_vs_oracle(small_domain, overlap):
     """dtb_groupby_create_reduce: reducers evaluated inside the group() call (side-stream overlap for
     small key domains, RowIndex path otherwise) must equal separate group + reduce."""
     import torch
     from datatable_b200 import engine
     from oracle import oracle as orc
     n = 600_000
+    engine.set_option("overlap_reducers", overlap)
     rng = np.random.default_rng(5 + small_domain)
     k = make_col(rng, INT32, n, "few" if small_domain else "wide", 0.03)
     v1 = make_col(rng, FLOAT64, n, "unit", 0.1)
@@ -251,6 +253,7 @@ def test_fused_create_reduce_vs_oracle(small_domain):
             want = orc.reduce(OPS[op], v, want_o, want_f, stype=vst)
             assert_reducer_equal(got, want, op, vst, ctx=f"fused {op} small={small_domain}")
     gb.close()
+    engine.set_option("overlap_reducers", 0)
 
 
 def test_rows_beyond_2_pow_30():
