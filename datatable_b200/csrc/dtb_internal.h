@@ -98,6 +98,7 @@ struct PassIO {
   int32_t*    idx_out;
   void*       keys_stage;   // src_kind 1 only, optional: buffer that receives the normalised keys in the
                             // count kernel; the scatter kernel of the pass then reads them from there
+  const void* hybrid = nullptr;   // src_kind 1 only: HybridKey* -- sort key = hybrid_top(key) (dtb_tiefix.cu)
 };
 
 // One stable pass = count + scan + scatter kernels.  work: radix_pass_work_bytes(n) of scratch;
@@ -160,5 +161,12 @@ int launch_gather(const void* src, int stype, int64_t nrows_src, const void* ord
                   int order_is64, int64_t n, void* out, cudaStream_t s);
 
 int launch_iota32(int32_t* out, int64_t n, cudaStream_t s);
+
+// Hybrid sort of wide single keys: order rows that tie on the top key bits by their low bits
+// (dtb_tiefix.cu).  counters: device uint32[2] = {long runs, fallback flag}.
+int launch_tie_fix(const uint32_t* top_keys, int32_t* order, int64_t begin, int64_t end, const KeyNorm& k,
+                   int low_bits, uint32_t* long_list, uint32_t long_cap, uint32_t* counters, cudaStream_t s);
+// Histogram of the leading 12 bits of the normalised key of one raw column (hist: uint32[4096], zeroed here).
+int launch_top12_histogram(const KeyNorm& k, int total_bits, int64_t n, uint32_t* hist, cudaStream_t s);
 
 }  // namespace dtb

@@ -520,7 +520,7 @@ static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shif
 {
   const KeyNorm& k = kp.k[0];
 #define DTB_CASE(T)                                                                          \
-  { RawSrc<T, KeyT> src; src.init(k);                                                        \
+  { RawSrc<T, KeyT> src; src.init(k, (const HybridKey*)io.hybrid);                           \
     return run_pass<KeyT>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift); }
   switch (k.stype) {
     case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)
