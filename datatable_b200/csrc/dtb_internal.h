@@ -99,6 +99,7 @@ struct PassIO {
   void*       keys_stage;   // src_kind 1 only, optional: buffer that receives the normalised keys in the
                             // count kernel; the scatter kernel of the pass then reads them from there
   const void* hybrid = nullptr;   // src_kind 1 only: HybridKey* -- sort key = hybrid_top(key) (dtb_tiefix.cu)
+  int         narrow_out = 0;     // 64-bit keys, > 0: keys_out receives (key >> narrow_out) as uint32 (later passes run on 32-bit keys)
 };
 
 // One stable pass = count + scan + scatter kernels.  work: radix_pass_work_bytes(n) of scratch;

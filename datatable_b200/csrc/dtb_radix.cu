@@ -207,6 +207,7 @@ struct PassArgs {
   const unsigned short* tile_counts;   // [ntiles][NBINS] rows of this digit in every tile
   u32*           group_count;   // optional (last pass, small key domains): rows per group key
   int            group_shift;
+  int            narrow;        // 64-bit keys only, > 0: write (key >> narrow) as uint32 -- the low bits are consumed
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -438,7 +439,12 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
     if (valid) {
       const u32 d = (u32)(k >> a.shift) & a.mask;
       const u32 dst = bin_dst[d] + (u32)p;
-      if (a.keys_out) a.keys_out[dst] = k;
+      if (a.keys_out) {
+        if constexpr (sizeof(KeyT) == 8) {
+          if (a.narrow) reinterpret_cast<u32*>(a.keys_out)[dst] = (u32)(k >> a.narrow);
+          else a.keys_out[dst] = k;
+        } else a.keys_out[dst] = k;
+      }
       a.idx_out[dst] = rid;
     }
   }
@@ -454,6 +460,7 @@ static int run_scatter(Src src, const PassIO& io, int64_t n, int shift, u32 mask
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
   a.n = n; a.shift = shift; a.mask = mask; a.chunk_offs = counts; a.digit_base = base;
   a.tile_counts = tile_counts; a.group_count = group_count; a.group_shift = group_shift;
+  a.narrow = io.narrow_out;
   constexpr size_t smem = PassCfg<KeyT, NBINS>::SMEM;
   auto kern = scatter_kernel<KeyT, Src, NBINS, MINB>;
   static bool configured = false;   // per instantiation
