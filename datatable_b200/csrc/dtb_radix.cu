@@ -217,6 +217,29 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -----------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, u32 count) {
+  const u32 a = (u32)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");      // visible to the async proxy
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, u32 bytes, uint64_t* bar) {
+  const u32 d = (u32)__cvta_generic_to_shared(smem_dst), b = (u32)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
+  const u32 b = (u32)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" :: "r"(b), "r"(parity) : "memory");
+}
+
 template <typename KeyT, int NBINS> struct PassCfg {
   static constexpr int WARPS = PASS_THREADS / 32;
   // 256 bins: row ids are prefetched into shared memory with cp.async; 1024 bins: the tables take that
@@ -237,7 +260,7 @@ template <typename KeyT, int NBINS> struct PassCfg {
 // Thread t owns the BPT = NBINS/256 consecutive digits t*BPT.. in the scan phase.
 template <typename KeyT, typename Src, int NBINS, bool FULL>
 __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsigned char* smem_raw, u32* s_wsum,
-                                             const int64_t base, const int tile_n)
+                                             uint64_t* s_bar, const int64_t base, const int tile_n)
 {
   constexpr int THREADS = PASS_THREADS, IPT = PASS_IPT, TILE = PASS_TILE;
   constexpr int WARPS = THREADS / 32;
@@ -264,9 +287,9 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
     if (USE_RIDX && have_idx) {
       const int32_t* g = a.idx_in + base;
       if (FULL) {
-#pragma unroll
-        for (int j = 0; j < IPT / 4; j++) { const int c = tid + j * THREADS; cp_async16(ridx + 4 * c, g + 4 * c); }
-        cp_async_commit();
+        // the whole 16 KB row-id tile is one TMA bulk copy issued by one thread; it lands in shared
+        // memory while the tile is being ranked and is awaited (mbarrier) before the reorder phase
+        if (tid == 0) { mbar_init(s_bar, 1); tma_load_1d(ridx, g, (u32)(TILE * sizeof(int32_t)), s_bar); }
       } else {
         for (int p = tid; p < tile_n; p += THREADS) ridx[p] = g[p];
       }
@@ -346,7 +369,7 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
     bin_dst[b0 + j] -= tstart;                                   // was: the digit's first output slot (set by the caller)
     tstart += run[j];
   }
-  if (USE_RIDX && have_idx && FULL) cp_async_wait_all();
+  if (USE_RIDX && have_idx && FULL) mbar_wait(s_bar, 0);
   __syncthreads();
 
   // ---- reorder the tile in shared memory ----
@@ -377,6 +400,7 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
   constexpr int BPT = NBINS / THREADS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ u32 s_wsum[WARPS];
+  __shared__ __align__(8) uint64_t s_bar;                       // mbarrier of the row-id TMA copy
   u32* bin_dst    = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
   KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);
   int32_t* sidx   = reinterpret_cast<int32_t*>(skey + TILE);
@@ -402,8 +426,8 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
     bin_dst[b] = bin_run;
   }
 
-  if (tile_n == TILE) scatter_tile<KeyT, Src, NBINS, true >(a, smem_raw, s_wsum, base, tile_n);
-  else                scatter_tile<KeyT, Src, NBINS, false>(a, smem_raw, s_wsum, base, tile_n);
+  if (tile_n == TILE) scatter_tile<KeyT, Src, NBINS, true >(a, smem_raw, s_wsum, &s_bar, base, tile_n);
+  else                scatter_tile<KeyT, Src, NBINS, false>(a, smem_raw, s_wsum, &s_bar, base, tile_n);
 
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
   const int lane = tid & 31;
