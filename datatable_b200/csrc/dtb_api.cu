@@ -264,7 +264,6 @@ static int bitlen(u64 v) { int b = 0; while (v) { b++; v >>= 1; } return b; }
 static int ctz64(u64 v) { int c = 0; while (!(v & 1)) { v >>= 1; c++; } return c; }
 
 static bool stype_supported(int st) { return stype_bytes(st) != 0; }
-static bool stype_is_float(int st) { return st == DTB_STYPE_FLOAT32 || st == DTB_STYPE_FLOAT64; }
 
 // ---------------------------------------------------------------------------
 // group(): plan + launch
@@ -311,7 +310,7 @@ static int plan_keys(const dtb_col* keys, const void* const* dptrs, int nkeys, c
                      int na_pos, const ColStats* st, KeyPlan& kp, int64_t& nacount_last)
 {
   kp.nkeys = nkeys;
-  int total = 0, sort_bits = 0;
+  int total = 0;
   // the last key is the least significant part of the composite
   for (int c = nkeys - 1; c >= 0; c--) {
     KeyNorm& k = kp.k[c];
@@ -336,7 +335,6 @@ static int plan_keys(const dtb_col* keys, const void* const* dptrs, int nkeys, c
     if (cs.nvalid == 0) { k.bits = 0; k.na_value = 0; }    // all-NA column is constant
     k.lshift = total;
     total += k.bits;
-    if (flags[c] & DTB_FLAG_SORT_ONLY) sort_bits = total;
     if (c == nkeys - 1) nacount_last = (int64_t)cs.nacount;
   }
   kp.total_bits = total;
@@ -344,7 +342,6 @@ static int plan_keys(const dtb_col* keys, const void* const* dptrs, int nkeys, c
   int gs = 0;
   for (int c = nkeys - 1; c >= 0 && (flags[c] & DTB_FLAG_SORT_ONLY); c--) gs = kp.k[c].lshift + kp.k[c].bits;
   kp.group_shift = gs;
-  (void)sort_bits;
   return DTB_OK;
 }
 

@@ -175,7 +175,6 @@ class Groupby:
             out_st = lib.dtb_reduce_out_stype(op, v.stype)
         if not out_st:
             raise _lib.DtbValueError(f"Invalid column of stype {v.stype} in reducer {op}")
-        self._keepalive = getattr(self, "_keepalive", [])
         if out is None:
             out, optr = _alloc(self.ngroups, out_st, v.on_device)
         else:
