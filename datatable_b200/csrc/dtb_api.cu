@@ -299,7 +299,7 @@ struct GroupResult {
   int64_t ngroups = -1;
   // direct-address reducer support (small key domains, device-resident key columns)
   bool    direct = false;
-  bool    direct_hot = false;
+  int64_t direct_gmax = 0;   // rows of the largest group
   KeyPlan direct_kp;
   int64_t direct_table = 0;
   DevBuf  gkeys;         // uint32[ngroups]
@@ -479,11 +479,12 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   if (nrounds > 2) { DTB_TRY(idxR1.alloc((size_t)n * 4, s)); }
 
   DTB_TL("scratch allocated");
-  u32 h_hmax[MAX_PASSES]; int n_hmax = 0;  // largest digit count per pass (read after the final sync)
 
   // ---- fused reducers: when the group key domain is small the reducers only need the key
-  //      columns, so they run on a side stream WHILE the sort passes run on `s`
-  //      (the passes are shared-memory bound, the reducers L2-atomic bound) -----------------------
+  //      columns, not the RowIndex: they stream the rows in storage order once the groups are known
+  //      (the streaming mode -- plain / shared-memory table / hot-key cache -- depends on the number of
+  //      groups and the size of the largest one, see plan_direct).  Option "overlap_reducers" runs
+  //      them on a side stream WHILE the sort passes run instead (hot keys guessed on the device). ----
   bool staged_keys = false;
   for (int c = 0; c < nkeys; c++) staged_keys = staged_keys || (in[c].buf.p != nullptr);
   const int dbits0 = (nrounds == 1) ? rounds[0].kp.total_bits - rounds[0].kp.group_shift : 99;
@@ -506,8 +507,8 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   DevBuf facc;
   const int64_t ftable = fused_direct ? ((int64_t)1 << dbits0) : 0;
   // Measured on C2: under the sort passes the accumulation gains ~2 % (both want the same SMs) and
-  // inflates every scatter launch by ~40 %, so by default it runs on `s` between the first count
-  // kernel and the first scatter; option "overlap_reducers" moves it to the side stream.
+  // inflates every scatter launch by ~40 %, so by default it runs on `s` after the offsets stage;
+  // option "overlap_reducers" moves it to the side stream.
   cudaStream_t rs = s;
   if (fused_direct) {
     if (opt_overlap) { DTB_TRY(t_side.ensure()); rs = t_side.stream; }
@@ -617,31 +618,28 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       io.keys_out = (last && !want_sorted_keys) ? nullptr : kout;
       int32_t* iout = last ? round_out : ((p & 1) ? idxB.as<int32_t>() : idxA.as<int32_t>());
       io.idx_out = iout;
-      const bool fork_here = fused_direct && ri == 0 && p == 0;
+      const bool fork_here = fused_direct && rs != s && ri == 0 && p == 0;
       DTB_TRY(launch_radix_pass(io, rk, kb, n, pp.shift[p], pp.bits[p], work.as<u32>(),
-                                hmax.as<u32>() + p, s, (fork_here && rs != s) ? t_side.fork : nullptr,
+                                hmax.as<u32>() + p, s, fork_here ? t_side.fork : nullptr,
                                 (count_table && last) ? gcount.as<u32>() : nullptr, rk.group_shift));
       if (fork_here) {
         // the digit totals of pass 0 exist (hmax): the reducers decide about hot keys on the device
-        if (rs != s) DTB_CUDA_CHECK(cudaStreamWaitEvent(rs, t_side.fork, 0));
+        DTB_CUDA_CHECK(cudaStreamWaitEvent(rs, t_side.fork, 0));
+        DirectPlan dp = {DIRECT_DEVICE_HOT, nullptr, ftable, hmax.as<u32>(), (u32)(0.02 * (double)n)};
         for (int i = 0; i < fr->n; i++) {
           if (fr->spec[i].op == DTB_OP_NROWS) continue;
-          ProfScope ps(rs != s ? "reduce_direct_overlapped" : "reduce_direct", rs);
-          DTB_TRY(launch_direct_accumulate(fr->spec[i].op, rk, 0, hmax.as<u32>(), fr->spec[i].value.data,
+          ProfScope ps("reduce_direct_overlapped", rs);
+          DTB_TRY(launch_direct_accumulate(fr->spec[i].op, rk, dp, fr->spec[i].value.data,
                                            fr->spec[i].value.stype, n, ftable,
                                            facc.as<u64>() + (size_t)ftable * 2 * i,
                                            facc.as<u64>() + (size_t)ftable * (2 * i + 1), rs));
         }
-        if (rs != s) DTB_CUDA_CHECK(cudaEventRecord(t_side.join, rs));
+        DTB_CUDA_CHECK(cudaEventRecord(t_side.join, rs));
       }
       if (last && want_sorted_keys) { sorted_keys = kout; last_key_bytes = key_bytes; }
       kin = kout;
       kout = (kout == keyA.p) ? keyB.p : keyA.p;
       iin = iout;
-    }
-    if (want_direct && nrounds == 1) {
-      DTB_CUDA_CHECK(cudaMemcpyAsync(h_hmax, hmax.p, sizeof(u32) * pp.npasses, cudaMemcpyDeviceToHost, s));
-      n_hmax = pp.npasses;
     }
     idx_cur = round_out;
   }
@@ -672,7 +670,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   // ---- group offsets -----------------------------------------------------------------
   if (do_groups) {
     const int64_t otiles = offsets_num_tiles(n);
-    DevBuf oscr; DTB_TRY(oscr.alloc(sizeof(u64) * (size_t)(otiles + 3), s));
+    DevBuf oscr; DTB_TRY(oscr.alloc(sizeof(u64) * (size_t)(otiles + 4), s));
     DTB_CUDA_CHECK(cudaMemsetAsync(oscr.p, 0, oscr.bytes, s));
     u64* d_ng = oscr.as<u64>() + otiles + 2;
     DevBuf headflags;
@@ -705,10 +703,10 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       }
       DTB_TRY(launch_group_offsets(headflags.p, 1, 0, n, offsets, d_ng, oscr.as<u64>(), s));
     }
-    u64 h_ng = 0;
-    DTB_CUDA_CHECK(cudaMemcpyAsync(&h_ng, d_ng, sizeof(u64), cudaMemcpyDeviceToHost, s));
+    u64 h_ng[2] = {0, 0};                    // {groups, rows of the largest group (count-table path only)}
+    DTB_CUDA_CHECK(cudaMemcpyAsync(h_ng, d_ng, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
-    res.ngroups = (int64_t)h_ng;
+    res.ngroups = (int64_t)h_ng[0];
     // group key of every group, for the direct-address reducers
     bool staged = false;
     for (int c = 0; c < nkeys; c++) staged = staged || (in[c].buf.p != nullptr);
@@ -720,10 +718,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
                                   res.gkeys.as<u32>(), s));
       }
       res.direct = true;
-      // a key owning a share f of the rows puts >= f*n rows into one bin of EVERY digit histogram
-      u32 least = 0xffffffffu;
-      for (int p = 0; p < n_hmax; p++) least = h_hmax[p] < least ? h_hmax[p] : least;
-      res.direct_hot = n_hmax > 0 && (double)least > 0.02 * (double)n;
+      res.direct_gmax = count_table ? (int64_t)h_ng[1] : n;       // unknown: assume the worst
       res.direct_kp = rounds[0].kp;
       res.direct_table = (int64_t)1 << dbits;
     }
@@ -735,6 +730,12 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     const int64_t ng = res.ngroups;
     fr->out.assign(fr->n, nullptr);
     if (fused_direct && rs != s) DTB_CUDA_CHECK(cudaStreamWaitEvent(s, t_side.join, 0));
+    DirectPlan dp = {DIRECT_PLAIN, nullptr, ftable, nullptr, 0};
+    DevBuf dmap;
+    if (fused_direct && rs == s && ng > 0) {
+      DTB_TRY(dmap.alloc(direct_map_bytes(ftable), s));
+      DTB_TRY(plan_direct(ftable, res.gkeys.as<u32>(), offsets, ng, n, res.direct_gmax, dmap.p, s, dp));
+    }
     DevBuf gacc;
     if (!fused_direct) DTB_TRY(gacc.alloc(sizeof(u64) * (size_t)(ng > 0 ? ng : 1) * 2, s));
     for (int i = 0; i < fr->n; i++) {
@@ -748,8 +749,14 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       if (sp.op == DTB_OP_NROWS) {
         DTB_TRY(launch_nrows(offsets, ng, ob.p, s));
       } else if (fused_direct) {
-        DTB_TRY(launch_direct_finalize(sp.op, sp.value.stype, facc.as<u64>() + (size_t)ftable * 2 * i,
-                                       facc.as<u64>() + (size_t)ftable * (2 * i + 1), res.gkeys.as<u32>(), ng, ob.p, s));
+        u64* a0 = facc.as<u64>() + (size_t)ftable * 2 * i;
+        u64* a1 = facc.as<u64>() + (size_t)ftable * (2 * i + 1);
+        if (rs == s && ng > 0) {
+          ProfScope ps("reduce_direct", s);
+          DTB_TRY(launch_direct_accumulate(sp.op, rounds[0].kp, dp, sp.value.data, sp.value.stype, n, ftable, a0, a1, s));
+        }
+        DTB_TRY(launch_direct_finalize(sp.op, sp.value.stype, a0, a1,
+                                       (dp.kind == DIRECT_SMALL && dp.map) ? nullptr : res.gkeys.as<u32>(), ng, ob.p, s));
       } else {
         DevIn dv; DTB_TRY(dv.bind(sp.value.data, (size_t)n * stype_bytes(sp.value.stype), s));
         ProfScope ps("reduce", s);
@@ -779,7 +786,7 @@ struct dtb_groupby {
   int64_t nrows = 0;
   // direct-address reducers: valid while the caller keeps the key columns alive and unchanged
   bool direct = false;
-  bool hot = false;
+  int64_t gmax = 0;           // rows of the largest group
   dtb::KeyPlan kp;
   int64_t table = 0;
   void* gkeys = nullptr;      // device uint32[ngroups]
@@ -917,7 +924,7 @@ int dtb_groupby_create_reduce(const dtb_col* keys, int nkeys, const int* flags, 
   g->norder = res.n - res.nskip;
   g->ngroups = res.ngroups;
   g->nrows = res.n;
-  if (res.direct) { g->direct = true; g->hot = res.direct_hot; g->kp = res.direct_kp; g->table = res.direct_table; g->gkeys = res.gkeys.detach(); }
+  if (res.direct) { g->direct = true; g->gmax = res.direct_gmax; g->kp = res.direct_kp; g->table = res.direct_table; g->gkeys = res.gkeys.detach(); }
   if (res.ngroups >= 0) {
     // shrink the worst-case offsets buffer to ngroups+1 entries
     DevBuf exact;
@@ -1021,9 +1028,13 @@ int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_valu
   if (g->ngroups == 0) return DTB_OK;
   DevOut d_out; DTB_TRY(d_out.bind(out, (size_t)g->ngroups * stype_bytes(out_st), s));
   DevBuf acc; DTB_TRY(acc.alloc(sizeof(u64) * (size_t)g->table * 2, s));
+  DevBuf dmap; DTB_TRY(dmap.alloc(direct_map_bytes(g->table), s));
+  DirectPlan dp;
+  DTB_TRY(plan_direct(g->table, (const uint32_t*)g->gkeys, (const int32_t*)g->offsets, g->ngroups, g->nrows,
+                      g->gmax, dmap.p, s, dp));
   {
     ProfScope ps("reduce_direct", s);
-    DTB_TRY(launch_reduce_direct(op, g->kp, g->hot, value.data, value.stype, g->nrows, g->table,
+    DTB_TRY(launch_reduce_direct(op, g->kp, dp, value.data, value.stype, g->nrows, g->table,
                                  (const uint32_t*)g->gkeys, g->ngroups, acc.as<u64>(),
                                  acc.as<u64>() + g->table, d_out.dptr, s));
   }

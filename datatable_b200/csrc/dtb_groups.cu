@@ -241,6 +241,12 @@ count_compact_kernel(const u32* __restrict__ count, const u64* __restrict__ bsum
     }
   }
   if (blockIdx.x == nb - 1 && t == 255) { *d_ngroups = g; offsets[g] = (int32_t)n; }
+  // d_ngroups[1] = rows of the largest group (the reducers pick their streaming mode from it)
+  u32 m = c[0] > c[1] ? c[0] : c[1];
+  m = c[2] > m ? c[2] : m; m = c[3] > m ? c[3] : m;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { const u32 o = __shfl_xor_sync(0xffffffffu, m, d); m = o > m ? o : m; }
+  if (lane == 0 && m) atomicMax(&d_ngroups[1], (u64)m);
 }
 
 int launch_offsets_from_counts(const uint32_t* count, int64_t table, int64_t n, int32_t* offsets,

@@ -145,13 +145,29 @@ int launch_reduce_impl(int op, const void* value, int stype, int64_t nrows_value
 int reduce_out_stype_host(int op, int stype);
 
 // Direct-address reducers over a small normalised key domain (see dtb_reduce.cu).
-// hot_keys: some key may own a large share of the rows -> combine equal keys inside a warp first.
-int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* value, int stype, int64_t n,
+enum { DIRECT_PLAIN = 0,        // one L2 atomic per row into acc[x]
+       DIRECT_SMALL = 1,        // <= 2048 accumulators: per-CTA shared-memory tables (map: uint16 x -> group, or NULL)
+       DIRECT_HOT = 2,          // skewed group sizes: rows of hot keys (map: uint8 hot[x]) fold in shared memory
+       DIRECT_DEVICE_HOT = 3 }; // legacy overlapped mode: hot-key folding decided on the device from hot_count
+struct DirectPlan {
+  int kind;
+  const void* map;
+  int64_t nslots;               // accumulators in use: table, or ngroups for a dense-mapped small table
+  const uint32_t* hot_count;
+  uint32_t hot_thresh;
+};
+size_t direct_map_bytes(int64_t table);
+// Chooses the streaming mode from the group structure (gmax = rows of the largest group) and builds the
+// map it needs in map_scratch (direct_map_bytes(table) bytes, device).
+int plan_direct(int64_t table, const uint32_t* gkeys, const int32_t* offsets, int64_t ngroups, int64_t n,
+                int64_t gmax, void* map_scratch, cudaStream_t s, DirectPlan& dp);
+int launch_reduce_direct(int op, const KeyPlan& kp, const DirectPlan& dp, const void* value, int stype, int64_t n,
                          int64_t table, const uint32_t* gkeys, int64_t ngroups,
                          unsigned long long* acc0, unsigned long long* acc1, void* out, cudaStream_t s);
-int launch_direct_accumulate(int op, const KeyPlan& kp, int hot_value, const uint32_t* hot_count,
+int launch_direct_accumulate(int op, const KeyPlan& kp, const DirectPlan& dp,
                              const void* value, int stype, int64_t n, int64_t table,
                              unsigned long long* acc0, unsigned long long* acc1, cudaStream_t s);
+// gkeys == NULL: the accumulators are indexed by group (dense-mapped small table).
 int launch_direct_finalize(int op, int stype, const unsigned long long* acc0, const unsigned long long* acc1,
                            const uint32_t* gkeys, int64_t ngroups, void* out, cudaStream_t s);
 int launch_nrows(const int32_t* offsets, int64_t ngroups, void* out, cudaStream_t s);

@@ -428,7 +428,7 @@ __global__ void finalize_direct_kernel(int op, int in_stype, int out_stype, cons
   const bool in_float = (in_stype == DTB_STYPE_FLOAT32 || in_stype == DTB_STYPE_FLOAT64);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride) {
-    const u32 x = gkeys[g];
+    const u32 x = gkeys ? gkeys[g] : (u32)g;          // NULL: the accumulators are indexed by group
     const u64 a = acc0[x];
     bool valid = true; u64 bits = a;
     switch (op) {
@@ -468,6 +468,24 @@ struct DirectComposite {
   }
 };
 
+// One shared-memory accumulator slot (the words a CTA-local table keeps per key) -> the global table.
+template <int CAT>
+__device__ __forceinline__ void slot_flush(u64 a0, u64 a1, int64_t g, u64* acc0, u64* acc1, int flag) {
+  if constexpr (CAT == CAT_SUMI) { if (a0) atomicAdd(&acc0[g], a0); }
+  else if constexpr (CAT == CAT_SUMF) {
+    const double d = __longlong_as_double((long long)a0);
+    if (d != 0.0) atomicAdd(reinterpret_cast<double*>(acc0) + g, d);
+  }
+  else if constexpr (CAT == CAT_MEAN) {
+    if (a1) { atomicAdd(reinterpret_cast<double*>(acc0) + g, __longlong_as_double((long long)a0)); atomicAdd(&acc1[g], a1); }
+  }
+  else if constexpr (CAT == CAT_MINMAX) {
+    if (flag) { if (a0 != ~0ull) atomicMin(&acc0[g], a0); }
+    else      { if (a0 != 0ull)  atomicMax(&acc0[g], a0); }
+  }
+  else { if (a0) atomicAdd(&acc0[g], a0); }
+}
+
 // Few distinct group keys (<= 2048): every CTA folds its rows into a shared-memory copy of the
 // accumulator table and flushes it once, so the L2 sees gridDim x groups atomics instead of one per row
 // (100 keys at 2e8 rows: 1.6e8 same-address L2 atomics took 30 ms; low-cardinality by() is the common case).
@@ -476,7 +494,8 @@ constexpr int SMALL_TABLE = 2048;
 template <typename T, int CAT, typename KSrc>
 __global__ void __launch_bounds__(512)
 direct_reduce_small_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load_t* __restrict__ v,
-                           int64_t n, int table, u64* acc0, u64* acc1, int flag)
+                           int64_t n, int table, const uint16_t* __restrict__ dense,
+                           u64* acc0, u64* acc1, int flag)
 {
   __shared__ u64 s0[SMALL_TABLE];
   __shared__ u64 s1[SMALL_TABLE];
@@ -489,7 +508,8 @@ direct_reduce_small_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const u32 x = (u32)(ksrc.load(i) >> gshift);
+    u32 x = (u32)(ksrc.load(i) >> gshift);
+    if (dense) x = dense[x];                                   // sparse key domain, few groups: x -> group
     Partial<CAT> part; p_init(part, flag);
     p_add<T, CAT>(part, v[i], true, flag);
     p_flush(part, (int64_t)(wofs + x), s0, s1, flag);          // shared-memory atomics
@@ -508,26 +528,81 @@ direct_reduce_small_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < table; i += blockDim.x) {
-    Partial<CAT> part;
-    if constexpr (CAT == CAT_SUMI) part.s = s0[i];
-    else if constexpr (CAT == CAT_SUMF) part.s = __longlong_as_double((long long)s0[i]);
-    else if constexpr (CAT == CAT_MEAN) { part.s = __longlong_as_double((long long)s0[i]); part.c = (u32)s1[i]; }
-    else if constexpr (CAT == CAT_MINMAX) part.key = s0[i];
-    else part.c = (u32)s0[i];
-    if constexpr (CAT == CAT_MEAN) {
-      // the per-CTA count may exceed 32 bits only for n > 2^32 rows per CTA: not reachable (n <= INT32_MAX)
-      if (s1[i]) { atomicAdd(reinterpret_cast<double*>(acc0) + i, part.s); atomicAdd(&acc1[i], s1[i]); }
-    } else if constexpr (CAT == CAT_COUNT) {
-      if (s0[i]) atomicAdd(&acc0[i], s0[i]);
-    } else {
-      p_flush(part, (int64_t)i, acc0, acc1, flag);
-    }
-  }
+  for (int i = threadIdx.x; i < table; i += blockDim.x) slot_flush<CAT>(s0[i], s1[i], (int64_t)i, acc0, acc1, flag);
 }
 
-static thread_local HotSpec t_hot = {nullptr, 0, 0};
-static thread_local int t_small_table = 0;
+// Skewed group sizes (some key owns more than ~0.1 % of the rows): one L2 atomic per row would
+// serialise on the hot accumulators (same-address L2 atomics retire at one per 5-15 ns: a key with
+// half of 2e8 rows cost 16 ms).  `hot[x]` (built from the group sizes, see plan_direct) marks the
+// keys above the threshold; their rows are folded inside the warp (MATCH.ANY, only in warps that hold
+// a hot row) and then inside the CTA in a small open-addressed shared-memory table that is flushed
+// once per CTA; every other row takes the plain one-atomic path.
+constexpr int HOT_SLOTS = 2048;
+constexpr u32 HOT_EMPTY = 0xffffffffu;
+
+template <typename T, int CAT, typename KSrc>
+__global__ void __launch_bounds__(512)
+direct_reduce_hot_kernel(KSrc ksrc, int gshift, const typename RawKey<T>::load_t* __restrict__ v,
+                         int64_t n, const uint8_t* __restrict__ hot, u64* acc0, u64* acc1, int flag)
+{
+  __shared__ u32 hkey[HOT_SLOTS];
+  __shared__ u64 h0[HOT_SLOTS];
+  __shared__ u64 h1[HOT_SLOTS];
+  const u64 ident = (CAT == CAT_MINMAX && flag) ? ~0ull : 0ull;
+  for (int i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x) { hkey[i] = HOT_EMPTY; h0[i] = ident; h1[i] = 0; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nround = ((n + 31) / 32) * 32;                // keep whole warps in the loop
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const bool in = i < n;
+    u32 x = 0;
+    Partial<CAT> part; p_init(part, flag);
+    bool is_hot = false;
+    if (in) {
+      x = (u32)(ksrc.load(i) >> gshift);
+      p_add<T, CAT>(part, v[i], true, flag);
+      is_hot = hot[x] != 0;
+    }
+    if (__any_sync(0xffffffffu, is_hot)) {                      // warp-uniform: the body shuffles
+      // cold lanes match nobody (their tag is unique in the warp; x < 2^22)
+      const unsigned peers = __match_any_sync(0xffffffffu, is_hot ? x : (0x80000000u | (u32)lane));
+      const int leader = __ffs(peers) - 1;
+      unsigned rest = peers & ~(1u << leader);
+      Partial<CAT> tot = part;
+      while (__any_sync(0xffffffffu, rest != 0)) {
+        const int src = rest ? (__ffs(rest) - 1) : lane;
+        Partial<CAT> o;
+        if constexpr (CAT == CAT_SUMI) o.s = __shfl_sync(0xffffffffu, part.s, src);
+        else if constexpr (CAT == CAT_SUMF) o.s = __shfl_sync(0xffffffffu, part.s, src);
+        else if constexpr (CAT == CAT_MEAN) { o.s = __shfl_sync(0xffffffffu, part.s, src); o.c = __shfl_sync(0xffffffffu, part.c, src); }
+        else if constexpr (CAT == CAT_MINMAX) o.key = __shfl_sync(0xffffffffu, part.key, src);
+        else o.c = __shfl_sync(0xffffffffu, part.c, src);
+        if (rest && lane == leader) p_merge(tot, o, flag);
+        rest &= rest - 1;
+      }
+      if (is_hot) {
+        if (lane == leader) {
+          bool done = false;
+          const u32 h = (x * 2654435761u) >> 21;                // 11 bits
+#pragma unroll 1
+          for (int t = 0; t < 8 && !done; t++) {
+            const u32 slot = (h + (u32)t) & (HOT_SLOTS - 1);
+            const u32 old = atomicCAS(&hkey[slot], HOT_EMPTY, x);
+            if (old == HOT_EMPTY || old == x) { p_flush(tot, (int64_t)slot, h0, h1, flag); done = true; }
+          }
+          if (!done) p_flush(tot, (int64_t)x, acc0, acc1, flag);
+        }
+      }
+    }
+    if (in && !is_hot) p_flush(part, (int64_t)x, acc0, acc1, flag);   // hot rows never touch L2 directly
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HOT_SLOTS; i += blockDim.x)
+    if (hkey[i] != HOT_EMPTY) slot_flush<CAT>(h0[i], h1[i], (int64_t)hkey[i], acc0, acc1, flag);
+}
+
+static thread_local DirectPlan t_dp = {DIRECT_PLAIN, nullptr, 0, nullptr, 0};
 
 template <typename T, int CAT, typename KSrc>
 static int run_direct(const KSrc& ks, int gshift, const void* v, int64_t n, u64* acc0, u64* acc1, int flag,
@@ -535,15 +610,26 @@ static int run_direct(const KSrc& ks, int gshift, const void* v, int64_t n, u64*
 {
   typedef typename RawKey<T>::load_t L;
   int64_t want = (n + 511) / 512;
-  if (t_small_table > 0) {
+  if (t_dp.kind == DIRECT_SMALL) {
     int grid = (int)(want > NUM_SMS_B200 * 4 ? NUM_SMS_B200 * 4 : want);
-    direct_reduce_small_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, t_small_table, acc0, acc1, flag);
+    direct_reduce_small_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, (int)t_dp.nslots,
+                                                                  (const uint16_t*)t_dp.map, acc0, acc1, flag);
     count_launch();
     DTB_CUDA_CHECK(cudaGetLastError());
     return DTB_OK;
   }
+  if (t_dp.kind == DIRECT_HOT) {
+    int grid = (int)(want > NUM_SMS_B200 * 4 ? NUM_SMS_B200 * 4 : want);
+    direct_reduce_hot_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, (const uint8_t*)t_dp.map,
+                                                                acc0, acc1, flag);
+    count_launch();
+    DTB_CUDA_CHECK(cudaGetLastError());
+    return DTB_OK;
+  }
+  HotSpec hs = {nullptr, 0, 0};
+  if (t_dp.kind == DIRECT_DEVICE_HOT) { hs.count = t_dp.hot_count; hs.thresh = t_dp.hot_thresh; }
   int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
-  direct_reduce_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag, t_hot);
+  direct_reduce_kernel<T, CAT, KSrc><<<grid, 512, 0, s>>>(ks, gshift, (const L*)v, n, acc0, acc1, flag, hs);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
@@ -588,18 +674,60 @@ static int direct_op(int op, int st, const KSrc& ks, int gshift, const void* v, 
   set_error("unknown reducer"); return DTB_EINVAL;
 }
 
-// Stage 1: stream every row into acc[x].  acc0/acc1: device scratch of `table` u64 each.
-// hot_count (device, optional): largest digit count of the first radix pass; a key owning more
-// than 2 % of the rows switches on the intra-warp pre-aggregation (decided on the device so that the
-// accumulation can run on a side stream while the sort is still in flight).
-int launch_direct_accumulate(int op, const KeyPlan& kp, int hot_value, const uint32_t* hot_count,
+// ---- how the rows are streamed: decided on the host once the groups are known ----------------
+__global__ void dense_map_kernel(const u32* __restrict__ gkeys, int64_t ng, uint16_t* __restrict__ dense) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ng) dense[gkeys[g]] = (uint16_t)g;
+}
+__global__ void hot_map_kernel(const u32* __restrict__ gkeys, const int32_t* __restrict__ offsets, int64_t ng,
+                               u32 thresh, uint8_t* __restrict__ hot) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride)
+    if ((u32)(offsets[g + 1] - offsets[g]) > thresh) hot[gkeys[g]] = 1;
+}
+
+size_t direct_map_bytes(int64_t table) { return (size_t)table * sizeof(uint16_t); }
+
+int plan_direct(int64_t table, const uint32_t* gkeys, const int32_t* offsets, int64_t ng, int64_t n,
+                int64_t gmax, void* map_scratch, cudaStream_t s, DirectPlan& dp)
+{
+  dp.kind = DIRECT_PLAIN; dp.map = nullptr; dp.nslots = table; dp.hot_count = nullptr; dp.hot_thresh = 0;
+  if (ng <= 0) return DTB_OK;
+  if (table <= SMALL_TABLE) { dp.kind = DIRECT_SMALL; return DTB_OK; }
+  if (ng <= SMALL_TABLE) {
+    // few groups in a sparse key domain: x -> group through an L2-resident map (only the entries of
+    // keys that occur are ever read, so the map needs no initialisation)
+    dense_map_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, s>>>(gkeys, ng, (uint16_t*)map_scratch);
+    count_launch();
+    DTB_CUDA_CHECK(cudaGetLastError());
+    dp.kind = DIRECT_SMALL; dp.map = map_scratch; dp.nslots = ng;
+    return DTB_OK;
+  }
+  const int64_t hot_at = (n / 1024 > 8192) ? n / 1024 : 8192;      // a key this large makes the call "skewed"
+  if (gmax > hot_at) {
+    const int64_t key_thresh = (n / 2048 > 1024) ? n / 2048 : 1024;  // at most 2048 keys can exceed it
+    DTB_CUDA_CHECK(cudaMemsetAsync(map_scratch, 0, (size_t)table, s));
+    const int grid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+    hot_map_kernel<<<grid, 256, 0, s>>>(gkeys, offsets, ng, (u32)key_thresh, (uint8_t*)map_scratch);
+    count_launch();
+    DTB_CUDA_CHECK(cudaGetLastError());
+    dp.kind = DIRECT_HOT; dp.map = map_scratch;
+  }
+  return DTB_OK;
+}
+
+// Stage 1: stream every row into acc[x] (acc[group] for a dense-mapped small table).  acc0/acc1: device
+// scratch of `table` u64 each.  DIRECT_DEVICE_HOT (reducers overlapped with the sort, before the groups
+// exist): dp.hot_count is the largest digit count of the first radix pass; more than dp.hot_thresh rows
+// in one bin switches on the intra-warp pre-aggregation, decided on the device.
+int launch_direct_accumulate(int op, const KeyPlan& kp, const DirectPlan& dp,
                              const void* value, int stype, int64_t n, int64_t table,
                              u64* acc0, u64* acc1, cudaStream_t s)
 {
   const int out_st = reduce_out_stype(op, stype);
   if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
-  t_hot.count = hot_count; t_hot.thresh = (u32)(0.02 * (double)n); t_hot.value = hot_value;
-  t_small_table = (table <= SMALL_TABLE) ? (int)table : 0;
+  t_dp = dp;
+  if (dp.kind == DIRECT_SMALL) table = dp.nslots;                // only the used accumulators are initialised
   const int tgrid = (int)((table + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (table + 255) / 256);
   fill_u64_kernel<<<tgrid, 256, 0, s>>>(acc0, table, (op == DTB_OP_MIN) ? ~0ull : 0ull);
   count_launch();
@@ -644,13 +772,14 @@ int launch_direct_finalize(int op, int stype, const u64* acc0, const u64* acc1, 
   return DTB_OK;
 }
 
-int launch_reduce_direct(int op, const KeyPlan& kp, bool hot_keys, const void* value, int stype, int64_t n,
+int launch_reduce_direct(int op, const KeyPlan& kp, const DirectPlan& dp, const void* value, int stype, int64_t n,
                          int64_t table, const uint32_t* gkeys, int64_t ng, u64* acc0, u64* acc1,
                          void* out, cudaStream_t s)
 {
   if (ng == 0) return DTB_OK;
-  DTB_TRY(launch_direct_accumulate(op, kp, hot_keys ? 1 : 0, nullptr, value, stype, n, table, acc0, acc1, s));
-  return launch_direct_finalize(op, stype, acc0, acc1, gkeys, ng, out, s);
+  DTB_TRY(launch_direct_accumulate(op, kp, dp, value, stype, n, table, acc0, acc1, s));
+  return launch_direct_finalize(op, stype, acc0, acc1, (dp.kind == DIRECT_SMALL && dp.map) ? nullptr : gkeys,
+                                ng, out, s);
 }
 
 // gkeys[g] = sorted_keys[offsets[g]] >> gshift  (the normalised key of every group)

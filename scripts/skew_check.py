@@ -14,7 +14,15 @@ def run(name, k):
         s = gb.reduced(0); ng = gb.ngroups; gb.close()
         b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     ok = abs(float(s.sum()) - float(v.sum())) < 1e-6 * float(v.sum())
-    print(f"{name:28s} ngroups={ng:9d}  {min(ts):8.2f} ms  {n/min(ts)/1e6:8.2f} Grows/s  sums_ok={ok}", flush=True)
+    # one more call with the per-kernel-family profile on: where did the time go?
+    engine.set_option("profile", 1); _lib.lib.dtb_profile_reset()
+    gb = engine.Groupby([k], [0], 1, reducers=[(_lib.OP_SUM, v)]); gb.close()
+    fam = {}
+    for nm, ms in _lib.profile_records():
+        fam[nm] = fam.get(nm, 0.0) + ms
+    engine.set_option("profile", 0)
+    split = " ".join(f"{a}={b:.2f}" for a, b in sorted(fam.items(), key=lambda t: -t[1])[:5])
+    print(f"{name:28s} ngroups={ng:9d}  {min(ts):8.2f} ms  {n/min(ts)/1e6:8.2f} Grows/s  sums_ok={ok}  [{split}]", flush=True)
 run("uniform 1e6 keys", torch.randint(0, 1_000_000, (n,), generator=g, device="cuda", dtype=torch.int32))
 run("2 keys", torch.randint(0, 2, (n,), generator=g, device="cuda", dtype=torch.int32))
 run("100 keys", torch.randint(0, 100, (n,), generator=g, device="cuda", dtype=torch.int32))
@@ -22,4 +30,6 @@ z = (torch.rand(n, generator=g, device="cuda") ** 8 * 1_000_000).to(torch.int32)
 run("power-law head (x^8)", z)
 hot = torch.randint(0, 1_000_000, (n,), generator=g, device="cuda", dtype=torch.int32); hot[::2] = 7
 run("one key owns 50 %", hot)
+sp = torch.randint(0, 300, (n,), generator=g, device="cuda", dtype=torch.int32) * 9973 + 11
+run("300 keys in a 3e6 domain", sp)
 run("sorted input", torch.sort(torch.randint(0, 1_000_000, (n,), generator=g, device="cuda", dtype=torch.int32)).values)

@@ -223,6 +223,65 @@ def test_groupby_handle_multikey_direct():
     gb.close()
 
 
+def _check_direct_modes(k, kst, vals, ctx):
+    """fused create_reduce and the handle's reduce against the oracle, every reducer, on one key column"""
+    import torch
+    from datatable_b200 import engine
+    from oracle import oracle as orc
+    want_o, want_f, want_ng = orc.group([k], [0], 1, stypes=[kst])
+    kd = torch.from_numpy(k).cuda()
+    ops = ("sum", "mean", "min", "max", "count", "countna")
+    reds = [(op, v, vst) for v, vst in vals for op in ops]
+    gb = engine.Groupby([engine.Col(kd, kst)], [0], 1,
+                        reducers=[(OPS[op], engine.Col(torch.from_numpy(v).cuda(), vst)) for op, v, vst in reds])
+    assert gb.ngroups == want_ng
+    assert np.array_equal(gb.order().cpu().numpy(), want_o)
+    assert np.array_equal(gb.offsets().cpu().numpy(), want_f)
+    for i, (op, v, vst) in enumerate(reds):
+        want = orc.reduce(OPS[op], v, want_o, want_f, stype=vst)
+        assert_reducer_equal(gb.reduced(i).cpu().numpy(), want, op, vst, ctx=f"{ctx} fused {op} vst={vst}")
+        got = gb.reduce(OPS[op], engine.Col(torch.from_numpy(v).cuda(), vst)).cpu().numpy()
+        assert_reducer_equal(got, want, op, vst, ctx=f"{ctx} handle {op} vst={vst}")
+    gb.close()
+
+
+def test_direct_reducers_few_groups_in_sparse_domain():
+    """<= 2048 groups whose keys are spread over a domain of millions: the rows fold into per-CTA
+    shared-memory tables through a key -> group map (dtb_reduce.cu, plan_direct)."""
+    rng = np.random.default_rng(4242)
+    n = 700_000
+    for ngroups, kst in ((3, INT32), (150, INT32), (2048, INT64), (2049, INT32)):
+        domain = rng.choice(3_000_000, ngroups, replace=False).astype(NPT[kst]) - 1_000_000
+        k = domain[rng.integers(0, ngroups, n)]
+        k[:ngroups] = domain                                   # every key occurs
+        if ngroups == 150:
+            k[rng.random(n) < 0.02] = NA[kst]
+        vals = [(make_col(rng, FLOAT64, n, "unit", 0.1), FLOAT64), (make_col(rng, INT32, n, "unit", 0.1), INT32),
+                (make_col(rng, FLOAT32, n, "few", 0.1), FLOAT32)]
+        _check_direct_modes(k, kst, vals, f"sparse ng={ngroups}")
+
+
+def test_direct_reducers_skewed_group_sizes():
+    """Thousands of groups, some of them huge: rows of the hot keys fold in a shared-memory cache (more hot
+    keys than cache slots here, so the overflow path to the global table runs too), the rest go one atomic
+    per row; one giant key on top."""
+    rng = np.random.default_rng(777)
+    hot = rng.choice(2_000_000, 3500, replace=False)
+    cold = rng.choice(2_000_000, 10_000, replace=False)
+    k = np.concatenate([np.repeat(hot, 1100), np.full(20_000, hot[0]), cold[rng.integers(0, len(cold), 300_000)]])
+    k = k.astype(np.int32)
+    rng.shuffle(k)
+    n = len(k)
+    k[rng.random(n) < 0.001] = NA[INT32]
+    vals = [(make_col(rng, FLOAT64, n, "unit", 0.1), FLOAT64), (make_col(rng, INT64, n, "unit", 0.1), INT64)]
+    _check_direct_modes(k, INT32, vals, "skewed")
+    # half of the rows in one key, the rest spread out
+    k2 = rng.integers(0, 1_000_000, 1_000_000).astype(np.int32)
+    k2[rng.random(len(k2)) < 0.5] = 123_456
+    vals2 = [(make_col(rng, FLOAT64, len(k2), "unit", 0.0), FLOAT64), (make_col(rng, INT8, len(k2), "unit", 0.2), INT8)]
+    _check_direct_modes(k2, INT32, vals2, "half-hot")
+
+
 @pytest.mark.parametrize("overlap", [0, 1])
 @pytest.mark.parametrize("small_domain", [True, False])
 def test_fused_create_reduce_vs_oracle(small_domain, overlap):
