@@ -240,6 +240,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
       "WAIT_DONE:\n\t}" :: "r"(b), "r"(parity) : "memory");
 }
 
+enum { RANK_MASKS = 0, RANK_BALLOT = 1 };
+int g_opt_rank_ballot = 1;          // option "rank_ballot"
+
 template <typename KeyT, int NBINS> struct PassCfg {
   static constexpr int WARPS = PASS_THREADS / 32;
   // 256 bins: row ids are prefetched into shared memory with cp.async; 1024 bins: the tables take that
@@ -258,7 +261,7 @@ template <typename KeyT, int NBINS> struct PassCfg {
 // scattered shared-memory write of the reorder phase is ONE 8-byte store per row, not two
 // 4-byte stores: shared-memory wavefronts, not HBM, bound this kernel.
 // Thread t owns the BPT = NBINS/256 consecutive digits t*BPT.. in the scan phase.
-template <typename KeyT, typename Src, int NBINS, bool FULL>
+template <typename KeyT, typename Src, int NBINS, bool FULL, int RANK>
 __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsigned char* smem_raw, u32* s_wsum,
                                              uint64_t* s_bar, const int64_t base, const int tile_n)
 {
@@ -282,8 +285,10 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
     u32* z = reinterpret_cast<u32*>(whist);
 #pragma unroll
     for (int j = 0; j < WARPS * NBINS / 2 / THREADS; j++) z[tid + j * THREADS] = 0;
+    if constexpr (RANK == RANK_MASKS) {
 #pragma unroll
-    for (int j = 0; j < WARPS * NBINS / THREADS; j++) wmask_all[tid + j * THREADS] = 0;
+      for (int j = 0; j < WARPS * NBINS / THREADS; j++) wmask_all[tid + j * THREADS] = 0;
+    }
     if (USE_RIDX && have_idx) {
       const int32_t* g = a.idx_in + base;
       if (FULL) {
@@ -307,28 +312,56 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
   __syncthreads();
 
   // ---- rank inside the warp: rows with equal digits keep (item, lane) order ----
-  // The lanes holding the same digit are found with a shared-memory atomicOr on a per-warp
-  // mask table, not MATCH.ANY: on sm_100 MATCH.ANY issues once per ~60 SM cycles and bound
-  // the whole kernel; the atomicOr sequence costs ~7 (scripts/ubench/match_bench.cu).
+  // The lanes holding the same digit ("peers") are found either
+  //   RANK_BALLOT: with one __ballot_sync per digit bit (peers = AND over the bits of "lanes whose bit
+  //     equals mine"): no shared-memory traffic, and the cost does not depend on how the digits are
+  //     distributed -- a hot digit makes the atomicOr form serialise on one shared-memory word;
+  //   RANK_MASKS: with a shared-memory atomicOr on a per-warp mask table.
+  // Never MATCH.ANY: on sm_100 it issues once per ~60 SM cycles and bound the whole kernel
+  // (scripts/ubench/match_bench.cu).
   u32 rank2[IPT / 2];                                         // two 16-bit ranks per register
   unsigned short* myhist = whist + warp * NBINS;
   u32* wmask = wmask_all + warp * NBINS;
   const unsigned lt = lanemask_lt();
   const unsigned lanebit = 1u << lane;
+  constexpr int LOGB = (NBINS == 256) ? 8 : 10;
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const bool valid = FULL || (wbase + i * 32 + lane) < tile_n;
     const u32 d = (u32)(key[i] >> a.shift) & a.mask;
-    if (valid) atomicOr(&wmask[d], lanebit);
-    __syncwarp();
-    unsigned peers = 0; unsigned short cnt = 0;
-    if (valid) { peers = wmask[d]; cnt = myhist[d]; }
-    const unsigned before = peers & lt;
-    const u32 r = (u32)cnt + (u32)__popc(before);
-    if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
-    __syncwarp();                                               // all reads of this round precede the update
-    if (valid && before == 0) { myhist[d] = cnt + (unsigned short)__popc(peers); wmask[d] = 0; }
-    __syncwarp();
+    if constexpr (RANK == RANK_BALLOT) {
+      unsigned peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+      for (int b = 0; b < LOGB; b++) {
+        // peers &= (lanes whose bit b equals mine); digit bits above the pass width are 0 in every
+        // lane and leave the mask unchanged.  4 instructions per bit (LOP3->P, VOTE, @!P NOT, AND).
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 t, p, 0xffffffff;\n\t"
+            "@!p not.b32 t, t;\n\t"
+            "and.b32 %0, %0, t;\n\t}"
+            : "+r"(peers) : "r"(d), "r"(1u << b));
+      }
+      const unsigned short cnt = valid ? myhist[d] : (unsigned short)0;
+      const unsigned before = peers & lt;
+      const u32 r = (u32)cnt + (u32)__popc(before);
+      if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
+      __syncwarp();                                             // all reads of this round precede the update
+      if (valid && before == 0) myhist[d] = cnt + (unsigned short)__popc(peers);
+      __syncwarp();
+    } else {
+      if (valid) atomicOr(&wmask[d], lanebit);
+      __syncwarp();
+      unsigned peers = 0; unsigned short cnt = 0;
+      if (valid) { peers = wmask[d]; cnt = myhist[d]; }
+      const unsigned before = peers & lt;
+      const u32 r = (u32)cnt + (u32)__popc(before);
+      if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
+      __syncwarp();                                             // all reads of this round precede the update
+      if (valid && before == 0) { myhist[d] = cnt + (unsigned short)__popc(peers); wmask[d] = 0; }
+      __syncwarp();
+    }
   }
   __syncthreads();
 
@@ -391,7 +424,14 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
   __syncthreads();
 }
 
-template <typename KeyT, typename Src, int NBINS, int MINB>
+// key of the sorted tile's slot q (32-bit keys are staged as (key, row id) pairs)
+template <typename KeyT>
+__device__ __forceinline__ KeyT staged_key(const KeyT* skey, int q) {
+  if constexpr (sizeof(KeyT) == 4) return (KeyT)reinterpret_cast<const uint2*>(skey)[q].x;
+  else return skey[q];
+}
+
+template <typename KeyT, typename Src, int NBINS, int MINB, int RANK>
 __global__ void __launch_bounds__(PASS_THREADS, MINB)
 scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
 {
@@ -426,8 +466,8 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
     bin_dst[b] = bin_run;
   }
 
-  if (tile_n == TILE) scatter_tile<KeyT, Src, NBINS, true >(a, smem_raw, s_wsum, &s_bar, base, tile_n);
-  else                scatter_tile<KeyT, Src, NBINS, false>(a, smem_raw, s_wsum, &s_bar, base, tile_n);
+  if (tile_n == TILE) scatter_tile<KeyT, Src, NBINS, true,  RANK>(a, smem_raw, s_wsum, &s_bar, base, tile_n);
+  else                scatter_tile<KeyT, Src, NBINS, false, RANK>(a, smem_raw, s_wsum, &s_bar, base, tile_n);
 
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
   const int lane = tid & 31;
@@ -446,18 +486,20 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
     }
     if (a.group_count) {
       // Last pass: the tile is sorted by the full composite key (its rows arrive sorted by the lower
-      // digits), so equal group keys are adjacent.  Every warp adds the lengths of the runs it sees
-      // to count[group key]; the Groupby offsets are then a scan over that L2-resident table
-      // instead of a pass over 4n bytes of sorted keys.
+      // digits), so equal group keys are adjacent.  Every run of equal group keys adds its length to
+      // count[group key]; the Groupby offsets are then a scan over that L2-resident table instead of a
+      // pass over 4n bytes of sorted keys.  A run [p, q] is counted as "+(q+1)" by its last row and
+      // "-p" by its first (mod 2^32): two atomics per run however many warps it spans -- one atomic
+      // per warp and run made few-key inputs serialise on a handful of L2 addresses.
+      const u32 NONE = 0xfffffffeu;                                 // no group key (they are < 2^22)
       const u32 x = valid ? (u32)(k >> a.group_shift) : 0xffffffffu;
-      const u32 xprev = __shfl_up_sync(0xffffffffu, x, 1);
-      const bool head = valid && (lane == 0 || xprev != x);
-      const unsigned hm = __ballot_sync(0xffffffffu, head);
-      const unsigned vm = __ballot_sync(0xffffffffu, valid);
-      if (head) {
-        const unsigned above = hm & ~((2u << lane) - 1u);           // heads in higher lanes
-        const int end = above ? (__ffs(above) - 1) : __popc(vm);    // valid lanes form a prefix
-        atomicAdd(&a.group_count[x], (u32)(end - lane));
+      u32 xprev = __shfl_up_sync(0xffffffffu, x, 1);
+      u32 xnext = __shfl_down_sync(0xffffffffu, x, 1);
+      if (lane == 0)  xprev = (valid && p > 0) ? (u32)(staged_key<KeyT>(skey, p - 1) >> a.group_shift) : NONE;
+      if (lane == 31) xnext = (p + 1 < tile_n) ? (u32)(staged_key<KeyT>(skey, p + 1) >> a.group_shift) : NONE;
+      if (valid) {
+        const bool head = xprev != x, tail = xnext != x;
+        if (head || tail) atomicAdd(&a.group_count[x], (tail ? (u32)p + 1u : 0u) - (head ? (u32)p : 0u));
       }
     }
     if (valid) {
@@ -486,14 +528,17 @@ static int run_scatter(Src src, const PassIO& io, int64_t n, int shift, u32 mask
   a.tile_counts = tile_counts; a.group_count = group_count; a.group_shift = group_shift;
   a.narrow = io.narrow_out;
   constexpr size_t smem = PassCfg<KeyT, NBINS>::SMEM;
-  auto kern = scatter_kernel<KeyT, Src, NBINS, MINB>;
+  auto kern_b = scatter_kernel<KeyT, Src, NBINS, MINB, RANK_BALLOT>;
+  auto kern_m = scatter_kernel<KeyT, Src, NBINS, MINB, RANK_MASKS>;
   static bool configured = false;   // per instantiation
   if (!configured) {
-    DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DTB_CUDA_CHECK(cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DTB_CUDA_CHECK(cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   prof_begin("radix_scatter", s);
-  kern<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
+  if (g_opt_rank_ballot) kern_b<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
+  else                   kern_m<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
   prof_end(s);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
