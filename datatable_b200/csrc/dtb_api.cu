@@ -827,7 +827,6 @@ int dtb_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "verbose")) { opt_verbose = value; return DTB_OK; }
   if (!strcmp(name, "profile")) { opt_profile = value; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { opt_overlap = value; return DTB_OK; }
-  if (!strcmp(name, "rank_ballot")) { g_opt_rank_ballot = value ? 1 : 0; return DTB_OK; }
   if (!strcmp(name, "hybrid_sort")) { opt_hybrid = value; return DTB_OK; }
   if (!strcmp(name, "trim_scratch")) { if (t_arena.depth == 0) t_arena.trim(); return DTB_OK; }
   set_error(std::string("unknown option ") + name);
@@ -852,7 +851,6 @@ int dtb_get_option(const char* name, int64_t* value) {
   if (!strcmp(name, "verbose")) { *value = opt_verbose; return DTB_OK; }
   if (!strcmp(name, "profile")) { *value = opt_profile; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { *value = opt_overlap; return DTB_OK; }
-  if (!strcmp(name, "rank_ballot")) { *value = g_opt_rank_ballot; return DTB_OK; }
   if (!strcmp(name, "hybrid_sort")) { *value = opt_hybrid; return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;

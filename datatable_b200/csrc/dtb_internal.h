@@ -179,8 +179,6 @@ int launch_gather(const void* src, int stype, int64_t nrows_src, const void* ord
 
 int launch_iota32(int32_t* out, int64_t n, cudaStream_t s);
 
-extern int g_opt_rank_ballot;   // scatter pass: rank with ballots (1, default) or shared-memory masks (0)
-
 // Hybrid sort of wide single keys: order rows that tie on the top key bits by their low bits
 // (dtb_tiefix.cu).  counters: device uint32[2] = {long runs, fallback flag}.
 int launch_tie_fix(const uint32_t* top_keys, int32_t* order, int64_t begin, int64_t end, const KeyNorm& k,

@@ -75,12 +75,12 @@ constexpr int CHUNK_ROWS = PASS_TILE * CHUNK_TILES;           // 65536 rows per 
 int64_t radix_num_chunks(int64_t n) { return (n + CHUNK_ROWS - 1) / CHUNK_ROWS; }
 
 // ===========================================================================
-// count: tile_counts[tile][digit] (u16) and counts[chunk][digit]
+// count: tile_pre[tile][digit] (u16, rows of the digit in the earlier tiles of the chunk) and counts[chunk][digit]
 // ===========================================================================
 template <typename KeyT, typename Src, int NBINS>
 __global__ void __launch_bounds__(PASS_THREADS)
 count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u32* __restrict__ counts,
-             unsigned short* __restrict__ tile_counts, KeyT* __restrict__ keys_out)
+             unsigned short* __restrict__ tile_pre, KeyT* __restrict__ keys_out)
 {
   // keys_out (first pass over a raw column): also store the normalised keys, so that the scatter
   // kernel of this pass streams 32/64-bit keys like every later pass instead of re-normalising.
@@ -118,7 +118,9 @@ count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u3
 #pragma unroll
     for (int j = 0; j < BPT; j++) {
       const u32 c = h[threadIdx.x + j * PASS_THREADS];
-      tile_counts[(size_t)(base / PASS_TILE) * NBINS + threadIdx.x + j * PASS_THREADS] = (unsigned short)c;   // <= 4096
+      // rows of this digit in the EARLIER tiles of the chunk (<= 15 * 4096, fits 16 bits): the scatter
+      // kernel adds it to the digit base and the chunk offset without walking the chunk's tiles
+      tile_pre[(size_t)(base / PASS_TILE) * NBINS + threadIdx.x + j * PASS_THREADS] = (unsigned short)total[j];
       total[j] += c;
     }
   }
@@ -204,7 +206,7 @@ struct PassArgs {
   u32            mask;
   const u32*     chunk_offs;    // [nchunks][NBINS] rows of this digit in earlier chunks
   const u32*     digit_base;    // [NBINS] first output slot of every digit
-  const unsigned short* tile_counts;   // [ntiles][NBINS] rows of this digit in every tile
+  const unsigned short* tile_pre;      // [ntiles][NBINS] rows of this digit in the earlier tiles of the chunk
   u32*           group_count;   // optional (last pass, small key domains): rows per group key
   int            group_shift;
   int            narrow;        // 64-bit keys only, > 0: write (key >> narrow) as uint32 -- the low bits are consumed
@@ -240,9 +242,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
       "WAIT_DONE:\n\t}" :: "r"(b), "r"(parity) : "memory");
 }
 
-enum { RANK_MASKS = 0, RANK_BALLOT = 1 };
-int g_opt_rank_ballot = 1;          // option "rank_ballot"
-
 template <typename KeyT, int NBINS> struct PassCfg {
   static constexpr int WARPS = PASS_THREADS / 32;
   // 256 bins: row ids are prefetched into shared memory with cp.async; 1024 bins: the tables take that
@@ -261,21 +260,20 @@ template <typename KeyT, int NBINS> struct PassCfg {
 // scattered shared-memory write of the reorder phase is ONE 8-byte store per row, not two
 // 4-byte stores: shared-memory wavefronts, not HBM, bound this kernel.
 // Thread t owns the BPT = NBINS/256 consecutive digits t*BPT.. in the scan phase.
-template <typename KeyT, typename Src, int NBINS, bool FULL, int RANK>
+template <typename KeyT, typename Src, int NBINS, bool FULL, int NB>
 __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsigned char* smem_raw, u32* s_wsum,
-                                             uint64_t* s_bar, const int64_t base, const int tile_n)
+                                             uint64_t* s_bar, const int64_t base, const int tile_n,
+                                             const u32 (&bin_run)[NBINS / PASS_THREADS])
 {
   constexpr int THREADS = PASS_THREADS, IPT = PASS_IPT, TILE = PASS_TILE;
   constexpr int WARPS = THREADS / 32;
   constexpr int BPT = NBINS / THREADS;
   constexpr bool USE_RIDX = PassCfg<KeyT, NBINS>::USE_RIDX;
-  static_assert(sizeof(u32) * WARPS * NBINS <= (sizeof(KeyT) + sizeof(int32_t)) * TILE, "mask table must fit the staging area");
   unsigned short* whist = reinterpret_cast<unsigned short*>(smem_raw);
   u32* bin_dst    = reinterpret_cast<u32*>(smem_raw + sizeof(unsigned short) * WARPS * NBINS);
   KeyT* skey      = reinterpret_cast<KeyT*>(bin_dst + NBINS + 4);
   int32_t* sidx   = reinterpret_cast<int32_t*>(skey + TILE);
   int32_t* ridx   = sidx + TILE;
-  u32* wmask_all  = reinterpret_cast<u32*>(skey);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool have_idx = a.idx_in != nullptr;
@@ -285,10 +283,6 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
     u32* z = reinterpret_cast<u32*>(whist);
 #pragma unroll
     for (int j = 0; j < WARPS * NBINS / 2 / THREADS; j++) z[tid + j * THREADS] = 0;
-    if constexpr (RANK == RANK_MASKS) {
-#pragma unroll
-      for (int j = 0; j < WARPS * NBINS / THREADS; j++) wmask_all[tid + j * THREADS] = 0;
-    }
     if (USE_RIDX && have_idx) {
       const int32_t* g = a.idx_in + base;
       if (FULL) {
@@ -309,59 +303,46 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
     const int lp = wbase + i * 32 + lane;
     key[i] = (FULL || lp < tile_n) ? a.src.load(base + lp) : (KeyT)0;
   }
+  // first output slot of the thread's digits (loaded by the caller before the keys, parked here until
+  // the scan phase: the store waits for those loads only after the key loads are in flight)
+#pragma unroll
+  for (int j = 0; j < BPT; j++) bin_dst[tid * BPT + j] = bin_run[j];
   __syncthreads();
 
   // ---- rank inside the warp: rows with equal digits keep (item, lane) order ----
-  // The lanes holding the same digit ("peers") are found either
-  //   RANK_BALLOT: with one __ballot_sync per digit bit (peers = AND over the bits of "lanes whose bit
-  //     equals mine"): no shared-memory traffic, and the cost does not depend on how the digits are
-  //     distributed -- a hot digit makes the atomicOr form serialise on one shared-memory word;
-  //   RANK_MASKS: with a shared-memory atomicOr on a per-warp mask table.
+  // The lanes holding the same digit ("peers") are found with one __ballot_sync per digit bit
+  // (peers = AND over the bits of "lanes whose bit equals mine"), NB = digit width of the pass: no
+  // shared-memory traffic, and the cost does not depend on how the digits are distributed.
+  // Measured against a shared-memory atomicOr on a per-warp mask table (one word per digit): C2 scatter
+  // passes 13.3 -> 11.9 ms, float64 sort -11 %; a hot digit made the atomicOr form serialise on one word.
   // Never MATCH.ANY: on sm_100 it issues once per ~60 SM cycles and bound the whole kernel
   // (scripts/ubench/match_bench.cu).
   u32 rank2[IPT / 2];                                         // two 16-bit ranks per register
   unsigned short* myhist = whist + warp * NBINS;
-  u32* wmask = wmask_all + warp * NBINS;
   const unsigned lt = lanemask_lt();
-  const unsigned lanebit = 1u << lane;
-  constexpr int LOGB = (NBINS == 256) ? 8 : 10;
 #pragma unroll
   for (int i = 0; i < IPT; i++) {
     const bool valid = FULL || (wbase + i * 32 + lane) < tile_n;
     const u32 d = (u32)(key[i] >> a.shift) & a.mask;
-    if constexpr (RANK == RANK_BALLOT) {
-      unsigned peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+    unsigned peers = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-      for (int b = 0; b < LOGB; b++) {
-        // peers &= (lanes whose bit b equals mine); digit bits above the pass width are 0 in every
-        // lane and leave the mask unchanged.  4 instructions per bit (LOP3->P, VOTE, @!P NOT, AND).
-        asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-            "and.b32 t, %1, %2;\n\t"
-            "setp.ne.u32 p, t, 0;\n\t"
-            "vote.sync.ballot.b32 t, p, 0xffffffff;\n\t"
-            "@!p not.b32 t, t;\n\t"
-            "and.b32 %0, %0, t;\n\t}"
-            : "+r"(peers) : "r"(d), "r"(1u << b));
-      }
-      const unsigned short cnt = valid ? myhist[d] : (unsigned short)0;
-      const unsigned before = peers & lt;
-      const u32 r = (u32)cnt + (u32)__popc(before);
-      if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
-      __syncwarp();                                             // all reads of this round precede the update
-      if (valid && before == 0) myhist[d] = cnt + (unsigned short)__popc(peers);
-      __syncwarp();
-    } else {
-      if (valid) atomicOr(&wmask[d], lanebit);
-      __syncwarp();
-      unsigned peers = 0; unsigned short cnt = 0;
-      if (valid) { peers = wmask[d]; cnt = myhist[d]; }
-      const unsigned before = peers & lt;
-      const u32 r = (u32)cnt + (u32)__popc(before);
-      if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
-      __syncwarp();                                             // all reads of this round precede the update
-      if (valid && before == 0) { myhist[d] = cnt + (unsigned short)__popc(peers); wmask[d] = 0; }
-      __syncwarp();
+    for (int b = 0; b < NB; b++) {
+      // peers &= (lanes whose bit b equals mine): 4 instructions per bit (LOP3->P, VOTE, @!P NOT, AND)
+      asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+          "and.b32 t, %1, %2;\n\t"
+          "setp.ne.u32 p, t, 0;\n\t"
+          "vote.sync.ballot.b32 t, p, 0xffffffff;\n\t"
+          "@!p not.b32 t, t;\n\t"
+          "and.b32 %0, %0, t;\n\t}"
+          : "+r"(peers) : "r"(d), "r"(1u << b));
     }
+    const unsigned short cnt = valid ? myhist[d] : (unsigned short)0;
+    const unsigned before = peers & lt;
+    const u32 r = (u32)cnt + (u32)__popc(before);
+    if (i & 1) rank2[i >> 1] |= r << 16; else rank2[i >> 1] = r;
+    __syncwarp();                                               // all reads of this round precede the update
+    if (valid && before == 0) myhist[d] = cnt + (unsigned short)__popc(peers);
+    __syncwarp();
   }
   __syncthreads();
 
@@ -431,7 +412,7 @@ __device__ __forceinline__ KeyT staged_key(const KeyT* skey, int q) {
   else return skey[q];
 }
 
-template <typename KeyT, typename Src, int NBINS, int MINB, int RANK>
+template <typename KeyT, typename Src, int NBINS, int MINB, int NB>
 __global__ void __launch_bounds__(PASS_THREADS, MINB)
 scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
 {
@@ -452,22 +433,18 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
   const int64_t base = tile * TILE;
   const int tile_n = (int)((a.n - base) < (int64_t)TILE ? (a.n - base) : (int64_t)TILE);
   const int64_t chunk = tile / CHUNK_TILES;
-  const int jt = (int)(tile % CHUNK_TILES);
 
   // first output slot of the thread's digits for this tile: digit base + earlier chunks + earlier
-  // tiles of the chunk; parked in shared memory until the scan phase
+  // tiles of the chunk (three independent loads, issued ahead of the key loads)
+  u32 bin_run[BPT];
 #pragma unroll
   for (int j = 0; j < BPT; j++) {
     const int b = tid * BPT + j;
-    u32 bin_run = a.digit_base[b] + a.chunk_offs[(size_t)chunk * NBINS + b];
-    const unsigned short* tc = a.tile_counts + (size_t)(chunk * CHUNK_TILES) * NBINS + b;
-#pragma unroll 4
-    for (int t = 0; t < jt; t++) bin_run += (u32)tc[(size_t)t * NBINS];
-    bin_dst[b] = bin_run;
+    bin_run[j] = a.digit_base[b] + a.chunk_offs[(size_t)chunk * NBINS + b] + (u32)a.tile_pre[(size_t)tile * NBINS + b];
   }
 
-  if (tile_n == TILE) scatter_tile<KeyT, Src, NBINS, true,  RANK>(a, smem_raw, s_wsum, &s_bar, base, tile_n);
-  else                scatter_tile<KeyT, Src, NBINS, false, RANK>(a, smem_raw, s_wsum, &s_bar, base, tile_n);
+  if (tile_n == TILE) scatter_tile<KeyT, Src, NBINS, true,  NB>(a, smem_raw, s_wsum, &s_bar, base, tile_n, bin_run);
+  else                scatter_tile<KeyT, Src, NBINS, false, NB>(a, smem_raw, s_wsum, &s_bar, base, tile_n, bin_run);
 
   // ---- coalesced scatter: consecutive threads write consecutive slots of a digit run ----
   const int lane = tid & 31;
@@ -525,20 +502,21 @@ static int run_scatter(Src src, const PassIO& io, int64_t n, int shift, u32 mask
   PassArgs<KeyT, Src> a;
   a.src = src; a.idx_in = io.idx_in; a.keys_out = (KeyT*)io.keys_out; a.idx_out = io.idx_out;
   a.n = n; a.shift = shift; a.mask = mask; a.chunk_offs = counts; a.digit_base = base;
-  a.tile_counts = tile_counts; a.group_count = group_count; a.group_shift = group_shift;
+  a.tile_pre = tile_counts; a.group_count = group_count; a.group_shift = group_shift;
   a.narrow = io.narrow_out;
   constexpr size_t smem = PassCfg<KeyT, NBINS>::SMEM;
-  auto kern_b = scatter_kernel<KeyT, Src, NBINS, MINB, RANK_BALLOT>;
-  auto kern_m = scatter_kernel<KeyT, Src, NBINS, MINB, RANK_MASKS>;
-  static bool configured = false;   // per instantiation
-  if (!configured) {
-    DTB_CUDA_CHECK(cudaFuncSetAttribute(kern_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DTB_CUDA_CHECK(cudaFuncSetAttribute(kern_m, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+  // NB = ballots per row in the rank phase = digit width, rounded up to a built variant
+  void (*kern)(const PassArgs<KeyT, Src>) = nullptr;
+  if constexpr (NBINS == 256) {
+    const int bits = __builtin_popcount(mask);
+    kern = bits <= 6 ? scatter_kernel<KeyT, Src, NBINS, MINB, 6>
+         : bits == 7 ? scatter_kernel<KeyT, Src, NBINS, MINB, 7> : scatter_kernel<KeyT, Src, NBINS, MINB, 8>;
+  } else {
+    kern = scatter_kernel<KeyT, Src, NBINS, MINB, 10>;
   }
+  DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin("radix_scatter", s);
-  if (g_opt_rank_ballot) kern_b<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
-  else                   kern_m<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
+  kern<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
   prof_end(s);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());

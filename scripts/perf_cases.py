@@ -1,4 +1,4 @@
-"""A/B of the scatter kernel's ranking variants (option "rank_ballot") on C2-shaped and skewed input."""
+"""Step time and per-kernel-family split on C2-shaped, skewed and float64-sort input (diagnostic)."""
 import sys, torch
 sys.path.insert(0, ".")
 from datatable_b200 import engine, _lib
@@ -37,9 +37,6 @@ cases.append(("power-law (n/4)", gb, z))
 cases.append(("2 keys (n/4)", gb, torch.randint(0, 2, (m,), generator=g, device="cuda", dtype=torch.int32)))
 cases.append(("f64 sort (n/4)", so, torch.randn(m, generator=g, device="cuda", dtype=torch.float64)))
 for name, mk, k in cases:
-    for mode in (1, 0):
-        engine.set_option("rank_ballot", mode)
-        f = mk(k)
-        best, avg = timed(f)
-        print(f"{name:22s} rank_ballot={mode}  best {best:7.2f} ms  avg {avg:7.2f} ms  [{families(f)}]", flush=True)
-engine.set_option("rank_ballot", 1)
+    f = mk(k)
+    best, avg = timed(f)
+    print(f"{name:22s} best {best:7.2f} ms  avg {avg:7.2f} ms  [{families(f)}]", flush=True)

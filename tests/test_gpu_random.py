@@ -346,16 +346,14 @@ def test_rows_beyond_2_pow_30():
     gb.close()
 
 
-@pytest.mark.parametrize("rank_ballot", [1, 0])
-@pytest.mark.parametrize("bits", [4, 8, 10])
-def test_digit_width_option_gives_identical_results(bits, rank_ballot):
-    """The RowIndex / offsets must not depend on the digit width of the passes (256- and 1024-bin kernels)
-    nor on how the scatter kernel finds equal digits inside a warp (ballots / shared-memory masks)."""
+@pytest.mark.parametrize("bits", [4, 6, 7, 8, 10])
+def test_digit_width_option_gives_identical_results(bits):
+    """The RowIndex / offsets must not depend on the digit width of the passes (6/7/8-ballot variants of
+    the 256-bin kernel, 1024-bin kernel)."""
     from datatable_b200 import engine
     from oracle import oracle as orc
     rng = np.random.default_rng(bits)
     n = 300_007
-    engine.set_option("rank_ballot", rank_ballot)
     cases = [(make_col(rng, INT32, n, "unit", 0.02), INT32), (make_col(rng, FLOAT64, n, "wide", 0.02), FLOAT64),
              (make_col(rng, INT64, n, "wide", 0.0), INT64)]
     engine.set_option("radix_bits", bits)
@@ -366,7 +364,6 @@ def test_digit_width_option_gives_identical_results(bits, rank_ballot):
             assert np.array_equal(got_o, want_o) and np.array_equal(got_f, want_f) and got_ng == want_ng
     finally:
         engine.set_option("radix_bits", 0)
-        engine.set_option("rank_ballot", 1)
 
 
 def test_hybrid_wide_key_sort_paths():
