@@ -472,8 +472,14 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
       const u32 x = valid ? (u32)(k >> a.group_shift) : 0xffffffffu;
       u32 xprev = __shfl_up_sync(0xffffffffu, x, 1);
       u32 xnext = __shfl_down_sync(0xffffffffu, x, 1);
-      if (lane == 0)  xprev = (valid && p > 0) ? (u32)(staged_key<KeyT>(skey, p - 1) >> a.group_shift) : NONE;
-      if (lane == 31) xnext = (p + 1 < tile_n) ? (u32)(staged_key<KeyT>(skey, p + 1) >> a.group_shift) : NONE;
+      // the neighbour outside the warp's window (lanes 0 and 31 only); every lane loads (slot 0 when it
+      // needs nothing: a broadcast) so that no branch is needed
+      const bool need = (lane == 0 && valid && p > 0) || (lane == 31 && p + 1 < tile_n);
+      const int q = need ? ((lane == 0) ? p - 1 : p + 1) : 0;
+      u32 xb = (u32)(staged_key<KeyT>(skey, q) >> a.group_shift);
+      xb = need ? xb : NONE;
+      xprev = (lane == 0) ? xb : xprev;
+      xnext = (lane == 31) ? xb : xnext;
       if (valid) {
         const bool head = xprev != x, tail = xnext != x;
         if (head || tail) atomicAdd(&a.group_count[x], (tail ? (u32)p + 1u : 0u) - (head ? (u32)p : 0u));

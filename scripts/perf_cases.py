@@ -3,6 +3,7 @@ import sys, torch
 sys.path.insert(0, ".")
 from datatable_b200 import engine, _lib
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
+if len(sys.argv) > 2: engine.set_option("radix_bits", int(sys.argv[2]))
 g = torch.Generator(device="cuda"); g.manual_seed(5)
 v = torch.rand(n, generator=g, device="cuda", dtype=torch.float64)
 
