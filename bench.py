@@ -122,10 +122,20 @@ def cpu_groupby_sum(k, v):
         return time.perf_counter() - t0, "reference", int(rdt.options.nthreads)
     from oracle import oracle as orc
     orc.build()
-    t0 = time.perf_counter()
-    o, f, ng = orc.group([k], [0], orc.NA_FIRST)
-    orc.reduce(orc.SUM, v, o, f)
-    return time.perf_counter() - t0, "port", 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 256))
+    orc.set_threads(cores)                              # chunk-parallel like the reference's own sort
+    try:
+        t0 = time.perf_counter()
+        o, f, ng = orc.group([k], [0], orc.NA_FIRST)
+        orc.reduce(orc.SUM, v, o, f)
+        dt = time.perf_counter() - t0
+    finally:
+        orc.set_threads(1)
+    return dt, "port", cores
 
 
 def host_sample(rows, groups, seed):

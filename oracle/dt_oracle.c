@@ -16,12 +16,45 @@
  * Each function cites the reference file:line it restates
  * (paths relative to /root/reference/src/core/).
  *
- * Plain C99, single-threaded, no dependencies.
+ * Plain C99 + pthreads.  Single-threaded by default (the parity tests); orc_set_threads(T)
+ * lets bench.py's CPU legs use the host's cores the way the reference does (its radix sort
+ * histograms and reorders chunk-parallel, sort.cc:904-1012, and its reducers are materialised
+ * group-parallel, column/column_impl.cc:78-103).  Results do not depend on T: every parallel
+ * region below is a static partition of the rows (or groups) with a deterministic combine.
  */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <pthread.h>
+
+/* ---- fork-join over T static parts ------------------------------------------------------- */
+#define ORC_MAX_THREADS 256
+static int g_threads = 1;
+void orc_set_threads(int t) { g_threads = t < 1 ? 1 : (t > ORC_MAX_THREADS ? ORC_MAX_THREADS : t); }
+int orc_get_threads(void) { return g_threads; }
+
+typedef void (*part_fn)(int t, int T, void* ctx);
+typedef struct { part_fn fn; void* ctx; int t, T; } part_arg;
+static void* part_tramp(void* p) { part_arg* a = (part_arg*)p; a->fn(a->t, a->T, a->ctx); return NULL; }
+static void par_run(int T, part_fn fn, void* ctx) {
+  if (T <= 1) { fn(0, 1, ctx); return; }
+  pthread_t th[ORC_MAX_THREADS]; part_arg arg[ORC_MAX_THREADS]; int started[ORC_MAX_THREADS];
+  for (int t = 1; t < T; t++) {
+    arg[t].fn = fn; arg[t].ctx = ctx; arg[t].t = t; arg[t].T = T;
+    started[t] = (pthread_create(&th[t], NULL, part_tramp, &arg[t]) == 0);
+  }
+  fn(0, T, ctx);
+  for (int t = 1; t < T; t++) {
+    if (started[t]) pthread_join(th[t], NULL);
+    else fn(t, T, ctx);                                  /* could not start a thread: do its part here */
+  }
+}
+/* rows [lo, hi) of part t out of T */
+static void part(int64_t n, int t, int T, int64_t* lo, int64_t* hi) {
+  *lo = n / T * t + (n % T) * t / T; *hi = n / T * (t + 1) + (n % T) * (t + 1) / T;
+}
+static int threads_for(int64_t n) { return n < 65536 ? 1 : g_threads; }
 
 /* stype codes: src/datatable/include/datatable.h:32-42 */
 enum {
@@ -72,71 +105,106 @@ static int64_t read_int(const void* p, int st, int64_t i, int* na) {
  * Returns the number of significant bits (sort.cc:735-736), or -1 for an
  * unsupported stype (NotImplError at sort.cc:673).
  *--------------------------------------------------------------------------*/
-static int normalise(const void* col, int st, int desc, int na_pos,
-                     int64_t n, uint64_t* x, int64_t* nacount)
+typedef struct {
+  const void* col; int st, desc, na_pos; int64_t n; uint64_t* x;
+  int phase;                       /* ints: 0 = stats, 1 = fill */
+  int64_t mn, mx;                  /* ints, phase 1 */
+  int64_t nna[ORC_MAX_THREADS], pmn[ORC_MAX_THREADS], pmx[ORC_MAX_THREADS];
+} norm_ctx;
+
+static void normalise_part(int t, int T, void* vc)
 {
+  norm_ctx* c = (norm_ctx*)vc;
+  int64_t lo, hi; part(c->n, t, T, &lo, &hi);
+  const void* col = c->col; const int st = c->st, desc = c->desc, na_pos = c->na_pos;
+  uint64_t* x = c->x;
   int64_t nna = 0;
   if (st == ST_BOOL) {
     const uint8_t* xi = (const uint8_t*)col;
     uint8_t rep = (na_pos == NA_LAST) ? 3 : 0;
-    for (int64_t j = 0; j < n; j++) {
-      uint8_t t = xi[j];
-      if (t == 128) { x[j] = rep; nna++; }
-      else x[j] = desc ? (uint8_t)((uint8_t)(128 - t) >> 6) : (uint8_t)(t + 1);
+    for (int64_t j = lo; j < hi; j++) {
+      uint8_t t8 = xi[j];
+      if (t8 == 128) { x[j] = rep; nna++; }
+      else x[j] = desc ? (uint8_t)((uint8_t)(128 - t8) >> 6) : (uint8_t)(t8 + 1);
     }
-    *nacount = nna;
-    return 2;
-  }
-  if (st == ST_FLOAT32) {
+  } else if (st == ST_FLOAT32) {
     const uint32_t* xi = (const uint32_t*)col;
     const uint32_t EXP = 0x7F800000u, SIG = 0x007FFFFFu, SBT = 0x80000000u;
     uint32_t rep = (na_pos == NA_LAST) ? 0xFFFFFFFFu : 0;
-    for (int64_t j = 0; j < n; j++) {
-      uint32_t t = xi[j];
-      if ((t & EXP) == EXP && (t & SIG) != 0) { x[j] = rep; nna++; }
-      else x[j] = desc ? (uint32_t)(t ^ (~SBT & ((t >> 31) - 1)))
-                       : (uint32_t)(t ^ (SBT | (0u - (t >> 31))));
+    for (int64_t j = lo; j < hi; j++) {
+      uint32_t u = xi[j];
+      if ((u & EXP) == EXP && (u & SIG) != 0) { x[j] = rep; nna++; }
+      else x[j] = desc ? (uint32_t)(u ^ (~SBT & ((u >> 31) - 1)))
+                       : (uint32_t)(u ^ (SBT | (0u - (u >> 31))));
     }
-    *nacount = nna;
-    return 32;
-  }
-  if (st == ST_FLOAT64) {
+  } else if (st == ST_FLOAT64) {
     const uint64_t* xi = (const uint64_t*)col;
     const uint64_t EXP = 0x7FF0000000000000ull, SIG = 0x000FFFFFFFFFFFFFull,
                    SBT = 0x8000000000000000ull;
     uint64_t rep = (na_pos == NA_LAST) ? ~0ull : 0;
-    for (int64_t j = 0; j < n; j++) {
-      uint64_t t = xi[j];
-      if ((t & EXP) == EXP && (t & SIG) != 0) { x[j] = rep; nna++; }
-      else x[j] = desc ? (t ^ (~SBT & ((t >> 63) - 1)))
-                       : (t ^ (SBT | (0ull - (t >> 63))));
+    for (int64_t j = lo; j < hi; j++) {
+      uint64_t u = xi[j];
+      if ((u & EXP) == EXP && (u & SIG) != 0) { x[j] = rep; nna++; }
+      else x[j] = desc ? (u ^ (~SBT & ((u >> 63) - 1)))
+                       : (u ^ (SBT | (0ull - (u >> 63))));
     }
-    *nacount = nna;
-    return 64;
+  } else if (c->phase == 0) {
+    /* integer family, pass 1: the column's non-NA min / max (stats.cc:601-634) */
+    int64_t mn = 0, mx = 0; int have = 0;
+    for (int64_t j = lo; j < hi; j++) {
+      int na; int64_t v = read_int(col, st, j, &na);
+      if (na) { nna++; continue; }
+      if (!have) { mn = mx = v; have = 1; }
+      else { if (v < mn) mn = v; if (v > mx) mx = v; }
+    }
+    c->pmn[t] = have ? mn : INT64_MAX;
+    c->pmx[t] = have ? mx : INT64_MIN;
+  } else {
+    /* integer family, pass 2 */
+    const int sz = stype_size(st);
+    const uint64_t tmask = (sz == 8) ? ~0ull : ((1ull << (8 * sz)) - 1);
+    const uint64_t range1 = ((uint64_t)c->mx - (uint64_t)c->mn + 1) & tmask;
+    const uint64_t rep = (na_pos == NA_LAST) ? range1 : 0;
+    const uint64_t inc = (na_pos == NA_LAST) ? 0 : 1;
+    for (int64_t j = lo; j < hi; j++) {
+      int na; int64_t v = read_int(col, st, j, &na);
+      if (na) x[j] = rep;
+      else x[j] = (desc ? ((uint64_t)c->mx - (uint64_t)v + inc)
+                        : ((uint64_t)v - (uint64_t)c->mn + inc)) & tmask;
+    }
+    return;
   }
-  int sz = stype_size(st);
+  c->nna[t] = nna;
+}
+
+static int normalise(const void* col, int st, int desc, int na_pos,
+                     int64_t n, uint64_t* x, int64_t* nacount)
+{
+  const int sz = stype_size(st);
   if (sz == 0) return -1;
-  /* integer family */
-  int64_t mn = 0, mx = 0; int have = 0;
-  for (int64_t j = 0; j < n; j++) {
-    int na; int64_t t = read_int(col, st, j, &na);
-    if (na) { nna++; continue; }
-    if (!have) { mn = mx = t; have = 1; }
-    else { if (t < mn) mn = t; if (t > mx) mx = t; }
-  }
-  uint64_t range1 = (uint64_t)mx - (uint64_t)mn + 1;   /* max - min + 1 */
-  uint64_t tmask = (sz == 8) ? ~0ull : ((1ull << (8 * sz)) - 1);
-  range1 &= tmask;
-  int nsig = 0; { uint64_t r = range1; while (r) { nsig++; r >>= 1; } }
-  uint64_t rep = (na_pos == NA_LAST) ? range1 : 0;
-  uint64_t inc = (na_pos == NA_LAST) ? 0 : 1;
-  for (int64_t j = 0; j < n; j++) {
-    int na; int64_t t = read_int(col, st, j, &na);
-    if (na) x[j] = rep;
-    else x[j] = (desc ? ((uint64_t)mx - (uint64_t)t + inc)
-                      : ((uint64_t)t - (uint64_t)mn + inc)) & tmask;
-  }
+  const int T = threads_for(n);
+  norm_ctx* c = (norm_ctx*)calloc(1, sizeof(norm_ctx));
+  c->col = col; c->st = st; c->desc = desc; c->na_pos = na_pos; c->n = n; c->x = x; c->phase = 0;
+  par_run(T, normalise_part, c);
+  int64_t nna = 0;
+  for (int t = 0; t < T; t++) nna += c->nna[t];
   *nacount = nna;
+  int nsig;
+  if (st == ST_BOOL) nsig = 2;
+  else if (st == ST_FLOAT32) nsig = 32;
+  else if (st == ST_FLOAT64) nsig = 64;
+  else {
+    int64_t mn = INT64_MAX, mx = INT64_MIN;
+    for (int t = 0; t < T; t++) { if (c->pmn[t] < mn) mn = c->pmn[t]; if (c->pmx[t] > mx) mx = c->pmx[t]; }
+    if (mn > mx) { mn = 0; mx = 0; }                     /* no valid value */
+    uint64_t range1 = (uint64_t)mx - (uint64_t)mn + 1;   /* max - min + 1 */
+    uint64_t tmask = (sz == 8) ? ~0ull : ((1ull << (8 * sz)) - 1);
+    range1 &= tmask;
+    nsig = 0; { uint64_t r = range1; while (r) { nsig++; r >>= 1; } }
+    c->phase = 1; c->mn = mn; c->mx = mx;
+    par_run(T, normalise_part, c);
+  }
+  free(c);
   return nsig;
 }
 
@@ -145,23 +213,77 @@ static int normalise(const void* col, int st, int desc, int na_pos,
  * (sort.cc:1129-1353, sort_insert.cc:96-144); its contract is only
  * "stable ascending order of the normalised key" (sort.cc:27-33), which an
  * LSD pass sequence satisfies identically. */
+typedef struct {
+  uint64_t* k; int32_t* o; uint64_t* k2; int32_t* o2; int64_t n; int shift; int64_t* hist; int phase;
+} lsd_ctx;
+
+static void lsd_part(int t, int T, void* vc)
+{
+  lsd_ctx* c = (lsd_ctx*)vc;
+  int64_t lo, hi; part(c->n, t, T, &lo, &hi);
+  int64_t* h = c->hist + (size_t)t * 256;
+  const uint64_t* k = c->k; const int shift = c->shift;
+  if (c->phase == 0) {
+    for (int64_t i = lo; i < hi; i++) h[(k[i] >> shift) & 255]++;
+  } else if (c->phase == 1) {
+    for (int64_t i = lo; i < hi; i++) {
+      int64_t d = h[(k[i] >> shift) & 255]++;
+      c->k2[d] = k[i]; c->o2[d] = c->o[i];
+    }
+  } else {
+    memcpy(c->k + lo, c->k2 + lo, (size_t)(hi - lo) * sizeof(uint64_t));
+    memcpy(c->o + lo, c->o2 + lo, (size_t)(hi - lo) * sizeof(int32_t));
+  }
+}
+
 static void lsd_pairs(uint64_t* k, int32_t* o, uint64_t* k2, int32_t* o2,
                       int64_t n, int nbits)
 {
+  /* chunk-parallel like the reference (build_histogram / reorder_data, sort.cc:904-1012): every
+   * part counts its contiguous chunk, the (digit, chunk) prefix gives each chunk its output slots,
+   * every part scatters its chunk -- stable because chunks keep their order inside a digit */
+  const int T = threads_for(n);
+  int64_t* hist = (int64_t*)malloc((size_t)T * 256 * sizeof(int64_t));
+  lsd_ctx c; c.k = k; c.o = o; c.k2 = k2; c.o2 = o2; c.n = n; c.hist = hist;
   for (int shift = 0; shift < nbits; shift += 8) {
-    int64_t hist[256]; memset(hist, 0, sizeof hist);
-    for (int64_t i = 0; i < n; i++) hist[(k[i] >> shift) & 255]++;
+    memset(hist, 0, (size_t)T * 256 * sizeof(int64_t));
+    c.shift = shift; c.phase = 0;
+    par_run(T, lsd_part, &c);
     int constant = 0;
-    for (int b = 0; b < 256; b++) if (hist[b] == n) constant = 1;
+    for (int b = 0; b < 256; b++) {
+      int64_t tot = 0;
+      for (int t = 0; t < T; t++) tot += hist[(size_t)t * 256 + b];
+      if (tot == n) constant = 1;
+    }
     if (constant) continue;
     int64_t run = 0;
-    for (int b = 0; b < 256; b++) { int64_t c = hist[b]; hist[b] = run; run += c; }
-    for (int64_t i = 0; i < n; i++) {
-      int64_t d = hist[(k[i] >> shift) & 255]++;
-      k2[d] = k[i]; o2[d] = o[i];
-    }
-    memcpy(k, k2, (size_t)n * sizeof(uint64_t));
-    memcpy(o, o2, (size_t)n * sizeof(int32_t));
+    for (int b = 0; b < 256; b++)
+      for (int t = 0; t < T; t++) {
+        int64_t cnt = hist[(size_t)t * 256 + b]; hist[(size_t)t * 256 + b] = run; run += cnt;
+      }
+    c.phase = 1; par_run(T, lsd_part, &c);
+    c.phase = 2; par_run(T, lsd_part, &c);
+  }
+  free(hist);
+}
+
+typedef struct {
+  int64_t n; int32_t* order; const uint64_t* x; uint64_t* k; uint8_t* head; int32_t* offsets; int phase;
+  int64_t pc[ORC_MAX_THREADS];
+} grp_ctx;
+
+static void grp_part(int t, int T, void* vc)
+{
+  grp_ctx* c = (grp_ctx*)vc;
+  int64_t lo, hi; part(c->n, t, T, &lo, &hi);
+  switch (c->phase) {
+    case 0: for (int64_t i = lo; i < hi; i++) c->order[i] = (int32_t)i; break;
+    case 1: for (int64_t i = lo; i < hi; i++) c->k[i] = c->x[c->order[i]]; break;
+    case 2: for (int64_t i = (lo > 1 ? lo : 1); i < hi; i++)
+              if (c->x[c->order[i]] != c->x[c->order[i - 1]]) c->head[i] = 1;
+            break;
+    case 3: { int64_t cnt = 0; for (int64_t i = lo; i < hi; i++) cnt += c->head[i]; c->pc[t] = cnt; break; }
+    case 4: { int64_t g = c->pc[t]; for (int64_t i = lo; i < hi; i++) if (c->head[i]) c->offsets[g++] = (int32_t)i; break; }
   }
 }
 
@@ -196,7 +318,9 @@ int orc_group(const void** cols, const int* stypes, const int* flags,
   uint64_t* k2 = (uint64_t*)malloc((size_t)n * 8);
   int32_t*  o2 = (int32_t*) malloc((size_t)n * 4);
   uint8_t* head = (uint8_t*)calloc((size_t)n, 1);
-  for (int64_t i = 0; i < n; i++) order[i] = (int32_t)i;
+  grp_ctx gc; gc.n = n; gc.order = order; gc.x = x; gc.k = k; gc.head = head; gc.offsets = offsets;
+  const int T = threads_for(n);
+  gc.phase = 0; par_run(T, grp_part, &gc);              /* order[i] = i */
 
   /* number of leading "by" columns whose values define the groups
    * (sort.cc:1471-1482: groups are frozen at the by -> sort transition) */
@@ -212,7 +336,7 @@ int orc_group(const void** cols, const int* stypes, const int* flags,
                          na_pos, n, x, &nna);
     if (nsig < 0) { rc = -1; break; }
     if (c == ncols - 1) nacount_last = nna;
-    for (int64_t i = 0; i < n; i++) k[i] = x[order[i]];
+    gc.phase = 1; par_run(T, grp_part, &gc);            /* k[i] = x[order[i]] */
     lsd_pairs(k, order, k2, o2, n, nsig);
   }
   if (rc == 0) {
@@ -223,11 +347,13 @@ int orc_group(const void** cols, const int* stypes, const int* flags,
         int64_t nna;
         normalise(cols[c], stypes[c], (flags[c] & FLAG_DESCENDING) != 0,
                   na_pos, n, x, &nna);
-        for (int64_t i = 1; i < n; i++)
-          if (x[order[i]] != x[order[i - 1]]) head[i] = 1;
+        gc.phase = 2; par_run(T, grp_part, &gc);        /* head[i] |= x[order[i]] != x[order[i-1]] */
       }
+      /* heads -> offsets: per-part counts, prefix, fill */
+      gc.phase = 3; par_run(T, grp_part, &gc);
       int64_t ng = 0;
-      for (int64_t i = 0; i < n; i++) if (head[i]) offsets[ng++] = (int32_t)i;
+      for (int t = 0; t < T; t++) { int64_t cnt = gc.pc[t]; gc.pc[t] = ng; ng += cnt; }
+      gc.phase = 4; par_run(T, grp_part, &gc);
       offsets[ng] = (int32_t)n;
       *ngroups = ng;
     } else {
@@ -279,12 +405,39 @@ int orc_gather(const void* src, int st, const int32_t* idx, int64_t n, void* out
  *         value wins; no valid rows -> NA.
  *   COUNT/COUNTNA column/count.h:35-56; NROWS column/count.h:82-87 -> int64.
  *--------------------------------------------------------------------------*/
+typedef struct {
+  int op; const void* v; int st; const int32_t* order; const int32_t* offsets; int64_t ng; void* out;
+} red_ctx;
+
+static void reduce_groups(int op, const void* v, int st, const int32_t* order,
+                          const int32_t* offsets, int64_t g_lo, int64_t g_hi, void* out);
+
+static void red_part(int t, int T, void* vc)
+{
+  /* groups are dealt out in blocks of 1024 round-robin, so that a few huge groups do not all land
+   * in one part (the reference's parallel_for_static over groups, column_impl.h:106) */
+  red_ctx* c = (red_ctx*)vc;
+  for (int64_t g0 = (int64_t)t * 1024; g0 < c->ng; g0 += (int64_t)T * 1024) {
+    int64_t g1 = g0 + 1024 < c->ng ? g0 + 1024 : c->ng;
+    reduce_groups(c->op, c->v, c->st, c->order, c->offsets, g0, g1, c->out);
+  }
+}
+
 int orc_reduce(int op, const void* v, int st, const int32_t* order,
                const int32_t* offsets, int64_t ng, void* out)
 {
-  int isf = (st == ST_FLOAT32 || st == ST_FLOAT64);
+  if (op < OP_SUM || op > OP_NROWS) return -1;
   if (op != OP_NROWS && !stype_size(st)) return -1;
-  for (int64_t g = 0; g < ng; g++) {
+  red_ctx c; c.op = op; c.v = v; c.st = st; c.order = order; c.offsets = offsets; c.ng = ng; c.out = out;
+  par_run(ng < 4096 ? 1 : g_threads, red_part, &c);
+  return 0;
+}
+
+static void reduce_groups(int op, const void* v, int st, const int32_t* order,
+                          const int32_t* offsets, int64_t g_lo, int64_t g_hi, void* out)
+{
+  int isf = (st == ST_FLOAT32 || st == ST_FLOAT64);
+  for (int64_t g = g_lo; g < g_hi; g++) {
     int64_t i0 = offsets[g], i1 = offsets[g + 1];
     if (op == OP_NROWS) { ((int64_t*)out)[g] = i1 - i0; continue; }
     int64_t isum = 0; float fsum = 0.0f; double dsum = 0.0;
@@ -335,8 +488,7 @@ int orc_reduce(int op, const void* v, int st, const int32_t* order,
         break;
       case OP_COUNT:   ((int64_t*)out)[g] = cnt; break;
       case OP_COUNTNA: ((int64_t*)out)[g] = (i1 - i0) - cnt; break;
-      default: return -1;
+      default: break;
     }
   }
-  return 0;
 }

@@ -53,6 +53,16 @@ def lib():
     return _lib
 
 
+def set_threads(t):
+    """Host threads of the parallel regions (default 1).  Results do not depend on it; only
+    bench.py's CPU legs raise it."""
+    lib().orc_set_threads(int(t))
+
+
+def get_threads():
+    return int(lib().orc_get_threads())
+
+
 def stype_of(a, stype=None):
     """stype code of a numpy array (bool columns may be passed as int8 + stype=BOOL)."""
     if stype is not None:
