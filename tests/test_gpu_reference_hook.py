@@ -1,0 +1,24 @@
+"""GPU: the REFERENCE itself, patched by integration/apply_hook.py so that its group() calls dtb_group
+(option sort.b200), must give the stock CPU results -- the drop-in boundary exercised from the
+reference's side.  Needs the patched build staged under integration/_ref_patched (git-ignored, built
+in the dev container from a scratch copy of the reference); skipped without it."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PATCHED = os.path.join(ROOT, "integration", "_ref_patched")
+
+
+def test_patched_reference_matches_its_own_cpu_path():
+    if not os.path.exists(os.path.join(PATCHED, "datatable", "__init__.py")):
+        pytest.skip("no patched reference build under integration/_ref_patched")
+    env = dict(os.environ, PYTHONPATH=PATCHED)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "check_hook.py")],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GPU path == CPU path" in r.stdout, r.stdout + r.stderr
