@@ -13,6 +13,10 @@ What it adds:
     bool/int/float key columns whose outputs are wrapped exactly like get_result_rowindex() /
     extract_groups() do (sort.cc:596-616).  DTB_ENOTIMPL falls through to the CPU path (outside the
     named path); any other error is raised as a dt RuntimeError with dtb_last_error().
+  * src/core/expr/fexpr_reduce_unary.cc -- option `sort.b200_reducers` (bool, default False; registered in
+    sort.cc): sum/mean/min/max/count/countna of a plain numeric column of the frame go through
+    `dtb_reduce` with the frame's RowIndex and the Groupby offsets, the result wrapped as a material
+    column of the reference's output stype.  Anything else keeps the reference's own reducer columns.
   * ci/ext.py         -- include path of include/dtb200.h, link + rpath of datatable_b200/lib/libdtb200.so.
 /root/reference itself is never touched.
 """
@@ -25,7 +29,9 @@ INCLUDE_ANCHOR = '#include "utils/misc.h"\n'
 INCLUDE_ADD = '#include <dtb200.h>      // B200 engine C-ABI (drop-in for group()); -I<repo>/include, see ci/ext.py\n'
 
 OPTION_ANCHOR = 'static bool sort_new = false;\n'
-OPTION_ADD = 'static bool sort_b200 = false;   // option sort.b200: route group() through libdtb200\n'
+OPTION_ADD = ('static bool sort_b200 = false;   // option sort.b200: route group() through libdtb200\n'
+              'static bool sort_b200_reducers = false;   // option sort.b200_reducers: reducers through dtb_reduce\n'
+              'bool dtb200_reducers_enabled() { return sort_b200_reducers; }\n')
 
 REGISTER_ANCHOR = '  dt::register_option(\n    "sort.new",'
 REGISTER_ADD = '''  dt::register_option(
@@ -33,6 +39,14 @@ REGISTER_ADD = '''  dt::register_option(
     []{ return py::obool(sort_b200); },
     [](const py::Arg& value) {
       sort_b200 = value.to_bool_strict();
+    },
+    nullptr);
+
+  dt::register_option(
+    "sort.b200_reducers",
+    []{ return py::obool(sort_b200_reducers); },
+    [](const py::Arg& value) {
+      sort_b200_reducers = value.to_bool_strict();
     },
     nullptr);
 
@@ -83,6 +97,75 @@ HOOK_ADD = '''  // ---- dtb200: the whole ordering + grouping on the GPU -------
 
 '''
 
+
+# ---- reducers: src/core/expr/fexpr_reduce_unary.cc ---------------------------------------------------
+RED_INCLUDE_ANCHOR = '#include "expr/workframe.h"\n'
+RED_INCLUDE_ADD = '''#include <cstring>
+#include "datatable.h"
+#include "stype.h"
+#include <dtb200.h>      // B200 engine C-ABI (reducers)
+bool dtb200_reducers_enabled();   // sort.cc, option sort.b200_reducers
+'''
+
+RED_HELPER_ANCHOR = 'FExpr_ReduceUnary::FExpr_ReduceUnary(ptrExpr&& arg)'
+RED_HELPER_ADD = '''// dtb200: reducer name -> DTB_OP_* (0 = not handled by the engine)
+static int dtb200_op_of(const std::string& name) {
+  if (name == "sum") return DTB_OP_SUM;
+  if (name == "mean") return DTB_OP_MEAN;
+  if (name == "min") return DTB_OP_MIN;
+  if (name == "max") return DTB_OP_MAX;
+  if (name == "count") return DTB_OP_COUNT;
+  if (name == "countna") return DTB_OP_COUNTNA;
+  return 0;
+}
+
+// dtb200: evaluate one reducer over a plain numeric column of frame `ifr` on the engine.
+// Returns false when the case is outside the engine's scope (the caller keeps the CPU path).
+static bool dtb200_reduce(EvalContext& ctx, size_t ifr, size_t icol, int op,
+                          const Groupby& gby, Column* out)
+{
+  const Column& src = ctx.get_datatable(ifr)->get_column(icol);
+  const RowIndex& ri = ctx.get_rowindex(ifr);
+  if (src.is_virtual() || gby.size() == 0) return false;
+  if (ri && !ri.isarr32()) return false;                       // ARR32 (the group() ordering) or identity
+  switch (src.stype()) {
+    case SType::BOOL: case SType::INT8: case SType::INT16: case SType::INT32:
+    case SType::INT64: case SType::FLOAT32: case SType::FLOAT64: break;
+    default: return false;
+  }
+  const int in_st = static_cast<int>(src.stype());             // SType values == DtStype_* codes
+  const int out_st = dtb_reduce_out_stype(op, in_st);
+  if (!out_st) return false;
+  const size_t ng = gby.size();
+  Buffer buf = Buffer::mem(ng * static_cast<size_t>(dtb_stype_size(out_st)));
+  dtb_col v; v.data = src.get_data_readonly(); v.stype = in_st; v.reserved = 0;
+  int rc = dtb_reduce(op, v, static_cast<int64_t>(src.nrows()),
+                      ri ? static_cast<const void*>(ri.indices32()) : nullptr, 0,
+                      gby.offsets_r(), static_cast<int64_t>(ng), nullptr, buf.xptr());
+  if (rc == DTB_ENOTIMPL) return false;
+  if (rc != DTB_OK) throw RuntimeError() << "dtb200: " << dtb_last_error();
+  *out = Column::new_mbuf_column(ng, static_cast<SType>(out_st), std::move(buf));
+  return true;
+}
+
+
+'''
+
+RED_LOOP_ANCHOR = '    Column coli = wf.retrieve_column(i);\n    coli = evaluate1('
+RED_LOOP_ADD = '''    {
+      // dtb200: a plain numeric column of the frame, reduced by sum/mean/min/max/count on the engine
+      size_t b200_ifr = 0, b200_icol = 0;
+      const int b200_op = dtb200_reducers_enabled() ? dtb200_op_of(name()) : 0;
+      if (b200_op && !is_wf_grouped && wf.is_reference_column(i, &b200_ifr, &b200_icol)) {
+        Column b200_out;
+        if (dtb200_reduce(ctx, b200_ifr, b200_icol, b200_op, gby, &b200_out)) {
+          outputs.add_column(std::move(b200_out), wf.retrieve_name(i), Grouping::GtoONE);
+          continue;
+        }
+      }
+    }
+'''
+
 EXT_ANCHOR = '            ext.compiler.add_linker_flag("-lstdc++")\n'
 EXT_ADD = '''            # dtb200: B200 engine C-ABI
             ext.compiler.add_compiler_flag("-I{inc}")
@@ -115,12 +198,18 @@ def main():
     s = insert(s, REGISTER_ANCHOR, REGISTER_ADD, before=True, what="option registration")
     s = insert(s, HOOK_ANCHOR, HOOK_ADD, before=True, what="group() hook")
     open(sort_cc, "w").write(s)
+    red_cc = os.path.join(tree, "src", "core", "expr", "fexpr_reduce_unary.cc")
+    r = open(red_cc).read()
+    r = insert(r, RED_INCLUDE_ANCHOR, RED_INCLUDE_ADD, before=False, what="reducer includes")
+    r = insert(r, RED_HELPER_ANCHOR, RED_HELPER_ADD, before=True, what="reducer helper")
+    r = insert(r, RED_LOOP_ANCHOR, RED_LOOP_ADD, before=True, what="reducer loop hook")
+    open(red_cc, "w").write(r)
     ext_py = os.path.join(tree, "ci", "ext.py")
     e = open(ext_py).read()
     add = EXT_ADD.format(inc=os.path.join(ROOT, "include"), lib=os.path.join(ROOT, "datatable_b200", "lib"))
     e = insert(e, EXT_ANCHOR, add, before=False, what="build flags")
     open(ext_py, "w").write(e)
-    print("apply_hook: patched", sort_cc, "and", ext_py)
+    print("apply_hook: patched", sort_cc, red_cc, "and", ext_py)
 
 
 if __name__ == "__main__":
