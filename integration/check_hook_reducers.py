@@ -7,7 +7,6 @@ With the option on, sum/mean/min/max/count/countna of plain numeric columns go t
   with sort.b200 on as well the whole DT[:, reducers, by(k)] runs on the engine.
 * no usable GPU: the engine's error must surface; reducers outside the engine's scope (prod, sd) and
   computed arguments (f.v * 2) must keep working through the reference's own columns.
-STATUS: compiled and dispatch-checked in the build container; the B200 equality run is still to be done.
 """
 import sys
 import numpy as np

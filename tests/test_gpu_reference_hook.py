@@ -14,11 +14,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PATCHED = os.path.join(ROOT, "integration", "_ref_patched")
 
 
-def test_patched_reference_matches_its_own_cpu_path():
+def _run(script):
     if not os.path.exists(os.path.join(PATCHED, "datatable", "__init__.py")):
         pytest.skip("no patched reference build under integration/_ref_patched")
     env = dict(os.environ, PYTHONPATH=PATCHED)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "check_hook.py")],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", script)],
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "GPU path == CPU path" in r.stdout, r.stdout + r.stderr
+    return r.stdout + r.stderr
+
+
+def test_patched_reference_matches_its_own_cpu_path():
+    """option sort.b200: the reference's group() through dtb_group"""
+    assert "GPU path == CPU path" in _run("check_hook.py")
+
+
+def test_patched_reference_reducers_match_its_own_cpu_path():
+    """option sort.b200_reducers: the reference's sum/mean/min/max/count through dtb_reduce, with its CPU
+    group() and with sort.b200 on (the whole DT[:, reducers, by(k)] on the engine)"""
+    out = _run("check_hook_reducers.py")
+    assert out.count("engine == CPU for 12 reducers") == 2, out
