@@ -1,11 +1,14 @@
 #!/usr/bin/env python
 """
-bench.py -- BASELINE.json's metric on BASELINE.json's config.
+bench.py -- BASELINE.json's metric on BASELINE.json's configs.
 
-    metric  : rows/sec of DT[:, sum(f.v), by(f.k)]  (groupby-sum)
+    metric  : rows/sec of DT[:, sum(f.v), by(f.k)]  (groupby-sum) ...
     config  : C2 = 1e9 rows, int32 key with 1e6 distinct values, float64 value, 1 x B200
-              (N > 1: every rank owns its own 1e9-row partition -> weak scaling; per-group
-               partials are merged with one NCCL all-gather + the same kernels)
+              (N > 1: every rank owns its own 1e9-row partition -> weak scaling; the per-group
+               partials are merged with an NCCL all-reduce of the dense per-key tables)
+              ... "; sort HBM GB/s vs peak": C3 (1e9-row float64 sort -> RowIndex) and C4 (2-key
+              groupby, 12 reducers) are timed at N = 1 in the same run and reported under
+              `other_configs` on the same JSON line.
 
 One "step" = one pass of the hot path over one batch:
     group() -> RowIndex + Groupby offsets, then the per-group SUM reducer.
@@ -14,8 +17,9 @@ One "step" = one pass of the hot path over one batch:
     e2e      the public Frame API on pinned HOST columns: H2D of k and v, the query,
              D2H of the result frame, all inside the timed region
     roofline dominant kernel (radix scatter pass): algorithmic bytes / CUDA-event time
-    cpu_baseline   the CPU oracle port (or the reference build under oracle/_ref when
-             present) on a bounded sample, timed on this box's host cores
+    cpu_baseline   the reference itself (oracle/_ref, an unmodified build of /root/reference staged by
+             oracle/build_ref.sh) or, where that is absent, the CPU oracle port, on a bounded sample,
+             timed on this box's host cores
 
 `--impl reference` times the CPU implementation alone and prints the same line.
 """
@@ -35,6 +39,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "rows/sec groupby-sum 1e9 int32 keys"
 UNIT = "rows/s"
+WORKLOAD = "C2: int32 key (1e6 distinct), float64 value, DT[:, sum(v), by(k)]"
 
 
 def parse():
@@ -46,9 +51,12 @@ def parse():
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (C2 = 1e9)")
     ap.add_argument("--groups", type=int, default=1_000_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-rows", type=int, default=50_000_000, help="bounded CPU sample per step")
+    ap.add_argument("--cpu-rows", type=int, default=0,
+                    help="rows per CPU step; 0 = the largest of 1e7/3e7/1e8/3e8/1e9 (<= --rows) whose run fits --cpu-budget")
+    ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds the whole CPU arm may take")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 sub-records")
     return ap.parse_args()
 
 
@@ -107,26 +115,41 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------
-# CPU side: the oracle port, or the reference itself when oracle/_ref holds a build of it
+# CPU side: the reference itself when oracle/_ref holds a build of it, else the oracle port
 # ---------------------------------------------------------------------------
-def cpu_groupby_sum(k, v):
-    """Returns (seconds, kind, cores) for DT[:, sum(v), by(k)] on host arrays."""
-    ref_dir = os.path.join(ROOT, "oracle", "_ref")
-    if os.path.exists(os.path.join(ref_dir, "datatable", "__init__.py")):
-        sys.path.insert(0, ref_dir)
-        import datatable as rdt                         # the reference, built from /root/reference
-        DT = rdt.Frame(k=k, v=v)
-        t0 = time.perf_counter()
-        R = DT[:, rdt.sum(rdt.f.v), rdt.by(rdt.f.k)]
-        R.materialize()
-        return time.perf_counter() - t0, "reference", int(rdt.options.nthreads)
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def have_reference():
+    return os.path.exists(os.path.join(REF_DIR, "datatable", "__init__.py"))
+
+
+def host_cores():
+    try:
+        return max(1, min(len(os.sched_getaffinity(0)), 256))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_groupby_sum(k, v, sort_new=False):
+    """Returns (seconds, kind, cores, ngroups) for DT[:, sum(v), by(k)] on host arrays."""
+    if have_reference():
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import datatable as rdt                         # the reference, built unmodified from /root/reference
+        rdt.options.sort.new = bool(sort_new)
+        try:
+            DT = rdt.Frame(k=k, v=v)
+            t0 = time.perf_counter()
+            R = DT[:, rdt.sum(rdt.f.v), rdt.by(rdt.f.k)]
+            R.materialize()
+            dt = time.perf_counter() - t0
+            return dt, "reference", int(rdt.options.nthreads), int(R.nrows)
+        finally:
+            rdt.options.sort.new = False
     from oracle import oracle as orc
     orc.build()
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-    cores = max(1, min(cores, 256))
+    cores = host_cores()
     orc.set_threads(cores)                              # chunk-parallel like the reference's own sort
     try:
         t0 = time.perf_counter()
@@ -135,7 +158,7 @@ def cpu_groupby_sum(k, v):
         dt = time.perf_counter() - t0
     finally:
         orc.set_threads(1)
-    return dt, "port", cores
+    return dt, "port", cores, int(ng)
 
 
 def host_sample(rows, groups, seed):
@@ -145,28 +168,61 @@ def host_sample(rows, groups, seed):
     return k, v
 
 
+LADDER = (10_000_000, 30_000_000, 100_000_000, 300_000_000, 1_000_000_000)
+
+
+def pick_cpu_rows(args, nsteps, make):
+    """Largest ladder size <= args.rows whose nsteps steps fit the CPU budget.  The reference's default
+    sort is far from linear in the row count (0.3 s at 1e7 rows, 13 s at 3e7 on 8 threads),
+    so every size is probed once instead of extrapolating.  Returns (rows, probes)."""
+    if args.cpu_rows > 0:
+        return min(args.rows, args.cpu_rows), []
+    t_start = time.perf_counter()
+    probes, best = [], min(args.rows, LADDER[0])
+    for rows in LADDER:
+        if rows > args.rows:
+            break
+        k, v = make(rows)
+        t, kind, cores, ng = cpu_groupby_sum(k, v)
+        probes.append({"rows": rows, "seconds": round(t, 3)})
+        spent = time.perf_counter() - t_start
+        if t * nsteps > args.cpu_budget - spent:
+            break
+        best = rows
+        # the next probe alone (>= 3x this one) must still leave room for the run at the current size
+        if spent + 3.0 * t + t * nsteps > args.cpu_budget:
+            break
+    return best, probes
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    rows = min(args.rows, args.cpu_rows)
+    nsteps = args.steps + args.warmup
+    rows, probes = pick_cpu_rows(args, nsteps, lambda r: host_sample(r, args.groups, 42))
     k, v = host_sample(rows, args.groups, 42)
     kind, cores = "port", 1
-    for _ in range(max(0, min(args.warmup, 1))):
+    for _ in range(args.warmup):
         cpu_groupby_sum(k, v)
     ts = []
     for _ in range(args.steps):
-        t, kind, cores = cpu_groupby_sum(k, v)
+        t, kind, cores, ng = cpu_groupby_sum(k, v)
         ts.append(t)
     ms = 1e3 * sum(ts) / len(ts)
     value = rows / (ms / 1e3)
+    why = ("the full C2 input" if rows == args.rows else
+           f"bounded sample: {nsteps} steps at the next ladder size do not fit the {args.cpu_budget:.0f} s CPU budget")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32 keys / float64 sums", "data": "synthetic",
-        "config": {"workload": "C2: int32 key (1e6 distinct), float64 value, DT[:, sum(v), by(k)]",
-                   "rows_per_step": rows, "groups": args.groups},
+        "config": {"workload": WORKLOAD, "rows_per_gpu": args.rows, "groups": args.groups},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{rows} rows of the C2 workload per step (uniform keys in [0,{args.groups}))"},
+                         "sample": f"{rows} rows of the C2 workload per step (uniform keys in [0,{args.groups})); {why}",
+                         "rows_per_step": rows, "probes": probes,
+                         "implementation": ("h2oai/datatable built unmodified from /root/reference (oracle/build_ref.sh), "
+                                            "default options (legacy SortContext path, nthreads = all cores)") if kind == "reference"
+                                           else "oracle/dt_oracle.c (pthreads port of the reference's algorithm)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -176,6 +232,75 @@ def run_reference(args, rank, world):
 # ---------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------
+def cuda_ms(torch, fn, reps):
+    ts, r = [], None
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sum(ts) / len(ts), r
+
+
+def other_configs(torch, engine, _lib, n, peak):
+    """C3 and C4 of BASELINE.json at N = 1, device-resident, CUDA-event timed (2 warm-up + 3 timed calls each),
+    each with a size-independent correctness check (the bit-exact parity runs at <= 1e8 rows are in tests/)."""
+    out = {}
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    # ---- C3: float64 column sort -> RowIndex (ARR32; the reference emits ARR32 below 2^31 rows, SURVEY.md mismatch 2)
+    x = torch.randn(n, generator=g, device="cuda", dtype=torch.float64)
+    x[::1000] = float("nan")
+
+    def c3():
+        h = engine.Groupby([x], [_lib.FLAG_SORT_ONLY], _lib.NA_FIRST)
+        return h
+    for _ in range(2):
+        c3().close()
+    ms, h = cuda_ms(torch, lambda: (c3()), 1)
+    st = _lib.last_call_stats()
+    xs = engine.gather(x, h.order_col())
+    nn = n // 1000 + (1 if n % 1000 else 0)
+    ok = bool(torch.isnan(xs[:nn]).all()) and bool((xs[nn + 1:] >= xs[nn:-1]).all())
+    h.close(); del xs
+    ms, _ = cuda_ms(torch, lambda: c3().close(), 3)
+    alg = 12.0 * n                                           # read the 8-byte key, write the 4-byte row id
+    out["C3"] = {"workload": "C3: float64 column sort (sign-flip image), N(0,1) + 0.1 % NaN -> RowIndex ARR32",
+                 "rows": n, "ms_per_step": ms, "rows_per_s": n / ms * 1e3,
+                 "alg_bytes_per_row": 12, "achieved_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak,
+                 "key_bits": st["key_bits"], "radix_passes": st["radix_passes"], "check_sorted_nan_first": ok}
+    del x
+    torch.cuda.empty_cache()
+    # ---- C4: (int64, int32) keys, mean/min/max/count over 3 float64 columns
+    k1 = torch.randint(0, 1000, (n,), generator=g, device="cuda", dtype=torch.int64) << 33
+    k2 = torch.randint(0, 1000, (n,), generator=g, device="cuda", dtype=torch.int32)
+    vs = [torch.randn(n, generator=g, device="cuda", dtype=torch.float64) for _ in range(3)]
+    for v in vs:
+        v[::100] = float("nan")
+    ops = [_lib.OP_MEAN, _lib.OP_MIN, _lib.OP_MAX, _lib.OP_COUNT]
+
+    def c4(keep=False):
+        gb = engine.Groupby([k1, k2], [0, 0], _lib.NA_FIRST, reducers=[(op, v) for v in vs for op in ops])
+        res = [gb.reduced(i) for i in range(12)] if keep else None
+        ng = gb.ngroups
+        gb.close()
+        return ng, res
+    c4()
+    ng, res = c4(keep=True)
+    valid0 = ~torch.isnan(vs[0])
+    ok = int(res[3].sum()) == int(valid0.sum())
+    ok = ok and float(torch.nan_to_num(res[2], nan=-1e300).max()) == float(vs[0][valid0].max())
+    ok = ok and float(torch.nan_to_num(res[1], nan=1e300).min()) == float(vs[0][valid0].min())
+    tot = float((res[0] * res[3]).sum()); want = float(vs[0][valid0].sum())
+    ok = ok and abs(tot - want) <= 1e-6 * max(1.0, abs(want)) * 10
+    del res, valid0
+    ms, _ = cuda_ms(torch, lambda: c4(), 3)
+    alg = 40.0 * n                                           # keys 8 + 4, three 8-byte value columns, 4-byte row id
+    out["C4"] = {"workload": "C4: by(int64 id<<33, int32 < 1000) -> 1e6 groups; mean/min/max/count over 3 float64 columns (1 % NaN)",
+                 "rows": n, "ms_per_step": ms, "rows_per_s": n / ms * 1e3, "ngroups": ng,
+                 "alg_bytes_per_row": 40, "achieved_GBps": alg / ms / 1e6, "frac_of_hbm_peak": alg / ms / 1e6 / peak,
+                 "checks_ok": bool(ok)}
+    return out
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -195,18 +320,25 @@ def run_b200(args, rank, local_rank, world):
     torch.cuda.synchronize()
 
     launches = [0]
+    main_prof = []            # profile records of the rank's own group()+reduce call (not of the merge)
+    profiling = [False]
 
     def step():
-        # group(): RowIndex int32[n] + Groupby offsets int32[ng+1], both left in HBM behind the handle
-        # and the SUM reducer, evaluated inside the same engine call (overlapped with the sort passes)
+        # group(): RowIndex int32[n] + Groupby offsets int32[ng+1], both left in HBM behind the handle,
+        # and the SUM reducer, evaluated inside the same engine call
         gb = engine.Groupby([k], [0], _lib.NA_FIRST, reducers=[(_lib.OP_SUM, v)])
         launches[0] += _lib.last_call_stats()["kernels_launched"]
+        if profiling[0]:
+            main_prof.extend(_lib.profile_records(reset=True))
         sums = gb.reduced(0)
         ng = gb.ngroups
         if world > 1:
             gkeys = engine.gather(k, gb.first_rows())
             launches[0] += 2
-            gkeys, sums = ddist.merge_partials(gkeys, sums, _lib.OP_SUM)
+            gkeys, sums = ddist.merge_partials_dense(gkeys, sums, _lib.OP_SUM)
+            launches[0] += ddist.LAST_MERGE_LAUNCHES
+            if profiling[0]:
+                _lib.profile_records(reset=True)
         gb.close()
         return None, None, ng, sums
 
@@ -220,6 +352,7 @@ def run_b200(args, rank, local_rank, world):
     barrier()
 
     engine.set_option("profile", 1)
+    profiling[0] = True
     _lib.profile_records(reset=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -235,7 +368,8 @@ def run_b200(args, rank, local_rank, world):
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     engine.set_option("profile", 0)
-    prof = _lib.profile_records(reset=True)
+    profiling[0] = False
+    _lib.profile_records(reset=True)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -254,21 +388,21 @@ def run_b200(args, rank, local_rank, world):
     if abs(tot - ref_tot) > 1e-6 * abs(ref_tot):
         raise SystemExit(f"bench.py: group sums do not add up: {tot} vs {ref_tot}")
 
-    # ---- roofline of the dominant kernel: the radix scatter passes --------------------------
+    # ---- roofline of the dominant kernel: the radix scatter passes of the rank's own call ------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     fam = {}
-    for name, ms in prof:
+    for name, ms in main_prof:
         fam.setdefault(name, []).append(ms)
     passes = fam.get("radix_scatter", [])
     npass_step = len(passes) // max(1, args.steps)
     # algorithmic bytes of one scatter launch over n rows (32-bit keys, int32 row ids):
-    #   first pass : read key 4 (row id = position) + write (key 4 + idx 4)  = 12 B/row
-    #   middle pass: read (key 4 + idx 4)           + write (key 4 + idx 4)  = 16 B/row
-    #   last pass  : read (key 4 + idx 4)           + write idx 4            = 12 B/row
+    #   first pass : read the raw key 4 (row id = position) + write (key 4 + idx 4)  = 12 B/row
+    #   middle pass: read (key 4 + idx 4)                   + write (key 4 + idx 4)  = 16 B/row
+    #   last pass  : read (key 4 + idx 4)                   + write idx 4            = 12 B/row
     #                (small key domain: group sizes go to the count table, the sorted keys are not written)
     pass_bytes = ([12.0 * n] + [16.0 * n] * max(0, npass_step - 2) + [12.0 * n]) if npass_step >= 2 else [8.0 * n]
     alg_bytes_launch = sum(pass_bytes) / max(1, npass_step)
@@ -294,11 +428,10 @@ def run_b200(args, rank, local_rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32 keys / float64 sums", "data": "synthetic",
-        "config": {"workload": "C2: int32 key (1e6 distinct), float64 value, DT[:, sum(v), by(k)]",
-                   "rows_per_gpu": n, "groups": G, "ngroups_found": ngroups,
+        "config": {"workload": WORKLOAD, "rows_per_gpu": n, "groups": G, "ngroups_found": ngroups,
                    "outputs": "RowIndex int32[n] + Groupby offsets int32[ng+1] + float64 sums[ng]",
                    "l2": "inputs (12 GB/GPU) exceed L2 (126 MB); no flush needed",
-                   "parallelism": f"row-partitioned x{world}, NCCL all-gather of per-group partials" if world > 1 else "single GPU"},
+                   "parallelism": f"row-partitioned x{world}, NCCL all-reduce of the dense per-key partial tables" if world > 1 else "single GPU"},
         "roofline": roofline,
         "roofline_step": {"alg_bytes_per_row": 16, "achieved": step_alg, "peak": peak, "unit": "GB/s", "frac": step_alg / peak},
         "kernel_ms_per_step": kernel_ms,
@@ -318,7 +451,7 @@ def run_b200(args, rank, local_rank, world):
             if world > 1:                                   # merge the per-rank result frames over NCCL
                 gk = torch.from_numpy(R.to_numpy("k")).cuda()
                 gs = torch.from_numpy(R.to_numpy("v")).cuda()
-                gk, gs = ddist.merge_partials(gk, gs, _lib.OP_SUM)
+                gk, gs = ddist.merge_partials_dense(gk, gs, _lib.OP_SUM)
                 gs.cpu()
             return R
         e2e_step()
@@ -341,12 +474,32 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
-        rows = min(n, args.cpu_rows)
-        kc = k[:rows].cpu().numpy(); vc = v[:rows].cpu().numpy()
-        secs, kind, cores = cpu_groupby_sum(kc, vc)
-        line["cpu_baseline"] = {"value": rows / secs, "unit": UNIT, "cores": cores, "kind": kind,
-                                "seconds": secs,
-                                "sample": f"first {rows} rows of the same C2 input (keys uniform in [0,{G}))"}
+        budget = argparse.Namespace(**vars(args)); budget.cpu_budget = min(args.cpu_budget, 30.0)
+        kc_all = k[:min(n, LADDER[2])].cpu().numpy(); vc_all = v[:min(n, LADDER[2])].cpu().numpy()
+        budget.rows = kc_all.shape[0]
+        rows, probes = pick_cpu_rows(budget, 2, lambda r: (kc_all[:r], vc_all[:r]))
+        kc, vc = kc_all[:rows], vc_all[:rows]
+        secs, kind, cores, ng_cpu = cpu_groupby_sum(kc, vc)
+        cb = {"value": rows / secs, "unit": UNIT, "cores": cores, "kind": kind, "seconds": secs,
+              "sample": f"first {rows} rows of the same C2 input (keys uniform in [0,{G})), about 10-30 s of CPU work incl. probes",
+              "probes": probes}
+        if kind == "reference":
+            try:                                            # the reference's experimental sorter, same sample
+                s2, _, _, ng2 = cpu_groupby_sum(kc, vc, sort_new=True)
+                cb["sort_new"] = {"value": rows / s2, "seconds": s2, "result_rows": ng2,
+                                  "note": "dt.options.sort.new=True; counted only if result_rows equals the default path's"}
+                cb["result_rows"] = ng_cpu
+            except Exception as e:                          # pragma: no cover
+                cb["sort_new"] = {"error": str(e)[:100]}
+        line["cpu_baseline"] = cb
+        del kc_all, vc_all
+
+    # ---- the other BASELINE configs (N = 1): C3 sort GB/s vs peak, C4 ---------------------------
+    if rank == 0 and world == 1 and not args.no_extra:
+        del k, v
+        torch.cuda.empty_cache()
+        engine.set_option("trim_scratch", 1)
+        line["other_configs"] = other_configs(torch, engine, _lib, n, peak)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -24,6 +24,7 @@ EXPORTS = [
     "dtb_groupby_order", "dtb_groupby_offsets", "dtb_groupby_destroy", "dtb_groupby_reduce", "dtb_reduce",
     "dtb_gather", "dtb_memcpy", "dtb_set_option", "dtb_get_option", "dtb_last_call_stats",
     "dtb_profile_count", "dtb_profile_get", "dtb_profile_reset",
+    "dtb_dense_scatter", "dtb_dense_compact",
 ]
 
 
@@ -100,6 +101,10 @@ def _load():
     lib.dtb_reduce.argtypes = [c.c_int, dtb_col, c.c_int64, c.c_void_p, c.c_int, c.c_void_p,
                                c.c_int64, c.c_void_p, c.c_void_p]
     lib.dtb_gather.argtypes = [dtb_col, c.c_int64, c.c_void_p, c.c_int, c.c_int64, c.c_void_p, c.c_void_p]
+    lib.dtb_dense_scatter.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_int64, c.c_int64, c.c_int64,
+                                      c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.dtb_dense_compact.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_void_p,
+                                      c.POINTER(c.c_int64), c.c_void_p]
     lib.dtb_memcpy.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p]
     lib.dtb_set_option.argtypes = [c.c_char_p, c.c_int64]
     lib.dtb_get_option.argtypes = [c.c_char_p, c.POINTER(c.c_int64)]

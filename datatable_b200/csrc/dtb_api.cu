@@ -27,6 +27,7 @@ static int64_t opt_radix_bits = 0;     // 0 = default (8-bit digits)
 static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
 static int64_t opt_hybrid = 0;         // 1 = hybrid top-bits + tie-fix sort for wide single keys (sort-only)
+static thread_local int opt_trust_offsets = 0;  // internal: dtb_groupby_reduce passes the handle's own offsets to dtb_reduce
 static int64_t opt_overlap = 0;        // 1 = run fused direct reducers on a side stream under the sort passes
 
 // ---------------------------------------------------------------------------
@@ -126,11 +127,25 @@ struct Arena {
   std::vector<Slab> slabs;
   size_t cur = 0, off = 0;
   int depth = 0;
+  int device = -1;              // the slabs (and last_stream) belong to this device
   cudaStream_t last_stream = nullptr;
   bool have_last = false;
 
   int begin(cudaStream_t s) {
     if (depth++ > 0) return DTB_OK;
+    // A thread may move between devices (dtb_init(d) / cudaSetDevice): scratch carved out of another
+    // device's slab would be an illegal address, so the arena follows the thread's current device and
+    // gives the old device's slabs back first.
+    int dev = 0;
+    DTB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (device != dev) {
+      if (device >= 0 && (!slabs.empty() || have_last)) {
+        DTB_CUDA_CHECK(cudaSetDevice(device));
+        trim();
+        DTB_CUDA_CHECK(cudaSetDevice(dev));
+      }
+      device = dev; have_last = false; last_stream = nullptr;
+    }
     // work enqueued by the previous call may still be using the slab on another stream
     if (have_last && last_stream != s) DTB_CUDA_CHECK(cudaStreamSynchronize(last_stream));
     last_stream = s; have_last = true;
@@ -279,7 +294,17 @@ struct FusedReducers {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  int device = -1;
   int ensure() {
+    int dev = 0;
+    DTB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (stream && device != dev) {               // the thread moved to another device: new stream there
+      cudaSetDevice(device);
+      cudaStreamDestroy(stream); cudaEventDestroy(fork); cudaEventDestroy(join);
+      cudaSetDevice(dev);
+      stream = nullptr;
+    }
+    device = dev;
     if (stream) return DTB_OK;
     int lo = 0, hi = 0;
     DTB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -433,6 +458,12 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     return DTB_OK;
   }
 
+  // by-columns that are all constant (0 bits) while sort columns vary: one group, and no kernel may
+  // shift a key by its full width (composite >> group_shift with group_shift == key width is undefined)
+  int by_bits = 0;
+  for (int c = 0; c < nkeys; c++) if (!(flags[c] & DTB_FLAG_SORT_ONLY)) by_bits += kp.k[c].bits;
+  const bool groups_k = do_groups && by_bits > 0;          // group boundaries come from the kernels
+
   // ---- rounds: a composite wider than 64 bits is sorted in several stable rounds,
   //      least significant key columns first (the reference refines column by column,
   //      sort.cc:561-595; here a round covers as many columns as fit in 64 bits) ----------
@@ -488,14 +519,14 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   bool staged_keys = false;
   for (int c = 0; c < nkeys; c++) staged_keys = staged_keys || (in[c].buf.p != nullptr);
   const int dbits0 = (nrounds == 1) ? rounds[0].kp.total_bits - rounds[0].kp.group_shift : 99;
-  bool fused_direct = fr && fr->n > 0 && do_groups && nrounds == 1 && !staged_keys && dbits0 <= 22 &&
+  bool fused_direct = fr && fr->n > 0 && groups_k && nrounds == 1 && !staged_keys && dbits0 <= 22 &&
                       na_pos != DTB_NA_REMOVE;
   if (fused_direct)
     for (int i = 0; i < fr->n; i++)
       fused_direct = fused_direct && (fr->spec[i].op == DTB_OP_NROWS || is_device_ptr(fr->spec[i].value.data));
   // Small key domain + handle path: the last pass counts rows per group key instead of writing
   // the sorted keys, and the offsets come from a scan over that table.
-  const bool count_table = want_direct && do_groups && nrounds == 1 && !staged_keys && dbits0 <= 22 &&
+  const bool count_table = want_direct && groups_k && nrounds == 1 && !staged_keys && dbits0 <= 22 &&
                            na_pos != DTB_NA_REMOVE;
   int64_t ctable = 0;
   DevBuf gcount;
@@ -573,7 +604,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     if (width > 10) width = 10;
     if (width < 4) width = 4;                                   // 64 bits / 4 = MAX_PASSES
     PassPlan pp; plan_passes(rk.total_bits, width, pp);
-    const bool want_sorted_keys = hybrid || (last_round && do_groups && rounds[ri].has_by && !count_table);
+    const bool want_sorted_keys = hybrid || (last_round && groups_k && rounds[ri].has_by && !count_table);
     // 64-bit keys whose sorted values are not needed afterwards: the passes over the low T-32 bits run
     // on 64-bit keys, the last of them writes only the upper 32 bits, and the remaining passes run on
     // 32-bit keys (8 instead of 12 bytes per row and pass in flight).  Never more passes than before.
@@ -668,7 +699,13 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
 
   DTB_TL("passes enqueued");
   // ---- group offsets -----------------------------------------------------------------
-  if (do_groups) {
+  if (do_groups && !groups_k) {
+    int32_t h[2] = {0, (int32_t)n};
+    DTB_CUDA_CHECK(cudaMemcpyAsync(offsets, h, sizeof(h), cudaMemcpyHostToDevice, s));
+    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+    res.ngroups = 1;
+  }
+  if (groups_k) {
     const int64_t otiles = offsets_num_tiles(n);
     DevBuf oscr; DTB_TRY(oscr.alloc(sizeof(u64) * (size_t)(otiles + 4), s));
     DTB_CUDA_CHECK(cudaMemsetAsync(oscr.p, 0, oscr.bytes, s));
@@ -828,7 +865,15 @@ int dtb_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "profile")) { opt_profile = value; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { opt_overlap = value; return DTB_OK; }
   if (!strcmp(name, "hybrid_sort")) { opt_hybrid = value; return DTB_OK; }
-  if (!strcmp(name, "trim_scratch")) { if (t_arena.depth == 0) t_arena.trim(); return DTB_OK; }
+  if (!strcmp(name, "trim_scratch")) {
+    if (t_arena.depth == 0 && t_arena.device >= 0) {
+      int cur = 0; cudaGetDevice(&cur);
+      if (cur != t_arena.device) cudaSetDevice(t_arena.device);
+      t_arena.trim();
+      if (cur != t_arena.device) cudaSetDevice(cur);
+    }
+    return DTB_OK;
+  }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
 }
@@ -928,11 +973,13 @@ int dtb_groupby_create_reduce(const dtb_col* keys, int nkeys, const int* flags, 
   if (res.ngroups >= 0) {
     // shrink the worst-case offsets buffer to ngroups+1 entries
     DevBuf exact;
+    // on failure the handle already owns the detached group keys and the fused reducer outputs:
+    // dtb_groupby_destroy releases them (res.order is still owned by `res`)
     rc = exact.alloc_owned(sizeof(int32_t) * (size_t)(res.ngroups + 1), s);
-    if (rc != DTB_OK) { delete g; return rc; }
+    if (rc != DTB_OK) { dtb_groupby_destroy(g, stream); return rc; }
     cudaError_t e = cudaMemcpyAsync(exact.p, res.offsets.p, sizeof(int32_t) * (size_t)(res.ngroups + 1),
                                     cudaMemcpyDeviceToDevice, s);
-    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); delete g; return DTB_ECUDA; }
+    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); dtb_groupby_destroy(g, stream); return DTB_ECUDA; }
     g->offsets = exact.detach();
   }
   g->order_base = res.order.detach();
@@ -979,12 +1026,26 @@ int dtb_reduce(int op, dtb_col value, int64_t nrows_value, const void* order, in
   if (ngroups == 0) return DTB_OK;
 
   DevIn d_off; DTB_TRY(d_off.bind(offsets, sizeof(int32_t) * (size_t)(ngroups + 1), s));
+  // caller-supplied offsets must be a Groupby: offsets[0] = 0, strictly increasing (groupby.h:41-47)
   int32_t n32 = 0;
+  int bad = 0;
   if (is_device_ptr(offsets)) {
+    DevBuf d_bad; DTB_TRY(d_bad.alloc(sizeof(int), s));
+    DTB_CUDA_CHECK(cudaMemsetAsync(d_bad.p, 0, sizeof(int), s));
+    if (!opt_trust_offsets) DTB_TRY(launch_offsets_check((const int32_t*)offsets, ngroups, d_bad.as<int>(), s));
     DTB_CUDA_CHECK(cudaMemcpyAsync(&n32, (const int32_t*)offsets + ngroups, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    DTB_CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
   } else {
-    n32 = ((const int32_t*)offsets)[ngroups];
+    const int32_t* ho = (const int32_t*)offsets;
+    n32 = ho[ngroups];
+    if (ho[0] != 0) bad = 1;
+    for (int64_t g = 0; g < ngroups && !bad; g++) if (ho[g] >= ho[g + 1]) bad = (int)(g < INT32_MAX ? g + 1 : INT32_MAX);
+  }
+  if (bad) {
+    set_error("offsets is not a Groupby: offsets[0] must be 0 and offsets strictly increasing (group " +
+              std::to_string(bad - 1) + " is empty or out of order)");
+    return DTB_EINVAL;
   }
   const int64_t n = n32;
   DevIn d_val, d_ord;
@@ -1015,8 +1076,12 @@ int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_valu
   if (g->ngroups < 0) { set_error("the handle holds no Groupby (sort-only call)"); return DTB_EINVAL; }
   ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   const bool device_value = (op == DTB_OP_NROWS) || is_device_ptr(value.data);
-  if (!g->direct || op == DTB_OP_NROWS || !device_value || nrows_value != g->nrows)
-    return dtb_reduce(op, value, nrows_value, g->order, 0, g->offsets, g->ngroups, stream, out);
+  if (!g->direct || op == DTB_OP_NROWS || !device_value || nrows_value != g->nrows) {
+    opt_trust_offsets = 1;                         // the handle's own offsets come from group()
+    const int rc = dtb_reduce(op, value, nrows_value, g->order, 0, g->offsets, g->ngroups, stream, out);
+    opt_trust_offsets = 0;
+    return rc;
+  }
   t_stats = dtb_call_stats{0, 0, 0, 0, 0};
   const int out_st = reduce_out_stype_host(op, value.stype);
   if (!out_st) {
@@ -1067,6 +1132,52 @@ int dtb_gather(dtb_col src, int64_t nrows_src, const void* order, int order_is64
     DTB_TRY(d_out.finish((size_t)n * esz, s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
   }
+  return DTB_OK;
+}
+
+int dtb_dense_scatter(const void* keys, int key_stype, const void* vals, int64_t n, int64_t kmin, int64_t table_size,
+                      void* table, void* present, dtb_stream stream)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  const int kb = (key_stype == DTB_STYPE_INT32) ? 4 : (key_stype == DTB_STYPE_INT64 ? 8 : 0);
+  if (!kb) { set_error("dense merge: group keys must be int32 or int64"); return DTB_ENOTIMPL; }
+  if (n < 0 || table_size < 1 || (n > 0 && (!keys || !vals)) || !table || !present) { set_error("bad dtb_dense_scatter arguments"); return DTB_EINVAL; }
+  if (!is_device_ptr(table) || !is_device_ptr(present) || (n > 0 && (!is_device_ptr(keys) || !is_device_ptr(vals)))) {
+    set_error("dense merge works on device buffers (they are NCCL all-reduced in place)"); return DTB_EINVAL;
+  }
+  DTB_TRY(ensure_context());
+  return launch_dense_scatter(keys, kb, vals, n, kmin, table_size, table, (uint32_t*)present, s);
+}
+
+int dtb_dense_compact(const void* table, const void* present, int64_t table_size, int64_t kmin, int key_stype,
+                      void* out_keys, void* out_vals, int64_t* ngroups_out, dtb_stream stream)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  const int kb = (key_stype == DTB_STYPE_INT32) ? 4 : (key_stype == DTB_STYPE_INT64 ? 8 : 0);
+  if (!kb) { set_error("dense merge: group keys must be int32 or int64"); return DTB_ENOTIMPL; }
+  if (!table || !present || !out_keys || !out_vals || !ngroups_out) { set_error("NULL argument"); return DTB_EINVAL; }
+  if (table_size < 1024 || table_size % 1024 || table_size > ((int64_t)1 << 22)) {
+    set_error("dense merge: table size must be a multiple of 1024 and at most 2^22"); return DTB_EINVAL;
+  }
+  if (!is_device_ptr(table) || !is_device_ptr(present) || !is_device_ptr(out_keys) || !is_device_ptr(out_vals)) {
+    set_error("dense merge works on device buffers"); return DTB_EINVAL;
+  }
+  DTB_TRY(ensure_context());
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  DevBuf offs, gidx, scr;
+  DTB_TRY(offs.alloc(sizeof(int32_t) * (size_t)(table_size + 1), s));
+  DTB_TRY(gidx.alloc(sizeof(u32) * (size_t)(table_size + 1), s));
+  DTB_TRY(scr.alloc(sizeof(u64) * (size_t)(2 * table_size / 1024 + 4), s));
+  u64* d_ng = scr.as<u64>() + 2 * table_size / 1024 + 2;
+  DTB_CUDA_CHECK(cudaMemsetAsync(d_ng, 0, 2 * sizeof(u64), s));
+  DTB_TRY(launch_offsets_from_counts((const u32*)present, table_size, 0, offs.as<int32_t>(), gidx.as<u32>(), d_ng, scr.as<u64>(), s));
+  u64 h_ng = 0;
+  DTB_CUDA_CHECK(cudaMemcpyAsync(&h_ng, d_ng, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  *ngroups_out = (int64_t)h_ng;
+  DTB_TRY(launch_dense_emit(gidx.as<u32>(), table, (int64_t)h_ng, kmin, kb, out_keys, out_vals, s));
   return DTB_OK;
 }
 

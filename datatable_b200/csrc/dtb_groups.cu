@@ -295,4 +295,58 @@ int launch_group_offsets(const void* sorted_keys, int key_bytes, int group_shift
   return DTB_OK;
 }
 
+// ===========================================================================
+// Dense per-key tables for the multi-GPU merge of per-group partials ("a final NCCL
+// reduce of per-group partials").  Every rank scatters its (group key, partial) list into a table
+// indexed by key - kmin; the tables are all-reduced in place over NVLink (NCCL, by the caller) and
+// compacted back into (key, value) lists with the count-table kernels above.  No re-sort, no host
+// round trip between the kernels.
+// ===========================================================================
+template <typename KT>
+__global__ void dense_scatter_kernel(const KT* __restrict__ keys, const u64* __restrict__ vals, int64_t n,
+                                     int64_t kmin, int64_t size, u64* __restrict__ table, u32* __restrict__ present)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t x = (int64_t)keys[i] - kmin;
+    if (x >= 0 && x < size) { table[x] = vals[i]; present[x] = 1u; }
+  }
+}
+
+template <typename KT>
+__global__ void dense_emit_kernel(const u32* __restrict__ gidx, const u64* __restrict__ table, int64_t ng, int64_t kmin,
+                                  KT* __restrict__ out_keys, u64* __restrict__ out_vals)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride) {
+    const u32 x = gidx[g];
+    out_keys[g] = (KT)(kmin + (int64_t)x);
+    out_vals[g] = table[x];
+  }
+}
+
+int launch_dense_scatter(const void* keys, int key_bytes, const void* vals, int64_t n, int64_t kmin, int64_t size,
+                         void* table, uint32_t* present, cudaStream_t s)
+{
+  if (n == 0) return DTB_OK;
+  const int grid = (int)((n + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (n + 255) / 256);
+  if (key_bytes == 4) dense_scatter_kernel<int32_t><<<grid, 256, 0, s>>>((const int32_t*)keys, (const u64*)vals, n, kmin, size, (u64*)table, present);
+  else                dense_scatter_kernel<int64_t><<<grid, 256, 0, s>>>((const int64_t*)keys, (const u64*)vals, n, kmin, size, (u64*)table, present);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+int launch_dense_emit(const uint32_t* gidx, const void* table, int64_t ng, int64_t kmin, int key_bytes,
+                      void* out_keys, void* out_vals, cudaStream_t s)
+{
+  if (ng == 0) return DTB_OK;
+  const int grid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+  if (key_bytes == 4) dense_emit_kernel<int32_t><<<grid, 256, 0, s>>>(gidx, (const u64*)table, ng, kmin, (int32_t*)out_keys, (u64*)out_vals);
+  else                dense_emit_kernel<int64_t><<<grid, 256, 0, s>>>(gidx, (const u64*)table, ng, kmin, (int64_t*)out_keys, (u64*)out_vals);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
 }  // namespace dtb

@@ -119,6 +119,12 @@ int launch_offsets_from_counts(const uint32_t* count, int64_t table, int64_t n, 
                                uint32_t* gkeys, unsigned long long* d_ngroups, unsigned long long* scratch,
                                cudaStream_t s);
 
+// Dense per-key tables for the multi-GPU merge of per-group partials (dtb_dense_scatter / dtb_dense_compact).
+int launch_dense_scatter(const void* keys, int key_bytes, const void* vals, int64_t n, int64_t kmin, int64_t size,
+                         void* table, uint32_t* present, cudaStream_t s);
+int launch_dense_emit(const uint32_t* gidx, const void* table, int64_t ng, int64_t kmin, int key_bytes,
+                      void* out_keys, void* out_vals, cudaStream_t s);
+
 // ---------------------------------------------------------------------------
 // Group offsets (replaces GroupGatherer, sort_groups.cc:34-117): heads where
 // (key >> group_shift) changes, compacted into offsets[] by a single-pass scan.
@@ -143,6 +149,8 @@ int launch_reduce_impl(int op, const void* value, int stype, int64_t nrows_value
                        int64_t n, unsigned long long* acc0, unsigned long long* acc1,
                        void* out, cudaStream_t s);
 int reduce_out_stype_host(int op, int stype);
+// *d_bad (device int, zeroed by the caller) = 1 + index of a group with offsets[g] >= offsets[g+1] (or offsets[0] != 0).
+int launch_offsets_check(const int32_t* offsets, int64_t ng, int* d_bad, cudaStream_t s);
 
 // Direct-address reducers over a small normalised key domain (see dtb_reduce.cu).
 enum { DIRECT_PLAIN = 0,        // one L2 atomic per row into acc[x]

@@ -256,7 +256,7 @@ static int reduce_out_stype(int op, int st) {
     case DTB_OP_SUM:  return isint ? DTB_STYPE_INT64 : (isflt ? st : 0);           // fexpr_sumprod.cc:50-66
     case DTB_OP_MEAN: return isint ? DTB_STYPE_FLOAT64 : (isflt ? st : 0);         // fexpr_mean.cc:49-78
     case DTB_OP_MIN: case DTB_OP_MAX:
-      return st == DTB_STYPE_BOOL ? DTB_STYPE_INT8 : ((isint || isflt) ? st : 0);  // fexpr_minmax.cc:50-72
+      return (isint || isflt) ? st : 0;      // fexpr_minmax.cc:50-72: the column's own stype (bool8 stays bool8)
   }
   return 0;
 }
@@ -349,6 +349,25 @@ int launch_reduce_impl(int op, const void* value, int stype, int64_t nv, const v
 }
 
 int reduce_out_stype_host(int op, int st) { return reduce_out_stype(op, st); }
+
+// Groupby invariants (groupby.h:41-47): offsets[0] = 0 and strictly increasing.  reduce_kernel marks
+// group starts in a one-bit-per-row bitmap, so an empty group would silently shift every later group of
+// the tile: caller-supplied offsets are checked first.  *bad receives the index of a violating group + 1.
+__global__ void offsets_check_kernel(const int32_t* __restrict__ offsets, int64_t ng, int* bad) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride) {
+    if (offsets[g] >= offsets[g + 1] || (g == 0 && offsets[0] != 0)) atomicMax(bad, (int)(g < INT32_MAX ? g + 1 : INT32_MAX));
+  }
+}
+
+int launch_offsets_check(const int32_t* offsets, int64_t ng, int* d_bad, cudaStream_t s) {
+  if (ng == 0) return DTB_OK;
+  const int fgrid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+  offsets_check_kernel<<<fgrid, 256, 0, s>>>(offsets, ng, d_bad);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
 
 int launch_nrows(const int32_t* offsets, int64_t ng, void* out, cudaStream_t s) {
   if (ng == 0) return DTB_OK;

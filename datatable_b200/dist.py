@@ -8,8 +8,12 @@ one NCCL all-gather, and the same group()/reduce() kernels merge them.  Sums,
 counts, minima and maxima are associative, so the merged result equals the
 single-GPU result on the concatenated rows (float sums up to association).
 
-Two exchanges are built on the same kernels:
+Exchanges built on the same kernels:
 
+* `merge_partials_dense`     the partials are scattered into a dense table indexed by key - kmin, the
+                             tables are all-reduced IN PLACE by NCCL (one ncclAllReduce of <= 32 MB over
+                             NVLink) and compacted back: no re-sort, no re-group.  For SUM-like partials
+                             over a key range of at most 2^22 (C2); anything else falls back to:
 * `merge_partials`           all-gather of (key, partial) lists; every rank ends with the full result.
                              Moves 12-16 bytes per *group*; right when ngroups is small (C2).
 * `merge_partials_alltoall`  key-range all-to-all of the partial lists: rank r ends with the r-th key
@@ -19,6 +23,8 @@ Two exchanges are built on the same kernels:
                              Rank r ends with the r-th key range of the global RowIndex (int64 row ids,
                              the ARR64 case the reference cannot represent, SURVEY.md mismatch 3).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -37,9 +43,30 @@ def local_groupby(k, v, op):
     return gkeys, part
 
 
+def _dense_scatter(gkeys, part, kmin, table, present):
+    st = _lib.INT64 if gkeys.dtype == torch.int64 else _lib.INT32
+    _lib.check(_lib.lib.dtb_dense_scatter(ctypes.c_void_p(gkeys.data_ptr()), st, ctypes.c_void_p(part.data_ptr()),
+                                          gkeys.numel(), int(kmin), table.numel(), ctypes.c_void_p(table.data_ptr()),
+                                          ctypes.c_void_p(present.data_ptr()), engine._stream()))
+
+
+def _dense_compact(table, present, kmin, key_dtype):
+    st = _lib.INT64 if key_dtype == torch.int64 else _lib.INT32
+    size = table.numel()
+    out_k = torch.empty(size, dtype=key_dtype, device=table.device)
+    out_v = torch.empty(size, dtype=table.dtype, device=table.device)
+    ng = ctypes.c_int64(0)
+    _lib.check(_lib.lib.dtb_dense_compact(ctypes.c_void_p(table.data_ptr()), ctypes.c_void_p(present.data_ptr()), size,
+                                          int(kmin), st, ctypes.c_void_p(out_k.data_ptr()),
+                                          ctypes.c_void_p(out_v.data_ptr()), ctypes.byref(ng), engine._stream()))
+    return out_k[:ng.value], out_v[:ng.value]
+
+
 class _EngineKernels:
     """The product path: libdtb200.so kernels.  (tests/ swap in an oracle-backed object to run the
     exchange logic under gloo on CPU.)"""
+    dense_scatter = staticmethod(_dense_scatter)
+    dense_compact = staticmethod(_dense_compact)
     group = staticmethod(lambda keys: engine.group([keys], [0], _lib.NA_FIRST))
     sort = staticmethod(lambda keys: engine.group([keys], [_lib.FLAG_SORT_ONLY], _lib.NA_FIRST)[0])
     reduce = staticmethod(lambda op, v, order, offsets: engine.reduce(op, v, order, offsets))
@@ -71,13 +98,56 @@ def merge_partials(gkeys, part, op, group=None, kernels=_EngineKernels):
     return kernels.take(kall, first), merged
 
 
+DENSE_MAX = 1 << 22            # entries of the dense per-key table (32 MB of float64 partials)
+LAST_MERGE_LAUNCHES = 0        # engine kernels launched by the last merge on this rank (bench.py's count)
+_SUM_LIKE = (_lib.OP_SUM, _lib.OP_COUNT, _lib.OP_COUNTNA, _lib.OP_NROWS)
+
+
+def merge_partials_dense(gkeys, part, op, group=None, kernels=_EngineKernels):
+    """Merge every rank's (ascending group keys, SUM-like partials) through dense per-key tables that
+    NCCL all-reduces in place; every rank ends with the full (keys, merged partials) lists.
+
+    One small all-reduce learns the global key range (its two scalars are the only host round trip),
+    one all-reduce sums the tables.  Falls back to `merge_partials` for MIN/MAX partials (NA partials
+    do not all-reduce) and for key ranges beyond DENSE_MAX."""
+    global LAST_MERGE_LAUNCHES
+    world = dist.get_world_size(group)
+    if world == 1:
+        LAST_MERGE_LAUNCHES = 0
+        return gkeys, part
+    dev = gkeys.device
+    big = torch.iinfo(torch.int64).max
+    if gkeys.numel():
+        rng = torch.stack([-gkeys[0].to(torch.int64), gkeys[-1].to(torch.int64)])
+    else:
+        rng = torch.tensor([-big, -big], dtype=torch.int64, device=dev)
+    dist.all_reduce(rng, op=dist.ReduceOp.MAX, group=group)
+    neg_lo, hi = rng.tolist()
+    kmin = -neg_lo
+    span = hi - kmin + 1
+    if op not in _SUM_LIKE or part.element_size() != 8 or span > DENSE_MAX or span <= 0:
+        LAST_MERGE_LAUNCHES = 8
+        return merge_partials(gkeys, part, op, group, kernels) if span > 0 else (gkeys, part)
+    size = (span + 1023) // 1024 * 1024
+    table = torch.zeros(size, dtype=part.dtype, device=dev)
+    present = torch.zeros(size, dtype=torch.int32, device=dev)
+    kernels.dense_scatter(gkeys, part, kmin, table, present)
+    dist.all_reduce(table, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(present, op=dist.ReduceOp.SUM, group=group)
+    LAST_MERGE_LAUNCHES = 5          # scatter + block sums + scan + compact + emit
+    return kernels.dense_compact(table, present, kmin, gkeys.dtype)
+
+
 def groupby_partitioned(k, v, op=_lib.OP_SUM, group=None, exchange="allgather"):
     """DT[:, op(f.v), by(f.k)] over a frame row-partitioned across the ranks of `group`.
-    exchange="allgather": every rank gets all groups; "alltoall": rank r gets the r-th key range."""
+    exchange="allreduce": dense per-key tables all-reduced in place (every rank gets all groups);
+    "allgather": every rank gets all groups; "alltoall": rank r gets the r-th key range."""
     gkeys, part = local_groupby(k, v, op)
     if dist.is_available() and dist.is_initialized():
         if exchange == "alltoall":
             return merge_partials_alltoall(gkeys, part, op, group)
+        if exchange == "allreduce":
+            return merge_partials_dense(gkeys, part, op, group)
         return merge_partials(gkeys, part, op, group)
     return gkeys, part
 

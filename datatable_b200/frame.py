@@ -340,7 +340,7 @@ def _evaluate(DT, j, by_, sort_):
             ired = 0
             for name, e in zip(names, exprs):
                 if isinstance(e, Reducer):
-                    add(name, gb.reduced(ired), None)
+                    add(name, gb.reduced(ired), _red_stype(dcol, e))
                     ired += 1
                 else:
                     raise NotImplementedError("mixing reducers and plain columns under by() is outside the hot path")
@@ -370,9 +370,7 @@ def _evaluate(DT, j, by_, sort_):
         for name, e in zip(names, exprs):
             if not isinstance(e, Reducer):
                 raise NotImplementedError("mixing reducers and plain columns is outside the hot path")
-            add(name, _reduce(dcol, e, order, offs), None)
-        for n_ in out._cols:
-            out._stypes[n_] = engine.Col(out._cols[n_]).stype
+            add(name, _reduce(dcol, e, order, offs), _red_stype(dcol, e))
         out._nrows = 1
         return out
 
@@ -420,6 +418,13 @@ def _as_expr(v):
 def _index_through(order, pos):
     """order[pos] -- composition of RowIndexes (rowindex.cc:246-250) done as a gather."""
     return engine.gather(engine.Col(order, INT32), pos)
+
+
+def _red_stype(dcol, e):
+    """Output stype of a reducer column (bool8 min/max stay bool8, fexpr_minmax.cc:50-72)."""
+    if e.op == _lib.OP_NROWS or e.arg is None:
+        return INT64
+    return engine.reduce_out_stype(e.op, dcol(e.arg.name).stype)
 
 
 def _reduce(dcol, e, order, offsets):

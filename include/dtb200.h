@@ -206,6 +206,20 @@ DTB_API int dtb_gather(dtb_col src, int64_t nrows_src,
                const void* order, int order_is64, int64_t n,
                dtb_stream stream, void* out);
 
+/*
+ * Multi-GPU merge of per-group partials over a small group-key domain (one process per GPU; the
+ * reference is single-process, SURVEY.md 8e -- this is north_star's "final NCCL reduce of per-group
+ * partials").  Each rank scatters its (group key, 8-byte partial) list into a dense table indexed by
+ * key - kmin; the caller all-reduces `table` (SUM, typed as the partials are) and `present` (uint32
+ * SUM) in place with NCCL; dtb_dense_compact then lists the keys that occur on any rank, ascending,
+ * with their merged partials.  Device buffers only.  table/present must be zeroed before the scatter;
+ * table_size: multiple of 1024, at most 2^22.  key_stype: DTB_STYPE_INT32 or DTB_STYPE_INT64.
+ */
+DTB_API int dtb_dense_scatter(const void* keys, int key_stype, const void* vals, int64_t n, int64_t kmin,
+                      int64_t table_size, void* table, void* present, dtb_stream stream);
+DTB_API int dtb_dense_compact(const void* table, const void* present, int64_t table_size, int64_t kmin,
+                      int key_stype, void* out_keys, void* out_vals, int64_t* ngroups_out, dtb_stream stream);
+
 /* Copies nbytes between any two host/device buffers on `stream`
  * (cudaMemcpyDefault) and waits for completion.  Lets a binding read the
  * HBM-resident results of a dtb_groupby without linking the CUDA runtime. */

@@ -39,7 +39,7 @@ def test_pure_host_queries():
     assert L.dtb_reduce_out_stype(_lib.OP_SUM, _lib.FLOAT32) == _lib.FLOAT32
     assert L.dtb_reduce_out_stype(_lib.OP_MEAN, _lib.INT32) == _lib.FLOAT64
     assert L.dtb_reduce_out_stype(_lib.OP_MEAN, _lib.FLOAT32) == _lib.FLOAT32
-    assert L.dtb_reduce_out_stype(_lib.OP_MIN, _lib.BOOL) == _lib.INT8
+    assert L.dtb_reduce_out_stype(_lib.OP_MIN, _lib.BOOL) == _lib.BOOL      # bool8 in, bool8 out (reference: stype.bool8)
     assert L.dtb_reduce_out_stype(_lib.OP_MAX, _lib.INT16) == _lib.INT16
     assert L.dtb_reduce_out_stype(_lib.OP_COUNT, _lib.FLOAT64) == _lib.INT64
     assert L.dtb_reduce_out_stype(_lib.OP_SUM, 11) == 0

@@ -32,6 +32,18 @@ class OracleKernels:
     def take(src, idx):
         return src[idx.long()]
 
+    # numpy stand-ins of dtb_dense_scatter / dtb_dense_compact (include/dtb200.h)
+    @staticmethod
+    def dense_scatter(gkeys, part, kmin, table, present):
+        x = gkeys.long() - kmin
+        table[x] = part
+        present[x] = 1
+
+    @staticmethod
+    def dense_compact(table, present, kmin, key_dtype):
+        x = torch.nonzero(present).flatten()
+        return (x + kmin).to(key_dtype), table[x]
+
 
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -49,13 +61,20 @@ def _worker(rank, world, port, q):
         gkeys = k[o[f[:-1]]]
         mk, mv = ddist.merge_partials(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
                                       kernels=OracleKernels)
+        dk, dv = ddist.merge_partials_dense(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
+                                            kernels=OracleKernels)
+        # MIN partials do not all-reduce: the dense entry point must fall back to the all-gather merge
+        pmin = orc.reduce(orc.MIN, v, o, f)
+        nk, nv = ddist.merge_partials_dense(torch.from_numpy(gkeys), torch.from_numpy(pmin), _lib.OP_MIN,
+                                            kernels=OracleKernels)
         ak, av = ddist.merge_partials_alltoall(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
                                                kernels=OracleKernels)
         k64 = rng.integers(-10**12, 10**12, n).astype(np.int64)
         k64[::9] = k64[0]                             # ties across ranks: stability must hold globally
         row0 = 0 if rank == 0 else 5000
         sk, sid = ddist.sort_partitioned(torch.from_numpy(k64), row0, kernels=OracleKernels)
-        q.put((rank, k, v, mk.numpy(), mv.numpy(), ak.numpy(), av.numpy(), k64, sk.numpy(), sid.numpy()))
+        q.put((rank, k, v, mk.numpy(), mv.numpy(), ak.numpy(), av.numpy(), k64, sk.numpy(), sid.numpy(),
+               dk.numpy(), dv.numpy(), nk.numpy(), nv.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -78,6 +97,11 @@ def test_merge_partials_world2():
     for r in res:                                   # every rank holds the full merged result
         assert np.array_equal(r[3], uk)
         assert np.allclose(r[4], want, rtol=1e-12)
+    wmin = np.array([vall[kall == x].min() for x in uk])
+    for r in res:                                   # dense all-reduce merge == all-gather merge; MIN falls back
+        assert np.array_equal(r[10], uk) and r[10].dtype == np.int32
+        assert np.allclose(r[11], want, rtol=1e-12)
+        assert np.array_equal(r[12], uk) and np.array_equal(r[13], wmin)
     # all-to-all variant: the ranks hold disjoint ascending key ranges that concatenate to the result
     ak = np.concatenate([r[5] for r in res]); av = np.concatenate([r[6] for r in res])
     assert np.array_equal(ak, uk) and np.allclose(av, want, rtol=1e-12)
