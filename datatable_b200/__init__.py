@@ -8,6 +8,7 @@ library has not been built.  There is no CPU fallback.
 from . import _lib
 from ._lib import (DtbError, DtbValueError, DtbNotImplError, DtbCudaError, DtbMemoryError)
 from . import engine
-from .frame import Frame, f, by, sort, sum, mean, min, max, count, countna, unique, nunique   # noqa: A004
+from .frame import (Frame, f, by, sort, join, sum, mean, min, max, count, countna, first, last, sd, median,   # noqa: A004
+                    unique, nunique, union, intersect, setdiff, symdiff)
 
-__all__ = ["engine", "Frame", "f", "by", "sort", "sum", "mean", "min", "max", "count", "countna", "unique", "nunique", "DtbError", "DtbValueError", "DtbNotImplError", "DtbCudaError", "DtbMemoryError"]
+__all__ = ["engine", "Frame", "f", "by", "sort", "sum", "mean", "min", "max", "count", "countna", "first", "last", "sd", "median", "join", "unique", "nunique", "union", "intersect", "setdiff", "symdiff", "DtbError", "DtbValueError", "DtbNotImplError", "DtbCudaError", "DtbMemoryError"]

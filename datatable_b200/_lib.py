@@ -16,6 +16,8 @@ BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64, DATE32, TIME64 = 1, 2, 3, 4, 
 FLAG_NONE, FLAG_DESCENDING, FLAG_SORT_ONLY = 0, 2, 4
 NA_FIRST, NA_LAST, NA_REMOVE = 1, 2, 3
 OP_SUM, OP_MEAN, OP_MIN, OP_MAX, OP_COUNT, OP_COUNTNA, OP_NROWS = 1, 2, 3, 4, 5, 6, 7
+OP_FIRST, OP_LAST, OP_SD, OP_MEDIAN, OP_NUNIQUE = 8, 9, 10, 11, 12
+SET_UNION, SET_INTERSECT, SET_SETDIFF, SET_SYMDIFF = 0, 1, 2, 3
 OK, EINVAL, ENOTIMPL, ECUDA, ENOMEM, ENOSPACE = 0, -1, -2, -3, -4, -5
 
 EXPORTS = [
@@ -25,6 +27,7 @@ EXPORTS = [
     "dtb_gather", "dtb_memcpy", "dtb_set_option", "dtb_get_option", "dtb_last_call_stats",
     "dtb_profile_count", "dtb_profile_get", "dtb_profile_reset",
     "dtb_dense_scatter", "dtb_dense_compact",
+    "dtb_sort_grouped", "dtb_set_select", "dtb_largest_group", "dtb_join",
 ]
 
 
@@ -105,6 +108,13 @@ def _load():
                                       c.c_void_p, c.c_void_p, c.c_void_p]
     lib.dtb_dense_compact.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int, c.c_void_p, c.c_void_p,
                                       c.POINTER(c.c_int64), c.c_void_p]
+    lib.dtb_sort_grouped.argtypes = [dtb_col, c.c_int64, c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p, c.c_void_p]
+    lib.dtb_set_select.argtypes = [c.c_int, c.c_void_p, c.c_void_p, c.c_int64, c.POINTER(c.c_int64), c.c_int,
+                                   c.c_void_p, c.c_void_p, c.POINTER(c.c_int64)]
+    lib.dtb_largest_group.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_void_p, c.POINTER(c.c_int64),
+                                      c.POINTER(c.c_int64)]
+    lib.dtb_join.argtypes = [c.POINTER(dtb_col), c.POINTER(dtb_col), c.c_int, c.c_int64, c.c_int64, c.c_void_p,
+                             c.c_void_p]
     lib.dtb_memcpy.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_void_p]
     lib.dtb_set_option.argtypes = [c.c_char_p, c.c_int64]
     lib.dtb_get_option.argtypes = [c.c_char_p, c.POINTER(c.c_int64)]

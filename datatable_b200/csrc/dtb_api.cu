@@ -523,7 +523,8 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
                       na_pos != DTB_NA_REMOVE;
   if (fused_direct)
     for (int i = 0; i < fr->n; i++)
-      fused_direct = fused_direct && (fr->spec[i].op == DTB_OP_NROWS || is_device_ptr(fr->spec[i].value.data));
+      fused_direct = fused_direct && fr->spec[i].op <= DTB_OP_NROWS &&           // streaming modes exist for sum..nrows only
+                     (fr->spec[i].op == DTB_OP_NROWS || is_device_ptr(fr->spec[i].value.data));
   // Small key domain + handle path: the last pass counts rows per group key instead of writing
   // the sorted keys, and the offsets come from a scan over that table.
   const bool count_table = want_direct && groups_k && nrounds == 1 && !staged_keys && dbits0 <= 22 &&
@@ -796,9 +797,13 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
                                        (dp.kind == DIRECT_SMALL && dp.map) ? nullptr : res.gkeys.as<u32>(), ng, ob.p, s));
       } else {
         DevIn dv; DTB_TRY(dv.bind(sp.value.data, (size_t)n * stype_bytes(sp.value.stype), s));
+        DevBuf extra;
+        const size_t xb = reduce_extra_bytes(sp.op, ng, n);
+        if (xb) DTB_TRY(extra.alloc(xb, s));
         ProfScope ps("reduce", s);
         DTB_TRY(launch_reduce_impl(sp.op, dv.dptr, sp.value.stype, n, order + res.nskip, 0, offsets, ng,
-                                   ng > 0 ? (int64_t)(n - res.nskip) : 0, gacc.as<u64>(), gacc.as<u64>() + ng, ob.p, s));
+                                   ng > 0 ? (int64_t)(n - res.nskip) : 0, gacc.as<u64>(), gacc.as<u64>() + ng, ob.p, s,
+                                   xb ? extra.p : nullptr));
       }
       fr->out[i] = ob.detach();
     }
@@ -959,6 +964,10 @@ int dtb_groupby_create_reduce(const dtb_col* keys, int nkeys, const int* flags, 
   if (nreducers > 0 && flags && nkeys > 0 && (flags[0] & DTB_FLAG_SORT_ONLY)) {
     set_error("reducers need a Groupby: the first key column must not be SORT_ONLY"); return DTB_EINVAL;
   }
+  for (int i = 0; i < nreducers; i++)
+    if (reducers[i].op == DTB_OP_MEDIAN || reducers[i].op == DTB_OP_NUNIQUE) {
+      set_error("median/nunique read rows sorted inside their group: use dtb_sort_grouped + dtb_reduce"); return DTB_EINVAL;
+    }
   ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   GroupResult res;
   FusedReducers fr; fr.spec = reducers; fr.n = nreducers;
@@ -1055,11 +1064,14 @@ int dtb_reduce(int op, dtb_col value, int64_t nrows_value, const void* order, in
   }
   DevOut d_out; DTB_TRY(d_out.bind(out, (size_t)ngroups * stype_bytes(out_st), s));
   DevBuf acc; DTB_TRY(acc.alloc(sizeof(u64) * (size_t)ngroups * 2, s));
+  DevBuf extra;
+  const size_t xb = reduce_extra_bytes(op, ngroups, n);
+  if (xb) DTB_TRY(extra.alloc(xb, s));
   {
     ProfScope ps("reduce", s);
     DTB_TRY(launch_reduce_impl(op, d_val.dptr, value.stype, nrows_value, d_ord.dptr, order_is64,
                                (const int32_t*)d_off.dptr, ngroups, n, acc.as<u64>(),
-                               acc.as<u64>() + ngroups, d_out.dptr, s));
+                               acc.as<u64>() + ngroups, d_out.dptr, s, xb ? extra.p : nullptr));
   }
   if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   if (d_out.staged()) {
@@ -1076,7 +1088,7 @@ int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_valu
   if (g->ngroups < 0) { set_error("the handle holds no Groupby (sort-only call)"); return DTB_EINVAL; }
   ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
   const bool device_value = (op == DTB_OP_NROWS) || is_device_ptr(value.data);
-  if (!g->direct || op == DTB_OP_NROWS || !device_value || nrows_value != g->nrows) {
+  if (!g->direct || op == DTB_OP_NROWS || op >= DTB_OP_FIRST || !device_value || nrows_value != g->nrows) {
     opt_trust_offsets = 1;                         // the handle's own offsets come from group()
     const int rc = dtb_reduce(op, value, nrows_value, g->order, 0, g->offsets, g->ngroups, stream, out);
     opt_trust_offsets = 0;
@@ -1178,6 +1190,146 @@ int dtb_dense_compact(const void* table, const void* present, int64_t table_size
   DTB_CUDA_CHECK(cudaStreamSynchronize(s));
   *ngroups_out = (int64_t)h_ng;
   DTB_TRY(launch_dense_emit(gidx.as<u32>(), table, (int64_t)h_ng, kmin, kb, out_keys, out_vals, s));
+  return DTB_OK;
+}
+
+int dtb_sort_grouped(dtb_col value, int64_t nrows_value, const void* order, const void* offsets, int64_t ngroups,
+                     dtb_stream stream, void* order_out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  const int esz = stype_bytes(value.stype);
+  if (!esz) { set_error("Unable to sort Column of stype " + std::to_string(value.stype)); return DTB_ENOTIMPL; }
+  if (ngroups < 0 || !offsets) { set_error("bad dtb_sort_grouped arguments"); return DTB_EINVAL; }
+  DTB_TRY(ensure_context());
+  if (ngroups == 0) return DTB_OK;
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  DevIn d_off; DTB_TRY(d_off.bind(offsets, sizeof(int32_t) * (size_t)(ngroups + 1), s));
+  int32_t n32 = 0;
+  DTB_CUDA_CHECK(cudaMemcpyAsync(&n32, (const int32_t*)d_off.dptr + ngroups, sizeof(int32_t), cudaMemcpyDefault, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int64_t n = n32;
+  if (n == 0) return DTB_OK;
+  if (!order_out) { set_error("order_out is NULL"); return DTB_EINVAL; }
+  DevIn d_val, d_ord;
+  DTB_TRY(d_val.bind(value.data, (size_t)nrows_value * esz, s));
+  DTB_TRY(d_ord.bind(order, (size_t)n * 4, s));
+  DevOut d_out; DTB_TRY(d_out.bind(order_out, (size_t)n * 4, s));
+  // sort by (group id, value): the group id of every sorted position and the value seen through the RowIndex
+  DevBuf gid, vg, iota;
+  DTB_TRY(gid.alloc((size_t)n * 4, s));
+  DTB_TRY(vg.alloc((size_t)n * esz, s));
+  DTB_TRY(launch_expand_gid((const int32_t*)d_off.dptr, ngroups, n, gid.as<int32_t>(), s));
+  const void* ord = d_ord.dptr;
+  if (!ord) { DTB_TRY(iota.alloc((size_t)n * 4, s)); DTB_TRY(launch_iota32(iota.as<int32_t>(), n, s)); ord = iota.p; }
+  DTB_TRY(launch_gather(d_val.dptr, value.stype, nrows_value, ord, 0, n, vg.p, s));
+  dtb_col keys[2] = {{gid.p, DTB_STYPE_INT32, 0}, {vg.p, value.stype, 0}};
+  const int flags[2] = {DTB_FLAG_SORT_ONLY, DTB_FLAG_SORT_ONLY};
+  GroupResult res;
+  DTB_TRY(group_core(keys, 2, flags, DTB_NA_FIRST, n, s, nullptr, nullptr, res));
+  // positions -> rows
+  DTB_TRY(launch_gather(ord, DTB_STYPE_INT32, n, res.order.p, 0, n, d_out.dptr, s));
+  if (d_out.staged()) DTB_TRY(d_out.finish((size_t)n * 4, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return DTB_OK;
+}
+
+int dtb_set_select(int mode, const void* order, const void* offsets, int64_t ngroups, const int64_t* cum_sizes,
+                   int ninputs, dtb_stream stream, void* rows_out, int64_t* nout)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  if (mode < DTB_SET_UNION || mode > DTB_SET_SYMDIFF) { set_error("unknown set operation"); return DTB_EINVAL; }
+  if (ngroups < 0 || !nout || ninputs < 1 || ninputs > 64 || !cum_sizes) { set_error("bad dtb_set_select arguments"); return DTB_EINVAL; }
+  *nout = 0;
+  DTB_TRY(ensure_context());
+  if (ngroups == 0) return DTB_OK;
+  if (!order || !offsets || !rows_out) { set_error("NULL argument"); return DTB_EINVAL; }
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  const int64_t n = cum_sizes[ninputs - 1];
+  DevIn d_ord, d_off;
+  DTB_TRY(d_ord.bind(order, (size_t)n * 4, s));
+  DTB_TRY(d_off.bind(offsets, sizeof(int32_t) * (size_t)(ngroups + 1), s));
+  DevOut d_out; DTB_TRY(d_out.bind(rows_out, (size_t)ngroups * 4, s));
+  DevBuf d_sizes, flags, pos, oscr;
+  DTB_TRY(d_sizes.alloc(sizeof(int64_t) * (size_t)ninputs, s));
+  DTB_CUDA_CHECK(cudaMemcpyAsync(d_sizes.p, cum_sizes, sizeof(int64_t) * (size_t)ninputs, cudaMemcpyHostToDevice, s));
+  const int64_t m = ngroups + 1;                          // flags[0] = sentinel head for the compaction
+  DTB_TRY(flags.alloc((size_t)m + 64, s));
+  DTB_CUDA_CHECK(cudaMemsetAsync(flags.p, 0, (size_t)m + 64, s));
+  DTB_TRY(launch_set_select((const int32_t*)d_ord.dptr, (const int32_t*)d_off.dptr, ngroups, d_sizes.as<int64_t>(),
+                            ninputs, mode, flags.as<uint8_t>(), s));
+  const int64_t otiles = offsets_num_tiles(m);
+  DTB_TRY(pos.alloc(sizeof(int32_t) * (size_t)(m + 1), s));
+  DTB_TRY(oscr.alloc(sizeof(u64) * (size_t)(otiles + 4), s));
+  DTB_CUDA_CHECK(cudaMemsetAsync(oscr.p, 0, oscr.bytes, s));
+  u64* d_ng = oscr.as<u64>() + otiles + 2;
+  DTB_TRY(launch_group_offsets(flags.p, 1, 0, m, pos.as<int32_t>(), d_ng, oscr.as<u64>(), s));
+  u64 h_ng = 0;
+  DTB_CUDA_CHECK(cudaMemcpyAsync(&h_ng, d_ng, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int64_t nsel = (int64_t)h_ng - 1;                 // without the sentinel
+  DTB_TRY(launch_set_emit(pos.as<int32_t>(), nsel, (const int32_t*)d_ord.dptr, (const int32_t*)d_off.dptr,
+                          (int32_t*)d_out.dptr, s));
+  if (d_out.staged()) DTB_TRY(d_out.finish((size_t)nsel * 4, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  *nout = nsel;
+  return DTB_OK;
+}
+
+int dtb_largest_group(const void* offsets, int64_t ngroups, int64_t skip, dtb_stream stream, int64_t* index_out,
+                      int64_t* size_out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  if (!index_out || !size_out || ngroups < 0 || skip < 0) { set_error("bad dtb_largest_group arguments"); return DTB_EINVAL; }
+  *index_out = -1; *size_out = 0;
+  DTB_TRY(ensure_context());
+  if (ngroups <= skip) return DTB_OK;
+  if (!offsets) { set_error("offsets is NULL"); return DTB_EINVAL; }
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  DevIn d_off; DTB_TRY(d_off.bind(offsets, sizeof(int32_t) * (size_t)(ngroups + 1), s));
+  DevBuf r; DTB_TRY(r.alloc(sizeof(u64), s));
+  DTB_CUDA_CHECK(cudaMemsetAsync(r.p, 0, sizeof(u64), s));
+  DTB_TRY(launch_largest_group((const int32_t*)d_off.dptr, ngroups, skip, r.as<u64>(), s));
+  u64 h = 0;
+  DTB_CUDA_CHECK(cudaMemcpyAsync(&h, r.p, sizeof(u64), cudaMemcpyDeviceToHost, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  if (h) { *size_out = (int64_t)(h >> 32); *index_out = (int64_t)(0xffffffffu - (u32)(h & 0xffffffffu)); }
+  return DTB_OK;
+}
+
+int dtb_join(const dtb_col* xkeys, const dtb_col* jkeys, int nkeys, int64_t nrows_x, int64_t nrows_j,
+             dtb_stream stream, void* index_out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  if (nkeys < 1 || nkeys > MAX_KEYS || !xkeys || !jkeys) { set_error("number of key columns must be in 1.." + std::to_string(MAX_KEYS)); return DTB_EINVAL; }
+  if (nrows_x < 0 || nrows_j < 0 || nrows_j > (int64_t)INT32_MAX) { set_error("bad row counts"); return DTB_EINVAL; }
+  for (int c = 0; c < nkeys; c++) {
+    if (!stype_supported(xkeys[c].stype) || !stype_supported(jkeys[c].stype)) {
+      set_error("join keys of stype " + std::to_string(xkeys[c].stype) + " / " + std::to_string(jkeys[c].stype) + " are not supported");
+      return DTB_ENOTIMPL;
+    }
+    const bool xd = xkeys[c].stype == DTB_STYPE_DATE32 || xkeys[c].stype == DTB_STYPE_TIME64;
+    const bool jd = jkeys[c].stype == DTB_STYPE_DATE32 || jkeys[c].stype == DTB_STYPE_TIME64;
+    if ((xd || jd) && xkeys[c].stype != jkeys[c].stype) {       // join.cc:384-385: date/time only join their own type
+      set_error("a date/time key column can only be joined to a column of the same type"); return DTB_EINVAL;
+    }
+  }
+  DTB_TRY(ensure_context());
+  if (nrows_x == 0) return DTB_OK;
+  if (!index_out) { set_error("index_out is NULL"); return DTB_EINVAL; }
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  std::vector<DevIn> xin(nkeys), jin(nkeys);
+  const void* xp[MAX_KEYS]; const void* jp[MAX_KEYS]; int xst[MAX_KEYS], jst[MAX_KEYS];
+  for (int c = 0; c < nkeys; c++) {
+    DTB_TRY(xin[c].bind(xkeys[c].data, (size_t)nrows_x * stype_bytes(xkeys[c].stype), s));
+    DTB_TRY(jin[c].bind(jkeys[c].data, (size_t)nrows_j * stype_bytes(jkeys[c].stype), s));
+    xp[c] = xin[c].dptr; jp[c] = jin[c].dptr; xst[c] = xkeys[c].stype; jst[c] = jkeys[c].stype;
+  }
+  DevOut d_out; DTB_TRY(d_out.bind(index_out, (size_t)nrows_x * 4, s));
+  DTB_TRY(launch_join(nkeys, xp, xst, jp, jst, nrows_x, nrows_j, (int32_t*)d_out.dptr, s));
+  if (d_out.staged()) { DTB_TRY(d_out.finish((size_t)nrows_x * 4, s)); DTB_CUDA_CHECK(cudaStreamSynchronize(s)); }
   return DTB_OK;
 }
 

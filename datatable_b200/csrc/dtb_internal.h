@@ -147,7 +147,9 @@ int launch_mark_heads(const void* sorted_keys, int key_bytes, int group_shift, i
 int launch_reduce_impl(int op, const void* value, int stype, int64_t nrows_value,
                        const void* order, int order_is64, const int32_t* offsets, int64_t ngroups,
                        int64_t n, unsigned long long* acc0, unsigned long long* acc1,
-                       void* out, cudaStream_t s);
+                       void* out, cudaStream_t s, void* extra = nullptr);
+// device scratch `extra` that launch_reduce_impl needs for `op` (sd: m2[ng]; nunique: one flag byte per row)
+size_t reduce_extra_bytes(int op, int64_t ng, int64_t n);
 int reduce_out_stype_host(int op, int stype);
 // *d_bad (device int, zeroed by the caller) = 1 + index of a group with offsets[g] >= offsets[g+1] (or offsets[0] != 0).
 int launch_offsets_check(const int32_t* offsets, int64_t ng, int* d_bad, cudaStream_t s);
@@ -186,6 +188,27 @@ int launch_gather(const void* src, int stype, int64_t nrows_src, const void* ord
                   int order_is64, int64_t n, void* out, cudaStream_t s);
 
 int launch_iota32(int32_t* out, int64_t n, cudaStream_t s);
+
+// ---------------------------------------------------------------------------
+// SURVEY.md 8(f) rows (dtb_next.cu): ordered reducers, set operations, mode, join
+// ---------------------------------------------------------------------------
+int launch_firstlast(const void* v, int stype, int64_t nv, const int32_t* order, const int32_t* offsets,
+                     int64_t ng, int last, void* out, cudaStream_t s);
+int launch_expand_gid(const int32_t* offsets, int64_t ng, int64_t n, int32_t* gid, cudaStream_t s);
+// sum/cnt: the MEAN accumulators of the same column; m2: double[ng], zeroed
+int launch_sd(const void* v, int stype, int64_t nv, const int32_t* order, const int32_t* offsets, int64_t ng, int64_t n,
+              const unsigned long long* sum, const unsigned long long* cnt, double* m2, void* out, cudaStream_t s);
+int launch_median(const void* v, int stype, int64_t nv, const int32_t* order, const int32_t* offsets,
+                  int64_t ng, void* out, cudaStream_t s);
+int launch_distinct_flags(const void* v, int stype, int64_t nv, const int32_t* order, const int32_t* offsets,
+                          int64_t ng, int64_t n, int8_t* flag, cudaStream_t s);
+int launch_set_select(const int32_t* order, const int32_t* offsets, int64_t ng, const int64_t* d_sizes, int K,
+                      int mode, uint8_t* flags, cudaStream_t s);
+int launch_set_emit(const int32_t* pos, int64_t nsel, const int32_t* order, const int32_t* offsets, int32_t* out_rows,
+                    cudaStream_t s);
+int launch_largest_group(const int32_t* offsets, int64_t ng, int64_t skip, unsigned long long* d_result, cudaStream_t s);
+int launch_join(int nkeys, const void* const* xcols, const int* xst, const void* const* jcols, const int* jst,
+                int64_t nx, int64_t nj, int32_t* out, cudaStream_t s);
 
 // Hybrid sort of wide single keys: order rows that tie on the top key bits by their low bits
 // (dtb_tiefix.cu).  counters: device uint32[2] = {long runs, fallback flag}.

@@ -257,7 +257,17 @@ static int reduce_out_stype(int op, int st) {
     case DTB_OP_MEAN: return isint ? DTB_STYPE_FLOAT64 : (isflt ? st : 0);         // fexpr_mean.cc:49-78
     case DTB_OP_MIN: case DTB_OP_MAX:
       return (isint || isflt) ? st : 0;      // fexpr_minmax.cc:50-72: the column's own stype (bool8 stays bool8)
+    case DTB_OP_FIRST: case DTB_OP_LAST: return stype_bytes(st) ? st : 0;          // head_reduce_unary.cc:126-128
+    case DTB_OP_SD: case DTB_OP_MEDIAN:                                           // head_reduce_unary.cc:224-245, 480-506
+      return isint ? DTB_STYPE_FLOAT64 : (isflt ? st : 0);
+    case DTB_OP_NUNIQUE: return stype_bytes(st) ? DTB_STYPE_INT64 : 0;            // head_reduce_unary.cc:398-415
   }
+  return 0;
+}
+
+size_t reduce_extra_bytes(int op, int64_t ng, int64_t n) {
+  if (op == DTB_OP_SD) return sizeof(double) * (size_t)(ng > 0 ? ng : 1);
+  if (op == DTB_OP_NUNIQUE) return (size_t)n + 16;
   return 0;
 }
 
@@ -308,12 +318,38 @@ static int dispatch_T(int st, const void* v, int64_t nv, const void* order, int 
 // acc0/acc1: device scratch of ng u64 each (allocated by the caller in dtb_api.cu)
 int launch_reduce_impl(int op, const void* value, int stype, int64_t nv, const void* order, int order_is64,
                        const int32_t* offsets, int64_t ng, int64_t n, u64* acc0, u64* acc1,
-                       void* out, cudaStream_t s)
+                       void* out, cudaStream_t s, void* extra)
 {
   const int out_st = reduce_out_stype(op, stype);
   if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
   if (ng == 0) return DTB_OK;
   const int fgrid = (int)((ng + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (ng + 255) / 256);
+  if (op >= DTB_OP_FIRST && op <= DTB_OP_NUNIQUE) {
+    // within-group ordered reducers (dtb_next.cu): they walk the ARR32 RowIndex
+    if (order_is64) { set_error("first/last/sd/median/nunique take an int32 RowIndex"); return DTB_ENOTIMPL; }
+    const int32_t* o32 = (const int32_t*)order;
+    if (op == DTB_OP_FIRST || op == DTB_OP_LAST) return launch_firstlast(value, stype, nv, o32, offsets, ng, op == DTB_OP_LAST, out, s);
+    if (op == DTB_OP_MEDIAN) return launch_median(value, stype, nv, o32, offsets, ng, out, s);
+    if (!extra) { set_error("internal: reducer scratch missing"); return DTB_EINVAL; }
+    if (op == DTB_OP_SD) {
+      fill_u64_kernel<<<fgrid, 256, 0, s>>>(acc0, ng, 0ull);
+      fill_u64_kernel<<<fgrid, 256, 0, s>>>(acc1, ng, 0ull);
+      fill_u64_kernel<<<fgrid, 256, 0, s>>>((u64*)extra, ng, 0ull);
+      count_launch(3);
+      if (n > 0) DTB_TRY(dispatch_T<CAT_MEAN>(stype, value, nv, order, 0, offsets, ng, n, acc0, acc1, 0, s));
+      return launch_sd(value, stype, nv, o32, offsets, ng, n, acc0, acc1, (double*)extra, out, s);
+    }
+    // NUNIQUE: flag the rows that start a new distinct value, then count the flags per group
+    int8_t* flag = (int8_t*)extra;
+    DTB_TRY(launch_distinct_flags(value, stype, nv, o32, offsets, ng, n, flag, s));
+    fill_u64_kernel<<<fgrid, 256, 0, s>>>(acc0, ng, 0ull);
+    count_launch();
+    if (n > 0) DTB_TRY(dispatch_T<CAT_COUNT>(DTB_STYPE_INT8, flag, n, nullptr, 0, offsets, ng, n, acc0, acc1, 0, s));
+    finalize_kernel<<<fgrid, 256, 0, s>>>(DTB_OP_COUNT, DTB_STYPE_INT8, DTB_STYPE_INT64, acc0, acc1, ng, out);
+    count_launch();
+    DTB_CUDA_CHECK(cudaGetLastError());
+    return DTB_OK;
+  }
   if (op == DTB_OP_NROWS) {
     nrows_kernel<<<fgrid, 256, 0, s>>>(offsets, ng, (int64_t*)out);
     count_launch();

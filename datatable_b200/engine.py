@@ -190,6 +190,26 @@ class Groupby:
             _memcpy_d2d(t.data_ptr(), lib.dtb_groupby_reduced(self._h, i), t.numel() * t.element_size())
         return t
 
+    def sort_grouped(self, value):
+        """RowIndex with the rows of every group ordered by `value` (NA first): what median / nunique read."""
+        v = Col(value)
+        t = torch.empty(self.norder, dtype=torch.int32, device="cuda")
+        if self.norder:
+            check(lib.dtb_sort_grouped(v.c(), v.nrows, ctypes.c_void_p(self.order_ptr), ctypes.c_void_p(self.offsets_ptr),
+                                       self.ngroups, _stream(), ctypes.c_void_p(t.data_ptr())))
+        return t
+
+    def reduce_ordered(self, op, value, order):
+        """Reducer over the handle's groups but another RowIndex (the output of sort_grouped)."""
+        v = Col(value)
+        out_st = lib.dtb_reduce_out_stype(op, v.stype)
+        if not out_st:
+            raise _lib.DtbValueError(f"Invalid column of stype {v.stype} in reducer {op}")
+        out, optr = _alloc(self.ngroups, out_st, True)
+        check(lib.dtb_reduce(op, v.c(), v.nrows, ctypes.c_void_p(order.data_ptr()), 0, ctypes.c_void_p(self.offsets_ptr),
+                             self.ngroups, _stream(), ctypes.c_void_p(optr)))
+        return out
+
     def order_col(self):
         """The RowIndex as a zero-copy column view (valid while the handle lives)."""
         return Col.from_ptr(self.order_ptr, INT32, self.norder, owner=self)
@@ -274,6 +294,63 @@ def gather(src, order, stype=None):
         out = out.view(np.bool_)
     check(lib.dtb_gather(s.c(), s.nrows, ctypes.c_void_p(o.ptr), 1 if o.stype == INT64 else 0, n,
                          _stream(), ctypes.c_void_p(optr)))
+    return out
+
+
+def sort_grouped(value, order, offsets, stype=None):
+    """Column::sort_grouped (sort.cc:1499-1530): reorder the rows inside every group of (order, offsets)
+    by `value` ascending, NA first, stable.  Returns the new int32 RowIndex (median / nunique read it)."""
+    v = Col(value, stype)
+    f = Col(offsets)
+    ngroups = f.nrows - 1
+    o = None if order is None else Col(order)
+    if o is not None and o.stype != INT32:
+        raise _lib.DtbValueError("order must be int32")
+    n = int(offsets[-1].item()) if is_tensor(offsets) else int(offsets[-1])
+    device = v.on_device and f.on_device and (o is None or o.on_device)
+    out, optr = _alloc(n, INT32, device)
+    check(lib.dtb_sort_grouped(v.c(), v.nrows, ctypes.c_void_p(o.ptr) if o is not None else None,
+                               ctypes.c_void_p(f.ptr), ngroups, _stream(), ctypes.c_void_p(optr)))
+    return out
+
+
+def set_select(mode, order, offsets, cum_sizes):
+    """Group selection of union / intersect / setdiff / symdiff (set_funcs.cc:126-456): the first-row
+    indices of the groups the operation keeps (int32, same memory kind as `order`)."""
+    o, f = Col(order), Col(offsets)
+    ngroups = f.nrows - 1
+    device = o.on_device and f.on_device
+    out, optr = _alloc(max(ngroups, 0), INT32, device)
+    K = len(cum_sizes)
+    cs = (ctypes.c_int64 * K)(*[int(x) for x in cum_sizes])
+    nout = ctypes.c_int64(0)
+    check(lib.dtb_set_select(int(mode), ctypes.c_void_p(o.ptr), ctypes.c_void_p(f.ptr), ngroups, cs, K,
+                             _stream(), ctypes.c_void_p(optr), ctypes.byref(nout)))
+    return out[:nout.value]
+
+
+def largest_group(offsets, skip=0):
+    """(index, size) of the first largest group among groups [skip, ngroups) -- mode / nmodal (stats.cc:984-991)."""
+    f = Col(offsets)
+    idx, size = ctypes.c_int64(-1), ctypes.c_int64(0)
+    check(lib.dtb_largest_group(ctypes.c_void_p(f.ptr), f.nrows - 1, int(skip), _stream(),
+                                ctypes.byref(idx), ctypes.byref(size)))
+    return idx.value, size.value
+
+
+def join_index(xcols, jcols):
+    """natural_join (frame/join.cc:392-470): for every X row the row of J (sorted by its key columns) with
+    equal key, or the NA index; int32, in HBM when every column is."""
+    xs, js = [Col(c) for c in xcols], [Col(c) for c in jcols]
+    if len(xs) != len(js) or not xs:
+        raise _lib.DtbValueError("join needs the same number (>= 1) of key columns on both sides")
+    nx, nj = xs[0].nrows, js[0].nrows
+    device = all(c.on_device for c in xs + js)
+    out, optr = _alloc(nx, INT32, device)
+    nk = len(xs)
+    cx = (dtb_col * nk)(*[c.c() for c in xs])
+    cj = (dtb_col * nk)(*[c.c() for c in js])
+    check(lib.dtb_join(cx, cj, nk, nx, nj, _stream(), ctypes.c_void_p(optr)))
     return out
 
 

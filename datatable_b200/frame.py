@@ -70,6 +70,12 @@ def mean(x): return Reducer(_lib.OP_MEAN, "mean", x)
 def min(x): return Reducer(_lib.OP_MIN, "min", x)          # noqa: A001
 def max(x): return Reducer(_lib.OP_MAX, "max", x)          # noqa: A001
 def countna(x): return Reducer(_lib.OP_COUNTNA, "countna", x)
+# within-group ordered reducers (src/core/expr/head_reduce_unary.cc:544-558)
+def first(x): return Reducer(_lib.OP_FIRST, "first", x)
+def last(x): return Reducer(_lib.OP_LAST, "last", x)
+def sd(x): return Reducer(_lib.OP_SD, "sd", x)
+def median(x): return Reducer(_lib.OP_MEDIAN, "median", x)
+def nunique(x): return Reducer(_lib.OP_NUNIQUE, "nunique", x) if isinstance(x, (ColRef, str)) else _frame_nunique(x)
 
 
 def count(x=None):
@@ -79,6 +85,17 @@ def count(x=None):
 class by:
     def __init__(self, *cols):
         self.cols = [_as_ref(c) for c in _flatten(cols)]
+
+
+class join:
+    """join(J): natural join with the keyed frame J (src/core/expr/py_join.cc; frame/join.cc:392-470)."""
+
+    def __init__(self, frame):
+        if not isinstance(frame, Frame):
+            raise TypeError("The argument to join() must be a Frame")
+        if not frame.key:
+            raise ValueError("The join frame is not keyed")
+        self.frame = frame
 
 
 class sort:
@@ -129,6 +146,7 @@ class Frame:
     def __init__(self, data=None, stypes=None, **kwargs):
         self._cols = {}
         self._stypes = {}
+        self._key = ()
         if data is None:
             data = kwargs
         if isinstance(data, Frame):
@@ -204,6 +222,52 @@ class Frame:
         fr._nrows = self._nrows
         return fr
 
+    # -- DT.key (frame/key.cc:118-180): sort by the key columns, require unique rows, key columns first
+    @property
+    def key(self):
+        return tuple(self._key)
+
+    @key.setter
+    def key(self, val):
+        names = [val] if isinstance(val, str) else list(val or [])
+        if not names:
+            self._key = ()
+            return
+        for nm in names:
+            if not isinstance(nm, str):
+                raise TypeError("Key should be a list/tuple of column names")
+            if nm not in self._cols:
+                raise KeyError(f"Column `{nm}` does not exist in the Frame")
+        if len(set(names)) != len(names):
+            raise ValueError("A column is specified multiple times within the key")
+        if self._nrows:
+            order, offsets, ng = engine.group([self._col(nm) for nm in names], [0] * len(names), NA_FIRST)
+            if ng < self._nrows:
+                raise ValueError("Cannot set a key: the values are not unique")
+        rest = [nm for nm in self._cols if nm not in names]
+        cols, sts = {}, {}
+        for nm in names + rest:
+            c = self._col(nm)
+            if self._nrows:
+                o = order if (engine.is_tensor(c.data) and c.data.is_cuda) == engine.is_tensor(order) else (
+                    order.cpu().numpy() if engine.is_tensor(order) else torch.from_numpy(order).cuda())
+                cols[nm] = engine.gather(c, o)
+            else:
+                cols[nm] = c.data
+            sts[nm] = c.stype
+        self._cols, self._stypes = cols, sts
+        self._key = tuple(names)
+
+    # -- column statistics that go through group() (stats.cc:955-1003) ---------------------------
+    def nunique(self):
+        return _frame_nunique(self)
+
+    def mode(self):
+        return _frame_mode(self)[0]
+
+    def nmodal(self):
+        return _frame_mode(self)[1]
+
     # -- DT.sort(cols) (sort.cc:1544-1574) ------------------------------------------
     def sort(self, *cols):
         return self[:, :, sort(*cols)]
@@ -215,16 +279,22 @@ class Frame:
         if len(item) < 2:
             raise ValueError("Frame[...] needs at least i and j")
         i, j = item[0], item[1]
-        by_, sort_ = None, None
+        by_, sort_, join_ = None, None, None
         for m in item[2:]:
             if isinstance(m, by):
                 by_ = m
             elif isinstance(m, sort):
                 sort_ = m
+            elif isinstance(m, join):
+                join_ = m
             else:
                 raise TypeError(f"Unsupported modifier {m!r}")
         if not (isinstance(i, slice) and i == slice(None)):
             raise NotImplementedError("row filters are outside the GPU hot path (use i = :)")
+        if join_ is not None:
+            if by_ is not None or sort_ is not None:
+                raise NotImplementedError("join() together with by()/sort() is outside the GPU hot path")
+            return _evaluate_join(self, j, join_.frame)
         return _evaluate(self, j, by_, sort_)
 
 
@@ -311,7 +381,9 @@ def _evaluate(DT, j, by_, sort_):
             # RowIndex + Groupby stay in HBM behind a handle; reducers go through it
             # the reducers of j are known before group() runs: hand them over so that the engine can
             # overlap them with the sort (dtb_groupby_create_reduce)
-            reds = [(e.op, None if e.arg is None else dcol(e.arg.name)) for e in exprs if isinstance(e, Reducer)]
+            # (median / nunique read the rows sorted inside their group: evaluated after group(), below)
+            reds = [(e.op, None if e.arg is None else dcol(e.arg.name)) for e in exprs
+                    if isinstance(e, Reducer) and e.op not in _SORTED_OPS]
             gb = engine.Groupby(keycols, flags, na_pos, reducers=reds)
             ngroups = gb.ngroups
         else:
@@ -339,7 +411,10 @@ def _evaluate(DT, j, by_, sort_):
                 add(ref.name, engine.gather(c, first), c.stype)
             ired = 0
             for name, e in zip(names, exprs):
-                if isinstance(e, Reducer):
+                if isinstance(e, Reducer) and e.op in _SORTED_OPS:
+                    c = dcol(e.arg.name)                      # Median_ColumnImpl::pre_materialize_hook: sort_grouped first
+                    add(name, gb.reduce_ordered(e.op, c, gb.sort_grouped(c)), _red_stype(dcol, e))
+                elif isinstance(e, Reducer):
                     add(name, gb.reduced(ired), _red_stype(dcol, e))
                     ired += 1
                 else:
@@ -427,47 +502,171 @@ def _red_stype(dcol, e):
     return engine.reduce_out_stype(e.op, dcol(e.arg.name).stype)
 
 
+_SORTED_OPS = (_lib.OP_MEDIAN, _lib.OP_NUNIQUE)
+
+
 def _reduce(dcol, e, order, offsets):
     if e.op == _lib.OP_NROWS:
         return engine.reduce(e.op, None, order, offsets)
-    return engine.reduce(e.op, dcol(e.arg.name), order, offsets)
+    c = dcol(e.arg.name)
+    if e.op in _SORTED_OPS:
+        order = engine.sort_grouped(c, order, offsets)
+    return engine.reduce(e.op, c, order, offsets)
 
 
 # ---------------------------------------------------------------------------
-# First consumers of group() beyond DT[i, j, by, sort]
+# Callers of group() beyond DT[i, j, by, sort]: set operations, column statistics, join
 # ---------------------------------------------------------------------------
-def unique(frame):
-    """dt.unique(frame): the sorted unique values (NA first) of a single-column frame --
-    group() + first row of every group, as src/core/set_funcs.cc:100-140 does."""
-    if frame.ncols != 1:
-        raise NotImplementedError("unique() of a multi-column frame (set union) is outside the GPU hot path")
-    name = frame.names[0]
-    c = frame._col(name)
-    host = not (engine.is_tensor(c.data) and c.data.is_cuda)
-    t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
-    cd = engine.Col(t if t.is_cuda else t.cuda(), c.stype)
-    gb = engine.Groupby([cd], [0], NA_FIRST)
-    vals = engine.gather(cd, gb.first_rows())
-    gb.close()
+_INT_ORDER = [BOOL, INT8, INT16, INT32, INT64]
+_TORCH_OF = {BOOL: "int8", INT8: "int8", INT16: "int16", INT32: "int32", INT64: "int64", FLOAT32: "float32", FLOAT64: "float64"}
+
+
+def _dev(c):
+    t = c.data if engine.is_tensor(c.data) else torch.from_numpy(np.ascontiguousarray(c.data))
+    return t if t.is_cuda else t.cuda()
+
+
+def _promote(cols):
+    """Common stype of rbind-ed columns (the reference upcasts to the widest input type) with NA mapped."""
+    sts = {c.stype for c in cols}
+    if len(sts) == 1:
+        return [_dev(c) for c in cols], cols[0].stype
+    isf = any(st in (FLOAT32, FLOAT64) for st in sts)
+    tgt = (FLOAT32 if sts <= {FLOAT32} else FLOAT64) if isf else builtins_max(sts, key=_INT_ORDER.index)
+    out = []
+    for c in cols:
+        t = _dev(c)
+        if c.stype != tgt:
+            if c.stype in (FLOAT32, FLOAT64):
+                t = t.to(getattr(torch, _TORCH_OF[tgt]))
+            else:
+                na = t == _NA_VALUE[c.stype]
+                t = t.to(getattr(torch, _TORCH_OF[tgt]))
+                t = torch.where(na, torch.full_like(t, float("nan") if isf else _NA_VALUE[tgt]), t)
+        out.append(t)
+    return out, tgt
+
+
+import builtins as _builtins  # noqa: E402
+builtins_max = _builtins.max
+
+
+def _set_op(mode, frames):
+    frames = [fr for fr in _flatten(frames)]
+    for fr in frames:
+        if not isinstance(fr, Frame):
+            raise TypeError("set functions expect a list or sequence of Frames")
+        if fr.ncols > 1:
+            raise ValueError(f"Only single-column Frames are allowed, but received a Frame with {fr.ncols} columns")
+    frames = [fr for fr in frames if fr.ncols == 1]
+    if not frames:
+        return Frame()
+    name = frames[0].names[0]
+    host = not any(engine.is_tensor(fr._cols[fr.names[0]]) and fr._cols[fr.names[0]].is_cuda for fr in frames)
+    tens, st = _promote([fr._col(fr.names[0]) for fr in frames])
+    if len(frames) <= 1:
+        mode = _lib.SET_UNION                                  # set_funcs.cc:302-305, 356-359, 438-441
+    cat = tens[0] if len(tens) == 1 else torch.cat(tens)
+    cd = engine.Col(cat, st)
     out = Frame()
+    if cat.numel() == 0:
+        vals = cat
+    else:
+        order, offsets, ng = engine.group([cd], [0], NA_FIRST)
+        rows = engine.set_select(mode, order, offsets, np.cumsum([t.numel() for t in tens]))
+        vals = engine.gather(cd, rows)
     out._cols[name] = vals.cpu().numpy() if host else vals
-    out._stypes[name] = c.stype
+    out._stypes[name] = st
     out._nrows = int(vals.shape[0])
     return out
 
 
-def nunique(frame):
-    """Frame.nunique(): number of distinct non-NA values per column (stats.cc:949-1010 via group())."""
+def union(*frames): return _set_op(_lib.SET_UNION, frames)
+def intersect(*frames): return _set_op(_lib.SET_INTERSECT, frames)
+def setdiff(*frames): return _set_op(_lib.SET_SETDIFF, frames)
+def symdiff(*frames): return _set_op(_lib.SET_SYMDIFF, frames)
+
+
+def unique(frame):
+    """dt.unique(frame): the sorted unique values (NA first) -- the union of the frame's columns
+    (set_funcs.cc:203-216)."""
+    cols = []
+    for nm in frame.names:
+        fr = Frame(); fr._cols[nm] = frame._cols[nm]; fr._stypes[nm] = frame._stypes[nm]; fr._nrows = frame.nrows
+        cols.append(fr)
+    return _set_op(_lib.SET_UNION, cols)
+
+
+def _column_groups(frame, name):
+    c = frame._col(name)
+    cd = engine.Col(_dev(c), c.stype)
+    if cd.nrows == 0:
+        return cd, None, None, 0, False
+    order, offsets, ng = engine.group([cd], [0], NA_FIRST)
+    # the NA rows sort first: the column has NAs iff the first sorted row is NA (stats.cc:966-975)
+    first = engine.gather(cd, order[:1]).cpu().numpy()
+    has_na = bool(np.isnan(first[0])) if c.stype in (FLOAT32, FLOAT64) else bool(first[0] == _NA_VALUE[c.stype])
+    return cd, order, offsets, ng, has_na
+
+
+def _frame_nunique(frame):
+    """Frame.nunique(): distinct non-NA values per column (stats.cc:955-979 via group())."""
     out = Frame()
     for name in frame.names:
-        c = frame._col(name)
-        t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
-        cd = engine.Col(t if t.is_cuda else t.cuda(), c.stype)
-        gb = engine.Groupby([cd], [0], NA_FIRST, reducers=[(_lib.OP_COUNT, cd)])
-        valid = gb.reduced(0)                      # groups whose key is NA have count(key) == 0
-        n = int((valid > 0).sum().item()) if gb.ngroups > 0 else 0
-        gb.close()
-        out._cols[name] = np.array([n], dtype=np.int64)
+        cd, order, offsets, ng, has_na = _column_groups(frame, name)
+        out._cols[name] = np.array([ng - int(has_na)], dtype=np.int64)
         out._stypes[name] = INT64
     out._nrows = 1
     return out
+
+
+def _frame_mode(frame):
+    """(Frame.mode(), Frame.nmodal()): value and size of the first largest non-NA group (stats.cc:981-1003)."""
+    mode, nmodal = Frame(), Frame()
+    for name in frame.names:
+        cd, order, offsets, ng, has_na = _column_groups(frame, name)
+        idx, size = (-1, 0) if order is None else engine.largest_group(offsets, int(has_na))
+        if size:
+            val = engine.gather(cd, engine.gather(engine.Col(order, INT32), offsets[idx:idx + 1])).cpu().numpy()
+        else:
+            val = np.array([np.nan if cd.stype in (FLOAT32, FLOAT64) else _NA_VALUE[cd.stype]],
+                           dtype=getattr(np, _TORCH_OF[cd.stype]))
+        mode._cols[name] = val; mode._stypes[name] = cd.stype
+        nmodal._cols[name] = np.array([size], dtype=np.int64); nmodal._stypes[name] = INT64
+    mode._nrows = nmodal._nrows = 1
+    return mode, nmodal
+
+
+def _evaluate_join(X, j, J):
+    """X[:, j, join(J)] (eval_context.cc add_join + natural_join, frame/join.cc:392-470): J's key columns are
+    looked up by name in X; J's non-key columns are viewed through the resulting RowIndex."""
+    keys = list(J.key)
+    for nm in keys:
+        if nm not in X._cols:
+            raise ValueError(f"Key column `{nm}` does not exist in the left Frame")
+    host = not any(engine.is_tensor(c) and c.is_cuda for c in X._cols.values())
+    xk = [engine.Col(_dev(X._col(nm)), X._stypes[nm]) for nm in keys]
+    jk = [engine.Col(_dev(J._col(nm)), J._stypes[nm]) for nm in keys]
+    index = engine.join_index(xk, jk)
+    out = Frame()
+    wanted = None if j_is_all(j) else [e.name for e in _resolve_j_names(j)]
+    for nm in X.names:
+        if wanted is None or nm in wanted:
+            out._cols[nm] = X._cols[nm]; out._stypes[nm] = X._stypes[nm]
+    for nm in J.names:
+        if nm in keys or (wanted is not None and nm not in wanted):
+            continue
+        c = J._col(nm)
+        g = engine.gather(engine.Col(_dev(c), c.stype), index)
+        name, k = nm, 0
+        while name in out._cols:
+            name = f"{nm}.{k}"; k += 1
+        out._cols[name] = g.cpu().numpy() if host else g
+        out._stypes[name] = c.stype
+    out._nrows = X.nrows
+    return out
+
+
+def _resolve_j_names(j):
+    es = j if isinstance(j, (list, tuple)) else [j]
+    return [_as_ref(e) for e in es]

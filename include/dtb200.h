@@ -69,6 +69,18 @@ extern "C" {
 #define DTB_OP_COUNT    5   /* CountUnary_ColumnImpl<T,false> column/count.h:31-56   */
 #define DTB_OP_COUNTNA  6   /* CountUnary_ColumnImpl<T,true>                         */
 #define DTB_OP_NROWS    7   /* CountNullary_ColumnImpl        column/count.h:60-89   */
+/* within-group ordered reducers (expr/head_reduce_unary.cc) */
+#define DTB_OP_FIRST    8   /* FirstLast_ColumnImpl<true>     head_reduce_unary.cc:120-170: value of the group's first row */
+#define DTB_OP_LAST     9   /* FirstLast_ColumnImpl<false>                                                                  */
+#define DTB_OP_SD      10   /* sd_reducer                     head_reduce_unary.cc:197-219: sample sd, count <= 1 -> NA    */
+#define DTB_OP_MEDIAN  11   /* Median_ColumnImpl              head_reduce_unary.cc:421-468: needs dtb_sort_grouped's order */
+#define DTB_OP_NUNIQUE 12   /* op_nunique                     head_reduce_unary.cc:383-394: needs dtb_sort_grouped's order */
+
+/* set operations, set_funcs.cc:126-456 */
+#define DTB_SET_UNION      0
+#define DTB_SET_INTERSECT  1
+#define DTB_SET_SETDIFF    2
+#define DTB_SET_SYMDIFF    3
 
 /* error codes */
 #define DTB_OK         0
@@ -205,6 +217,45 @@ DTB_API int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nr
 DTB_API int dtb_gather(dtb_col src, int64_t nrows_src,
                const void* order, int order_is64, int64_t n,
                dtb_stream stream, void* out);
+
+/*
+ * dtb_sort_grouped -- replaces Column::sort_grouped (sort.cc:1499-1530): reorders the rows INSIDE every
+ * group of (order, offsets) by `value` ascending, NA first, stable; the groups themselves stay where
+ * they are.  order_out: int32[offsets[ngroups]].  DTB_OP_MEDIAN / DTB_OP_NUNIQUE expect this order
+ * (the reference's Median_ColumnImpl calls sort_grouped in its pre_materialize_hook).
+ */
+DTB_API int dtb_sort_grouped(dtb_col value, int64_t nrows_value, const void* order, const void* offsets,
+                     int64_t ngroups, dtb_stream stream, void* order_out);
+
+/*
+ * dtb_set_select -- the group-selection step of union / intersect / setdiff / symdiff
+ * (set_funcs.cc:126-456).  The caller concatenated K single-column inputs (input k holds the rows
+ * cum_sizes[k-1] .. cum_sizes[k]-1), grouped the result with dtb_group and passes its (order, offsets).
+ * rows_out: int32[ngroups] receives, for every group that the operation keeps, the row index of the
+ * group's first row (ascending group order); *nout = how many.  Gathering the concatenated column
+ * through rows_out gives the result column.
+ */
+DTB_API int dtb_set_select(int mode, const void* order, const void* offsets, int64_t ngroups,
+                   const int64_t* cum_sizes, int ninputs, dtb_stream stream, void* rows_out, int64_t* nout);
+
+/*
+ * dtb_largest_group -- the mode / nmodal scan of NumericStats<T>::compute_sorted_stats
+ * (stats.cc:984-991): index and size of the first largest group among groups [skip, ngroups)
+ * (skip = 1 when the first group holds the NA rows).  *index_out = -1 when there is no such group.
+ */
+DTB_API int dtb_largest_group(const void* offsets, int64_t ngroups, int64_t skip, dtb_stream stream,
+                      int64_t* index_out, int64_t* size_out);
+
+/*
+ * dtb_join -- replaces natural_join(xdt, jdt) (frame/join.cc:392-470): for every row of X the index
+ * of the row of the keyed frame J whose key columns all compare equal (FwCmp, join.cc:199-232: NA
+ * matches NA; an X value that J's integer key type cannot represent matches nothing), or the NA
+ * index INT32_MIN.  jkeys must be sorted ascending, NA first, with unique rows -- what setting a key
+ * produces (DataTable::set_key, frame/key.cc:118-180 = dtb_group + uniqueness check + dtb_gather).
+ * index_out: int32[nrows_x], the ARR32 RowIndex the reference applies to J's non-key columns.
+ */
+DTB_API int dtb_join(const dtb_col* xkeys, const dtb_col* jkeys, int nkeys, int64_t nrows_x, int64_t nrows_j,
+             dtb_stream stream, void* index_out);
 
 /*
  * Multi-GPU merge of per-group partials over a small group-key domain (one process per GPU; the

@@ -66,7 +66,9 @@ enum { FLAG_DESCENDING = 2, FLAG_SORT_ONLY = 4 };
 enum { NA_FIRST = 1, NA_LAST = 2, NA_REMOVE = 3 };
 /* reducer codes (ours; one per reference ColumnImpl) */
 enum { OP_SUM = 1, OP_MEAN = 2, OP_MIN = 3, OP_MAX = 4, OP_COUNT = 5,
-       OP_COUNTNA = 6, OP_NROWS = 7 };
+       OP_COUNTNA = 6, OP_NROWS = 7,
+       /* within-group ordered reducers, expr/head_reduce_unary.cc */
+       OP_FIRST = 8, OP_LAST = 9, OP_SD = 10, OP_MEDIAN = 11, OP_NUNIQUE = 12 };
 
 static int stype_size(int st) {
   switch (st) {
@@ -404,7 +406,85 @@ int orc_gather(const void* src, int st, const int32_t* idx, int64_t n, void* out
  *         same stype as input (bool -> int8); first strictly-better valid
  *         value wins; no valid rows -> NA.
  *   COUNT/COUNTNA column/count.h:35-56; NROWS column/count.h:82-87 -> int64.
+ *   FIRST/LAST expr/head_reduce_unary.cc:160-167: the element at the group's first / last
+ *         position (NA stays NA), input stype.
+ *   SD    expr/head_reduce_unary.cc:197-219: Welford recurrence over the valid rows in sorted
+ *         order; count <= 1 or NaN m2 -> NA; float32 -> float32, everything else -> float64.
+ *   MEDIAN expr/head_reduce_unary.cc:440-468: `order` must be sorted inside every group by the
+ *         value, NA first (Column::sort_grouped, sort.cc:1499-1530; oracle.sort_grouped);
+ *         skips the leading NAs, middle element or the mean of the two middle ones.
+ *   NUNIQUE expr/head_reduce_unary.cc:383-394: size of a std::set<T> of the valid values
+ *         (floats compare by value: -0.0 and +0.0 are one value) -> int64.
  *--------------------------------------------------------------------------*/
+static int cmp_i64(const void* a, const void* b) { int64_t x = *(const int64_t*)a, y = *(const int64_t*)b; return (x > y) - (x < y); }
+static int cmp_f64(const void* a, const void* b) { double x = *(const double*)a, y = *(const double*)b; return (x > y) - (x < y); }
+
+static double elem_as_double(const void* v, int st, int64_t j, int* na) {
+  if (st == ST_FLOAT32) { float f = ((const float*)v)[j]; *na = isnan(f); return (double)f; }
+  if (st == ST_FLOAT64) { double d = ((const double*)v)[j]; *na = isnan(d); return d; }
+  return (double)read_int(v, st, j, na);
+}
+
+static void ordered_groups(int op, const void* v, int st, const int32_t* order,
+                           const int32_t* offsets, int64_t g_lo, int64_t g_hi, void* out)
+{
+  int sz = stype_size(st);
+  int isf = (st == ST_FLOAT32 || st == ST_FLOAT64);
+  for (int64_t g = g_lo; g < g_hi; g++) {
+    int64_t i0 = offsets[g], i1 = offsets[g + 1];
+    if (op == OP_FIRST || op == OP_LAST) {
+      int64_t p = (op == OP_FIRST) ? i0 : i1 - 1;
+      int64_t j = order ? order[p] : p;
+      memcpy((char*)out + g * sz, (const char*)v + j * sz, (size_t)sz);
+    } else if (op == OP_SD) {
+      double mean = 0, m2 = 0; int64_t count = 0;
+      for (int64_t gi = i0; gi < i1; gi++) {
+        int64_t j = order ? order[gi] : gi;
+        int na; double value = elem_as_double(v, st, j, &na);
+        if (na) continue;
+        count++;
+        double tmp1 = value - mean;
+        mean += tmp1 / (double)count;
+        double tmp2 = value - mean;
+        m2 += tmp1 * tmp2;
+      }
+      int valid = !(count <= 1 || isnan(m2));
+      double sd = m2 >= 0 ? sqrt(m2 / (double)(count - 1)) : 0.0;
+      if (st == ST_FLOAT32) ((float*)out)[g] = valid ? (float)sd : NAN;
+      else ((double*)out)[g] = valid ? sd : NAN;
+    } else if (op == OP_MEDIAN) {
+      int na = 1;
+      while (i0 < i1) { int64_t j = order ? order[i0] : i0; (void)elem_as_double(v, st, j, &na); if (!na) break; i0++; }
+      if (i0 == i1) { if (st == ST_FLOAT32) ((float*)out)[g] = NAN; else ((double*)out)[g] = NAN; continue; }
+      int64_t jm = (i0 + i1) / 2;
+      int64_t r1 = order ? order[jm] : jm;
+      double v1 = elem_as_double(v, st, r1, &na);
+      if ((i1 - i0) & 1) {
+        if (st == ST_FLOAT32) ((float*)out)[g] = (float)v1; else ((double*)out)[g] = v1;
+      } else {
+        int64_t r2 = order ? order[jm - 1] : jm - 1;
+        double v2 = elem_as_double(v, st, r2, &na);
+        if (st == ST_FLOAT32) ((float*)out)[g] = ((float)v1 + (float)v2) / 2;
+        else ((double*)out)[g] = (v1 + v2) / 2;
+      }
+    } else if (op == OP_NUNIQUE) {
+      int64_t m = i1 - i0, k = 0, distinct = 0;
+      void* tmp = malloc((size_t)(m > 0 ? m : 1) * 8);
+      for (int64_t gi = i0; gi < i1; gi++) {
+        int64_t j = order ? order[gi] : gi;
+        int na;
+        if (isf) { double d = elem_as_double(v, st, j, &na); if (!na) ((double*)tmp)[k++] = d; }
+        else { int64_t t = read_int(v, st, j, &na); if (!na) ((int64_t*)tmp)[k++] = t; }
+      }
+      qsort(tmp, (size_t)k, 8, isf ? cmp_f64 : cmp_i64);
+      for (int64_t i = 0; i < k; i++)
+        if (i == 0 || (isf ? ((double*)tmp)[i] != ((double*)tmp)[i - 1] : ((int64_t*)tmp)[i] != ((int64_t*)tmp)[i - 1])) distinct++;
+      free(tmp);
+      ((int64_t*)out)[g] = distinct;
+    }
+  }
+}
+
 typedef struct {
   int op; const void* v; int st; const int32_t* order; const int32_t* offsets; int64_t ng; void* out;
 } red_ctx;
@@ -419,14 +499,15 @@ static void red_part(int t, int T, void* vc)
   red_ctx* c = (red_ctx*)vc;
   for (int64_t g0 = (int64_t)t * 1024; g0 < c->ng; g0 += (int64_t)T * 1024) {
     int64_t g1 = g0 + 1024 < c->ng ? g0 + 1024 : c->ng;
-    reduce_groups(c->op, c->v, c->st, c->order, c->offsets, g0, g1, c->out);
+    if (c->op >= OP_FIRST) ordered_groups(c->op, c->v, c->st, c->order, c->offsets, g0, g1, c->out);
+    else reduce_groups(c->op, c->v, c->st, c->order, c->offsets, g0, g1, c->out);
   }
 }
 
 int orc_reduce(int op, const void* v, int st, const int32_t* order,
                const int32_t* offsets, int64_t ng, void* out)
 {
-  if (op < OP_SUM || op > OP_NROWS) return -1;
+  if (op < OP_SUM || op > OP_NUNIQUE) return -1;
   if (op != OP_NROWS && !stype_size(st)) return -1;
   red_ctx c; c.op = op; c.v = v; c.st = st; c.order = order; c.offsets = offsets; c.ng = ng; c.out = out;
   par_run(ng < 4096 ? 1 : g_threads, red_part, &c);

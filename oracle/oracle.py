@@ -23,6 +23,8 @@ BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64 = 1, 2, 3, 4, 5, 6, 7
 DESCENDING, SORT_ONLY = 2, 4
 NA_FIRST, NA_LAST, NA_REMOVE = 1, 2, 3
 SUM, MEAN, MIN, MAX, COUNT, COUNTNA, NROWS = 1, 2, 3, 4, 5, 6, 7
+FIRST, LAST, SD, MEDIAN, NUNIQUE = 8, 9, 10, 11, 12
+SET_UNION, SET_INTERSECT, SET_SETDIFF, SET_SYMDIFF = 0, 1, 2, 3
 
 _NP2ST = {
     np.dtype(np.bool_): BOOL, np.dtype(np.int8): INT8, np.dtype(np.int16): INT16,
@@ -105,8 +107,10 @@ def group(cols, flags=None, na_pos=NA_FIRST, stypes=None):
 
 def out_dtype(op, st):
     """Output numpy dtype of a reducer (see orc_reduce header)."""
-    if op in (COUNT, COUNTNA, NROWS):
+    if op in (COUNT, COUNTNA, NROWS, NUNIQUE):
         return np.int64
+    if op in (SD, MEDIAN):
+        return np.float32 if st == FLOAT32 else np.float64
     if op == SUM:
         return {FLOAT32: np.float32, FLOAT64: np.float64}.get(st, np.int64)
     if op == MEAN:
@@ -138,4 +142,116 @@ def gather(src, idx, stype=None):
                           ctypes.c_int64(len(idx)), _ptr(out))
     if rc != 0:
         raise NotImplementedError("oracle: unsupported stype")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# restatements of the callers of group()
+# ---------------------------------------------------------------------------
+def sort_grouped(v, order, offsets, stype=None):
+    """Column::sort_grouped (sort.cc:1499-1530): rows reordered inside every group by the value,
+    ascending, NA first, stable; restated as a stable sort by (group id, value)."""
+    v = np.ascontiguousarray(v)
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = int(offsets[-1])
+    order = np.arange(n, dtype=np.int32) if order is None else np.asarray(order, dtype=np.int32)
+    gid = np.repeat(np.arange(len(offsets) - 1, dtype=np.int32), np.diff(offsets))
+    o2, _, _ = group([gid, v[order]], [SORT_ONLY, SORT_ONLY], NA_FIRST,
+                     stypes=None if stype is None else [INT32, stype])
+    return order[o2]
+
+
+def set_select(mode, order, offsets, cum_sizes):
+    """Group selection of union / intersect / setdiff / symdiff (set_funcs.cc:126-456): row index of the
+    first row of every kept group.  Inside a group the RowIndex ascends, so the inputs a group touches
+    are found from the row indices (input k holds rows cum_sizes[k-1] .. cum_sizes[k]-1)."""
+    out = []
+    K = len(cum_sizes)
+    for g in range(len(offsets) - 1):
+        rows = order[offsets[g]:offsets[g + 1]]
+        present = np.unique(np.searchsorted(np.asarray(cum_sizes), rows, side="right"))
+        if mode == SET_UNION or K < 2:
+            keep = True
+        elif mode == SET_INTERSECT:
+            keep = len(present) == K
+        elif mode == SET_SETDIFF:
+            keep = len(present) == 1 and present[0] == 0
+        else:
+            keep = (rows[0] < cum_sizes[0]) == (rows[-1] < cum_sizes[0]) if K == 2 else len(present) % 2 == 1
+        if keep:
+            out.append(rows[0])
+    return np.array(out, dtype=np.int32)
+
+
+def largest_group(offsets, skip):
+    """stats.cc:984-991: index and size of the first largest group among groups [skip, ng)."""
+    sizes = np.diff(np.asarray(offsets, dtype=np.int64))[skip:]
+    if len(sizes) == 0 or sizes.max() == 0:
+        return -1, 0
+    i = int(np.argmax(sizes))               # first maximum
+    return i + skip, int(sizes[i])
+
+
+def _na_mask(a, st):
+    if st in (FLOAT32, FLOAT64):
+        return np.isnan(a)
+    return a == {BOOL: -128, INT8: -128, INT16: -2**15, INT32: -2**31, INT64: -2**63}[st]
+
+
+def join_index(xcols, xst, jcols, jst):
+    """natural_join (frame/join.cc:392-470): for every X row, binary search (join.cc:392-406) over the
+    rows of J (sorted by its key, NA first) with the column comparators of FwCmp (join.cc:199-232)."""
+    nx, nj = len(xcols[0]), len(jcols[0])
+    xna = [_na_mask(c, s) for c, s in zip(xcols, xst)]
+    jna = [_na_mask(c, s) for c, s in zip(jcols, jst)]
+    out = np.full(nx, -2**31, dtype=np.int32)
+    if nj == 0:
+        return out
+    int_range = {BOOL: (-128, 127), INT8: (-128, 127), INT16: (-2**15, 2**15 - 1), INT32: (-2**31, 2**31 - 1),
+                 INT64: (-2**63, 2**63 - 1)}
+    for r in range(nx):
+        xv, bad = [], False
+        for c in range(len(xcols)):
+            if xna[c][r]:
+                xv.append(None); continue
+            x = xcols[c][r].item()
+            if jst[c] in int_range:                               # set_xrow: values J's type cannot hold match nothing
+                if isinstance(x, float) and (x != int(x) if np.isfinite(x) else True):
+                    bad = True
+                elif not (int_range[jst[c]][0] <= int(x) <= int_range[jst[c]][1]):
+                    bad = True
+                x = int(x) if not bad else x
+            elif jst[c] == FLOAT32:
+                x = float(np.float32(x))
+            else:
+                x = float(x)
+            xv.append(x)
+        if bad:
+            continue
+
+        def cmp(row):
+            for c in range(len(xcols)):
+                jvalid, xvalid = not jna[c][row], xv[c] is not None
+                if jvalid and xvalid:
+                    jv = jcols[c][row].item()
+                    if jv != xv[c]:
+                        return 1 if jv > xv[c] else -1
+                elif jvalid != xvalid:
+                    return int(jvalid) - int(xvalid)
+            return 0
+        start, end = 0, nj - 1
+        found = -1
+        while start < end:
+            mid = (start + end) >> 1
+            t = cmp(mid)
+            if t > 0:
+                end = mid
+            elif t < 0:
+                start = mid + 1
+            else:
+                found = mid; break
+        if found < 0 and cmp(start) == 0:
+            found = start
+        if found >= 0:
+            out[r] = found
     return out
