@@ -519,6 +519,19 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.empty_cache()
         engine.set_option("trim_scratch", 1)
         line["other_configs"] = other_configs(torch, engine, _lib, n, peak)
+    # ---- the drop-in number: the PATCHED reference's own query with the engine options off / on -----
+    patched = os.path.join(ROOT, "integration", "_ref_patched")
+    if rank == 0 and world == 1 and not args.no_extra and os.path.exists(os.path.join(patched, "datatable", "__init__.py")):
+        torch.cuda.empty_cache()
+        engine.set_option("trim_scratch", 1)
+        try:
+            env = dict(os.environ, PYTHONPATH=patched)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "integration", "bench_hook.py")], env=env,
+                               capture_output=True, text=True, timeout=600)
+            js = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            line["patched_reference"] = json.loads(js[-1]) if js else {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:                              # pragma: no cover
+            line["patched_reference"] = {"error": str(e)[:200]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -27,7 +27,7 @@ EXPORTS = [
     "dtb_gather", "dtb_memcpy", "dtb_set_option", "dtb_get_option", "dtb_last_call_stats",
     "dtb_profile_count", "dtb_profile_get", "dtb_profile_reset",
     "dtb_dense_scatter", "dtb_dense_compact",
-    "dtb_sort_grouped", "dtb_set_select", "dtb_largest_group", "dtb_join",
+    "dtb_sort_grouped", "dtb_set_select", "dtb_largest_group", "dtb_join", "dtb_cache_begin", "dtb_cache_end",
 ]
 
 
@@ -41,7 +41,7 @@ class dtb_reduce_spec(ctypes.Structure):
 
 class dtb_call_stats(ctypes.Structure):
     _fields_ = [("kernels_launched", ctypes.c_int32), ("radix_passes", ctypes.c_int32),
-                ("key_bits", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("key_bits", ctypes.c_int32), ("cache_hits", ctypes.c_int32),
                 ("scratch_bytes", ctypes.c_int64)]
 
 
@@ -139,7 +139,7 @@ def last_call_stats():
     st = dtb_call_stats()
     check(lib.dtb_last_call_stats(ctypes.byref(st)))
     return {"kernels_launched": st.kernels_launched, "radix_passes": st.radix_passes,
-            "key_bits": st.key_bits, "scratch_bytes": st.scratch_bytes}
+            "key_bits": st.key_bits, "cache_hits": st.cache_hits, "scratch_bytes": st.scratch_bytes}
 
 
 def profile_records(reset=True):

@@ -4,6 +4,7 @@
 #include <stdio.h>
 #include <chrono>
 #include <string.h>
+#include <list>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -28,6 +29,7 @@ static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
 static int64_t opt_hybrid = 0;         // 1 = hybrid top-bits + tie-fix sort for wide single keys (sort-only)
 static thread_local int opt_trust_offsets = 0;  // internal: dtb_groupby_reduce passes the handle's own offsets to dtb_reduce
+static int64_t opt_bucketed = 1;       // 1 = columns with >= 2 L2 atomics per row take the bucketed multi-reducer (dtb_bucket.cu)
 static int64_t opt_overlap = 0;        // 1 = run fused direct reducers on a side stream under the sort passes
 
 // ---------------------------------------------------------------------------
@@ -239,6 +241,26 @@ static bool is_device_ptr(const void* p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// Host inputs kept resident in HBM between the calls of one query (dtb_cache_begin / dtb_cache_end): the
+// reference-side hook calls dtb_group on the key columns and then dtb_reduce / dtb_gather on the value
+// columns and on the RowIndex it just received, all inside one EvalContext::evaluate(); without the cache
+// every call uploads its host buffers again.  Entries are keyed by (host pointer, bytes) and are only valid
+// while the caller guarantees the host buffers do not change -- the bracket is the caller's promise.
+struct InputCache {
+  struct Entry { const void* host; size_t bytes; void* dev; int device; };
+  std::vector<Entry> entries;
+  int depth = 0;
+  void* find(const void* p, size_t bytes, int dev) const {
+    for (const Entry& e : entries) if (e.host == p && e.bytes == bytes && e.device == dev) return e.dev;
+    return nullptr;
+  }
+  void clear() {
+    for (Entry& e : entries) { int cur = 0; cudaGetDevice(&cur); if (cur != e.device) cudaSetDevice(e.device); cudaFree(e.dev); if (cur != e.device) cudaSetDevice(cur); }
+    entries.clear();
+  }
+};
+static thread_local InputCache t_cache;
+
 // Input that may live on the host: staged into HBM when needed.
 struct DevIn {
   const void* dptr = nullptr;
@@ -246,6 +268,19 @@ struct DevIn {
   int bind(const void* p, size_t bytes, cudaStream_t s) {
     if (!p || bytes == 0) { dptr = p; return DTB_OK; }
     if (is_device_ptr(p)) { dptr = p; return DTB_OK; }
+    if (t_cache.depth > 0) {
+      int dev = 0; DTB_CUDA_CHECK(cudaGetDevice(&dev));
+      if (void* d = t_cache.find(p, bytes, dev)) { dptr = d; t_stats.cache_hits += 1; return DTB_OK; }
+      void* d = nullptr;
+      cudaError_t e = cudaMalloc(&d, bytes);
+      if (e == cudaSuccess) {
+        DTB_CUDA_CHECK(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s));
+        t_cache.entries.push_back({p, bytes, d, dev});
+        dptr = d;
+        return DTB_OK;
+      }
+      cudaGetLastError();                           // no room to keep it: stage it for this call only
+    }
     DTB_TRY(buf.alloc(bytes, s));
     DTB_CUDA_CHECK(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, s));
     dptr = buf.p;
@@ -272,6 +307,17 @@ struct DevOut {
   int finish(size_t nbytes, cudaStream_t s) {
     if (host && nbytes) DTB_CUDA_CHECK(cudaMemcpyAsync(host, dptr, nbytes, cudaMemcpyDeviceToHost, s));
     return DTB_OK;
+  }
+  // inside a cache bracket: keep a device copy of a result that went to the host (the hook hands the RowIndex
+  // of dtb_group straight back to dtb_reduce / dtb_gather)
+  static void remember(const void* host_ptr, const void* dev_src, size_t nbytes, cudaStream_t s) {
+    if (t_cache.depth <= 0 || !host_ptr || !nbytes) return;
+    int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (t_cache.find(host_ptr, nbytes, dev)) return;
+    void* d = nullptr;
+    if (cudaMalloc(&d, nbytes) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaMemcpyAsync(d, dev_src, nbytes, cudaMemcpyDeviceToDevice, s) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return; }
+    t_cache.entries.push_back({host_ptr, nbytes, d, dev});
   }
 };
 
@@ -537,6 +583,17 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     DTB_CUDA_CHECK(cudaMemsetAsync(gcount.p, 0, sizeof(u32) * (size_t)ctable, s));
   }
   DevBuf facc;
+  DevBuf bxk;                                          // bucketed reducers: the rows' composite keys, kept
+  bool bucket_wanted = false;                          // some value column costs >= 2 L2 atomics per row
+  if (fused_direct && opt_bucketed && dbits0 >= BK_MIN_DBITS && dbits0 <= BK_MAX_DBITS)
+    for (int i = 0; i < fr->n && !bucket_wanted; i++) {
+      if (fr->spec[i].op == DTB_OP_NROWS) continue;
+      int cost = 0;
+      for (int j = 0; j < fr->n; j++)
+        if (fr->spec[j].op != DTB_OP_NROWS && fr->spec[j].value.data == fr->spec[i].value.data)
+          cost += fr->spec[j].op == DTB_OP_MEAN ? 2 : 1;
+      bucket_wanted = cost >= 2;
+    }
   const int64_t ftable = fused_direct ? ((int64_t)1 << dbits0) : 0;
   // Measured on C2: under the sort passes the accumulation gains ~2 % (both want the same SMs) and
   // inflates every scatter launch by ~40 %, so by default it runs on `s` after the offsets stage;
@@ -624,9 +681,13 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     t_stats.radix_passes += pp.npasses;
 
     int src_kind = 1;
+    // multi-column keys whose reducers will take the bucketed path (dtb_bucket.cu): the composite keys are
+    // composed ONCE into a buffer the passes only read, and the bucket kernels read them again afterwards
+    const bool keep_composite = bucket_wanted && !fused_raw && nrounds == 1 && key_bytes == 4;
+    if (keep_composite) DTB_TRY(bxk.alloc(sizeof(u32) * (size_t)n, s));
     if (!fused_raw) {
       ProfScope ps("compose_keys", s);
-      DTB_TRY(launch_compose_keys(rk, n, idx_cur, keyA.p, key_bytes, s)); src_kind = 0;
+      DTB_TRY(launch_compose_keys(rk, n, idx_cur, keep_composite ? bxk.p : keyA.p, key_bytes, s)); src_kind = 0;
     }
 
     // per-pass scratch: chunk x digit counts + digit totals/bases; largest digit count per pass
@@ -635,7 +696,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
 
     int32_t* round_out = last_round ? order : ((ri & 1) ? idxR1.as<int32_t>() : idxR0.as<int32_t>());
     // raw single column: the first count kernel materialises the normalised keys into keyA
-    void* kin = keyA.p; void* kout = keyB.p;
+    void* kin = keep_composite ? bxk.p : keyA.p; void* kout = keyB.p;
     const int32_t* iin = idx_cur;
     for (int p = 0; p < pp.npasses; p++) {
       const bool last = (p == pp.npasses - 1);
@@ -776,6 +837,70 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     }
     DevBuf gacc;
     if (!fused_direct) DTB_TRY(gacc.alloc(sizeof(u64) * (size_t)(ng > 0 ? ng : 1) * 2, s));
+
+    // ---- bucketed multi-reducer: value columns that would cost two or more L2 atomics per row (mean = sum +
+    //      count; several reducers of one column) are partitioned by key bucket once and folded in shared
+    //      memory, all their reducers together (dtb_bucket.cu).  Spread-out keys only: few groups and hot keys
+    //      have their own streaming modes (plan_direct). --------------------------------------------------
+    struct BucketCol { const void* data; int stype; u64* w[BK_NWORDS]; };
+    std::vector<BucketCol> bcols;
+    std::vector<int> bcol_of(fr->n, -1);
+    std::list<DevBuf> bbufs;                                   // accumulator tables (live until the finalizes ran)
+    DevBuf bstart, bscr;
+    if (fused_direct && rs == s && ng > 0 && dp.kind == DIRECT_PLAIN && opt_bucketed &&
+        dbits0 >= BK_MIN_DBITS && dbits0 <= BK_MAX_DBITS) {
+      auto natomics = [](int op) { return op == DTB_OP_MEAN ? 2 : (op >= DTB_OP_SUM && op <= DTB_OP_COUNTNA ? 1 : 0); };
+      for (int i = 0; i < fr->n; i++) {
+        const dtb_reduce_spec& sp = fr->spec[i];
+        if (sp.op == DTB_OP_NROWS || bcol_of[i] >= 0 || !reduce_out_stype_host(sp.op, sp.value.stype)) continue;
+        int cost = 0;
+        for (int j = i; j < fr->n; j++)
+          if (fr->spec[j].op != DTB_OP_NROWS && fr->spec[j].value.data == sp.value.data && fr->spec[j].value.stype == sp.value.stype)
+            cost += natomics(fr->spec[j].op);
+        if (cost < 2) continue;
+        BucketCol bc; bc.data = sp.value.data; bc.stype = sp.value.stype;
+        for (int w = 0; w < BK_NWORDS; w++) bc.w[w] = nullptr;
+        bool want[BK_NWORDS] = {false, false, false, false, false, false};
+        const bool vflt = sp.value.stype == DTB_STYPE_FLOAT32 || sp.value.stype == DTB_STYPE_FLOAT64;
+        for (int j = i; j < fr->n; j++) {
+          const dtb_reduce_spec& sj = fr->spec[j];
+          if (sj.op == DTB_OP_NROWS || sj.value.data != sp.value.data || sj.value.stype != sp.value.stype) continue;
+          bcol_of[j] = (int)bcols.size();
+          switch (sj.op) {
+            case DTB_OP_SUM:  want[vflt ? BK_SUMF : BK_SUMI] = true; break;
+            case DTB_OP_MEAN: want[BK_SUMF] = want[BK_CNT] = true; break;
+            case DTB_OP_MIN:  want[BK_MIN] = true; break;
+            case DTB_OP_MAX:  want[BK_MAX] = true; break;
+            case DTB_OP_COUNT: want[BK_CNT] = true; break;
+            case DTB_OP_COUNTNA: want[BK_CNTNA] = true; break;
+          }
+        }
+        for (int w = 0; w < BK_NWORDS; w++) {
+          if (!want[w]) continue;
+          bbufs.emplace_back();
+          DTB_TRY(bbufs.back().alloc(sizeof(u64) * (size_t)ftable, s));
+          bc.w[w] = bbufs.back().as<u64>();
+          fill_u64(bc.w[w], ftable, w == BK_MIN ? ~0ull : 0ull, s);
+        }
+        bcols.push_back(bc);
+      }
+      if (!bcols.empty()) {
+        const int nb = 1 << (dbits0 > 11 ? dbits0 - 11 : 0);
+        int maxb = 1;
+        for (auto& bc : bcols) maxb = stype_bytes(bc.stype) > maxb ? stype_bytes(bc.stype) : maxb;
+        DTB_TRY(bstart.alloc(sizeof(u32) * (size_t)(512 + nb + 8), s));
+        DTB_TRY(bscr.alloc(bucket_scratch_bytes(n, maxb), s));
+        if (!bxk.p) {                                  // single raw key column: its normalised keys, once
+          DTB_TRY(bxk.alloc(sizeof(u32) * (size_t)n, s));
+          ProfScope ps("compose_keys", s); DTB_TRY(launch_compose_keys(rounds[0].kp, n, nullptr, bxk.p, 4, s));
+        }
+        u32* hist = bstart.as<u32>(); u32* start = hist + 512;
+        DTB_TRY(launch_bucket_starts(bxk.as<u32>(), rounds[0].kp.group_shift, n, nb, hist, start, s));
+        for (auto& bc : bcols)
+          DTB_TRY(launch_bucketed_reduce(bxk.as<u32>(), rounds[0].kp.group_shift, dbits0, bc.data, bc.stype, n, start,
+                                         bc.w, bscr.p, s));
+      }
+    }
     for (int i = 0; i < fr->n; i++) {
       const dtb_reduce_spec& sp = fr->spec[i];
       const int out_st = (sp.op == DTB_OP_NROWS) ? DTB_STYPE_INT64 : reduce_out_stype_host(sp.op, sp.value.stype);
@@ -786,6 +911,19 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       DevBuf ob; DTB_TRY(ob.alloc_owned((size_t)(ng > 0 ? ng : 1) * stype_bytes(out_st), s));
       if (sp.op == DTB_OP_NROWS) {
         DTB_TRY(launch_nrows(offsets, ng, ob.p, s));
+      } else if (bcol_of[i] >= 0) {
+        const BucketCol& bc = bcols[bcol_of[i]];
+        const bool vflt = sp.value.stype == DTB_STYPE_FLOAT32 || sp.value.stype == DTB_STYPE_FLOAT64;
+        const u64* a0 = nullptr; const u64* a1 = nullptr;
+        switch (sp.op) {
+          case DTB_OP_SUM:  a0 = bc.w[vflt ? BK_SUMF : BK_SUMI]; break;
+          case DTB_OP_MEAN: a0 = bc.w[BK_SUMF]; a1 = bc.w[BK_CNT]; break;
+          case DTB_OP_MIN:  a0 = bc.w[BK_MIN]; break;
+          case DTB_OP_MAX:  a0 = bc.w[BK_MAX]; break;
+          case DTB_OP_COUNT: a0 = bc.w[BK_CNT]; break;
+          default: a0 = bc.w[BK_CNTNA]; break;
+        }
+        DTB_TRY(launch_direct_finalize(sp.op, sp.value.stype, a0, a1, res.gkeys.as<u32>(), ng, ob.p, s));
       } else if (fused_direct) {
         u64* a0 = facc.as<u64>() + (size_t)ftable * 2 * i;
         u64* a1 = facc.as<u64>() + (size_t)ftable * (2 * i + 1);
@@ -869,6 +1007,7 @@ int dtb_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "verbose")) { opt_verbose = value; return DTB_OK; }
   if (!strcmp(name, "profile")) { opt_profile = value; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { opt_overlap = value; return DTB_OK; }
+  if (!strcmp(name, "bucketed_reducers")) { opt_bucketed = value ? 1 : 0; return DTB_OK; }
   if (!strcmp(name, "hybrid_sort")) { opt_hybrid = value; return DTB_OK; }
   if (!strcmp(name, "trim_scratch")) {
     if (t_arena.depth == 0 && t_arena.device >= 0) {
@@ -901,6 +1040,7 @@ int dtb_get_option(const char* name, int64_t* value) {
   if (!strcmp(name, "verbose")) { *value = opt_verbose; return DTB_OK; }
   if (!strcmp(name, "profile")) { *value = opt_profile; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { *value = opt_overlap; return DTB_OK; }
+  if (!strcmp(name, "bucketed_reducers")) { *value = opt_bucketed; return DTB_OK; }
   if (!strcmp(name, "hybrid_sort")) { *value = opt_hybrid; return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
@@ -934,6 +1074,7 @@ int dtb_group(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int6
   if (!order_dev && norder > 0) {
     const int32_t* src = res.order.as<int32_t>() + res.nskip;
     DTB_CUDA_CHECK(cudaMemcpyAsync(order_out, src, sizeof(int32_t) * (size_t)norder, cudaMemcpyDefault, s));
+    if (!is_device_ptr(order_out)) DevOut::remember(order_out, src, sizeof(int32_t) * (size_t)norder, s);
   }
   if (res.ngroups >= 0 && !offsets_dev) {
     if (offsets_cap < res.ngroups + 1) {
@@ -942,6 +1083,7 @@ int dtb_group(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int6
       return DTB_ENOSPACE;
     }
     DTB_CUDA_CHECK(cudaMemcpyAsync(offsets_out, res.offsets.p, sizeof(int32_t) * (size_t)(res.ngroups + 1), cudaMemcpyDefault, s));
+    if (!is_device_ptr(offsets_out)) DevOut::remember(offsets_out, res.offsets.p, sizeof(int32_t) * (size_t)(res.ngroups + 1), s);
   }
   DTB_CUDA_CHECK(cudaStreamSynchronize(s));
   return DTB_OK;
@@ -1330,6 +1472,16 @@ int dtb_join(const dtb_col* xkeys, const dtb_col* jkeys, int nkeys, int64_t nrow
   DevOut d_out; DTB_TRY(d_out.bind(index_out, (size_t)nrows_x * 4, s));
   DTB_TRY(launch_join(nkeys, xp, xst, jp, jst, nrows_x, nrows_j, (int32_t*)d_out.dptr, s));
   if (d_out.staged()) { DTB_TRY(d_out.finish((size_t)nrows_x * 4, s)); DTB_CUDA_CHECK(cudaStreamSynchronize(s)); }
+  return DTB_OK;
+}
+
+int dtb_cache_begin(void) {
+  t_cache.depth++;
+  return DTB_OK;
+}
+
+int dtb_cache_end(void) {
+  if (t_cache.depth > 0 && --t_cache.depth == 0) { cudaDeviceSynchronize(); t_cache.clear(); }
   return DTB_OK;
 }
 

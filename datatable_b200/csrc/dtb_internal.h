@@ -184,6 +184,17 @@ int launch_nrows(const int32_t* offsets, int64_t ngroups, void* out, cudaStream_
 int launch_group_keys(const void* sorted_keys, int key_bytes, const int32_t* offsets, int group_shift,
                       int64_t ngroups, uint32_t* gkeys, cudaStream_t s);
 
+// Bucketed multi-reducer (dtb_bucket.cu): all reducers of one value column in one sweep over rows partitioned
+// by group-key bucket, shared-memory accumulators.  Words a column can ask for:
+enum { BK_SUMI = 0, BK_SUMF = 1, BK_CNT = 2, BK_MIN = 3, BK_MAX = 4, BK_CNTNA = 5, BK_NWORDS = 6 };
+constexpr int BK_MAX_DBITS = 20, BK_MIN_DBITS = 12;
+// rows per bucket of the group keys xkeys[i] >> gshift: hist[512] scratch, start[nb+1]
+int launch_bucket_starts(const uint32_t* xkeys, int gshift, int64_t n, int nb, uint32_t* hist, uint32_t* start, cudaStream_t s);
+size_t bucket_scratch_bytes(int64_t n, int value_bytes);
+int launch_bucketed_reduce(const uint32_t* xkeys, int gshift, int dbits, const void* value, int stype, int64_t n,
+                           const uint32_t* start, unsigned long long* const* acc_w, void* scratch, cudaStream_t s);
+void fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t s);
+
 int launch_gather(const void* src, int stype, int64_t nrows_src, const void* order,
                   int order_is64, int64_t n, void* out, cudaStream_t s);
 

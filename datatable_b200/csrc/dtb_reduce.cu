@@ -194,6 +194,13 @@ __global__ void fill_u64_kernel(u64* p, int64_t n, u64 v) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
 }
 
+void fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t s) {
+  if (n <= 0) return;
+  const int g = (int)((n + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (n + 255) / 256);
+  fill_u64_kernel<<<g, 256, 0, s>>>(p, n, v);
+  count_launch();
+}
+
 __global__ void nrows_kernel(const int32_t* __restrict__ offsets, int64_t ng, int64_t* out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += stride)

@@ -271,6 +271,19 @@ DTB_API int dtb_dense_scatter(const void* keys, int key_stype, const void* vals,
 DTB_API int dtb_dense_compact(const void* table, const void* present, int64_t table_size, int64_t kmin,
                       int key_stype, void* out_keys, void* out_vals, int64_t* ngroups_out, dtb_stream stream);
 
+/*
+ * Residency bracket for HOST buffers: between dtb_cache_begin() and the matching dtb_cache_end() (calls
+ * nest; per thread) a host input staged into HBM by any entry point stays there and is reused by later
+ * calls that pass the same (pointer, size); the RowIndex / offsets that dtb_group copied to host memory
+ * are remembered too, so dtb_reduce / dtb_gather on them upload nothing.  The reference-side hook puts
+ * the bracket around EvalContext::evaluate(): one upload per column per query, where the
+ * reference's Buffers are host memory (buffer.cc:261-300).  The caller promises that the bracketed host
+ * buffers do not change; dtb_cache_end() releases the copies.  dtb_last_call_stats().cache_hits counts the
+ * cache hits of the last call.
+ */
+DTB_API int dtb_cache_begin(void);
+DTB_API int dtb_cache_end(void);
+
 /* Copies nbytes between any two host/device buffers on `stream`
  * (cudaMemcpyDefault) and waits for completion.  Lets a binding read the
  * HBM-resident results of a dtb_groupby without linking the CUDA runtime. */
@@ -305,7 +318,7 @@ typedef struct dtb_call_stats {
   int32_t kernels_launched;
   int32_t radix_passes;
   int32_t key_bits;
-  int32_t reserved;
+  int32_t cache_hits;        /* host inputs served from the dtb_cache_begin/end residency cache */
   int64_t scratch_bytes;
 } dtb_call_stats;
 DTB_API int dtb_last_call_stats(dtb_call_stats* out);

@@ -17,6 +17,11 @@ What it adds:
     sort.cc): sum/mean/min/max/count/countna of a plain numeric column of the frame go through
     `dtb_reduce` with the frame's RowIndex and the Groupby offsets, the result wrapped as a material
     column of the reference's output stype.  Anything else keeps the reference's own reducer columns.
+  * src/core/column/view.{h,cc} -- `ArrayView_ColumnImpl<T>::materialize` override: with `sort.b200` on, a
+    view of a material bool/int/float column through an ARR32/ARR64 RowIndex is gathered by `dtb_gather`
+    (the generic path is a per-element virtual get_element loop, column_impl.cc:78-103).
+  * src/core/expr/eval_context.cc -- a residency bracket (dtb_cache_begin/end) around EvalContext::evaluate():
+    host columns staged by group() / the reducers / the gathers of one query are uploaded once.
   * ci/ext.py         -- include path of include/dtb200.h, link + rpath of datatable_b200/lib/libdtb200.so.
 /root/reference itself is never touched.
 """
@@ -30,6 +35,7 @@ INCLUDE_ADD = '#include <dtb200.h>      // B200 engine C-ABI (drop-in for group(
 
 OPTION_ANCHOR = 'static bool sort_new = false;\n'
 OPTION_ADD = ('static bool sort_b200 = false;   // option sort.b200: route group() through libdtb200\n'
+              'bool dtb200_enabled() { return sort_b200; }\n'
               'static bool sort_b200_reducers = false;   // option sort.b200_reducers: reducers through dtb_reduce\n'
               'bool dtb200_reducers_enabled() { return sort_b200_reducers; }\n')
 
@@ -166,6 +172,54 @@ RED_LOOP_ADD = '''    {
     }
 '''
 
+# ---- ArrayView gather: src/core/column/view.{h,cc} --------------------------------------------------------
+VIEW_H_ANCHOR = '    // defined in sort.cc\n    void sort_grouped(const Groupby& gby, Column& out) override;\n'
+VIEW_H_ADD = '    void materialize(Column& out, bool to_memory) override;   // dtb200: gather on the engine\n'
+
+VIEW_CC_INCLUDE_ANCHOR = '#include "column/view.h"\n'
+VIEW_CC_INCLUDE_ADD = '''#include "stype.h"
+#include <dtb200.h>      // B200 engine C-ABI (RowIndex gather)
+bool dtb200_enabled();   // sort.cc, option sort.b200
+'''
+
+VIEW_CC_ANCHOR = 'template class ArrayView_ColumnImpl<int32_t>;\n'
+VIEW_CC_ADD = '''// dtb200: out[i] = indices[i] < 0 ? NA : arg[indices[i]] as one dtb_gather instead of the generic
+// per-element virtual loop (column_impl.cc:78-103).  Anything the engine does not cover keeps that loop.
+template <typename T>
+void ArrayView_ColumnImpl<T>::materialize(Column& out, bool to_memory) {
+  bool eligible = dtb200_enabled() && !arg.is_virtual() && nrows_ > 0;
+  if (eligible) {
+    switch (arg.stype()) {
+      case SType::BOOL: case SType::INT8: case SType::INT16: case SType::INT32: case SType::INT64:
+      case SType::FLOAT32: case SType::FLOAT64: case SType::DATE32: case SType::TIME64: break;
+      default: eligible = false;
+    }
+  }
+  if (eligible) {
+    const int st = static_cast<int>(arg.stype());               // SType values == DtStype_* codes
+    Buffer buf = Buffer::mem(nrows_ * static_cast<size_t>(dtb_stype_size(st)));
+    dtb_col src; src.data = arg.get_data_readonly(); src.stype = st; src.reserved = 0;
+    int rc = dtb_gather(src, static_cast<int64_t>(arg.nrows()), indices, sizeof(T) == 8,
+                        static_cast<int64_t>(nrows_), nullptr, buf.xptr());
+    if (rc == DTB_OK) {
+      out = Column::new_mbuf_column(nrows_, arg.stype(), std::move(buf));
+      return;
+    }
+    if (rc != DTB_ENOTIMPL) throw RuntimeError() << "dtb200: " << dtb_last_error();
+  }
+  ColumnImpl::materialize(out, to_memory);
+}
+
+'''
+
+# ---- residency bracket: src/core/expr/eval_context.cc ---------------------------------------------------
+EVAL_INCLUDE_ANCHOR = '#include "expr/eval_context.h"\n'
+EVAL_INCLUDE_ADD = '''#include <dtb200.h>      // B200 engine C-ABI (residency bracket)
+namespace { struct Dtb200CacheScope { Dtb200CacheScope() { dtb_cache_begin(); } ~Dtb200CacheScope() { dtb_cache_end(); } }; }
+'''
+EVAL_ANCHOR = 'py::oobj EvalContext::evaluate() {\n'
+EVAL_ADD = '  Dtb200CacheScope dtb200_cache_scope;   // host columns staged by the engine stay in HBM for this query\n'
+
 EXT_ANCHOR = '            ext.compiler.add_linker_flag("-lstdc++")\n'
 EXT_ADD = '''            # dtb200: B200 engine C-ABI
             ext.compiler.add_compiler_flag("-I{inc}")
@@ -204,6 +258,20 @@ def main():
     r = insert(r, RED_HELPER_ANCHOR, RED_HELPER_ADD, before=True, what="reducer helper")
     r = insert(r, RED_LOOP_ANCHOR, RED_LOOP_ADD, before=True, what="reducer loop hook")
     open(red_cc, "w").write(r)
+    view_h = os.path.join(tree, "src", "core", "column", "view.h")
+    h = open(view_h).read()
+    h = insert(h, VIEW_H_ANCHOR, VIEW_H_ADD, before=False, what="ArrayView materialize declaration")
+    open(view_h, "w").write(h)
+    view_cc = os.path.join(tree, "src", "core", "column", "view.cc")
+    v = open(view_cc).read()
+    v = insert(v, VIEW_CC_INCLUDE_ANCHOR, VIEW_CC_INCLUDE_ADD, before=False, what="view.cc includes")
+    v = insert(v, VIEW_CC_ANCHOR, VIEW_CC_ADD, before=True, what="ArrayView materialize")
+    open(view_cc, "w").write(v)
+    eval_cc = os.path.join(tree, "src", "core", "expr", "eval_context.cc")
+    ev = open(eval_cc).read()
+    ev = insert(ev, EVAL_INCLUDE_ANCHOR, EVAL_INCLUDE_ADD, before=False, what="eval_context includes")
+    ev = insert(ev, EVAL_ANCHOR, EVAL_ADD, before=False, what="residency bracket")
+    open(eval_cc, "w").write(ev)
     ext_py = os.path.join(tree, "ci", "ext.py")
     e = open(ext_py).read()
     add = EXT_ADD.format(inc=os.path.join(ROOT, "include"), lib=os.path.join(ROOT, "datatable_b200", "lib"))

@@ -12,3 +12,4 @@ cp -r "$SCRATCH/src/datatable" "$HERE/_ref_patched/"
 find "$HERE/_ref_patched" -name __pycache__ -type d -prune -exec rm -rf {} +
 strip -g "$HERE"/_ref_patched/datatable/lib/_datatable*.so
 PYTHONPATH="$HERE/_ref_patched" python "$HERE/check_hook.py"
+PYTHONPATH="$HERE/_ref_patched" python "$HERE/check_hook_views.py"

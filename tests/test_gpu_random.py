@@ -394,3 +394,36 @@ def test_hybrid_wide_key_sort_paths():
         engine.set_option("hybrid_sort", 0)
     got = engine.group([a], [SORT_ONLY], 1)[0]
     assert np.array_equal(got, orc.group([a], [SORT_ONLY], 1)[0])
+
+
+def test_bucketed_multi_reducer_vs_oracle_and_plain():
+    """Several reducers of one value column over a 2^12..2^20 key domain take the bucketed multi-reducer
+    (dtb_bucket.cu): every value stype x every op against the oracle, and against the one-atomic-per-row path."""
+    import torch
+    from datatable_b200 import engine, _lib
+    from oracle import oracle as orc
+    rng = np.random.default_rng(991)
+    n = 1_500_000
+    k = rng.integers(0, 50_000, n).astype(np.int32)
+    k[rng.random(n) < 0.01] = -2**31
+    want_o, want_f, want_ng = orc.group([k], [0], orc.NA_FIRST)
+    kd = torch.from_numpy(k).cuda()
+    ops = [("sum", _lib.OP_SUM, orc.SUM), ("mean", _lib.OP_MEAN, orc.MEAN), ("min", _lib.OP_MIN, orc.MIN),
+           ("max", _lib.OP_MAX, orc.MAX), ("count", _lib.OP_COUNT, orc.COUNT), ("countna", _lib.OP_COUNTNA, orc.COUNTNA)]
+    for vst in (BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64):
+        v = make_col(rng, vst, n, "few" if vst == BOOL else "unit", 0.1)
+        vd = engine.Col(torch.from_numpy(v).cuda(), vst)
+        results = {}
+        for bucketed in (1, 0):
+            engine.set_option("bucketed_reducers", bucketed)
+            try:
+                gb = engine.Groupby([kd], [0], _lib.NA_FIRST, reducers=[(op, vd) for _, op, _ in ops])
+                assert gb.ngroups == want_ng
+                results[bucketed] = [gb.reduced(i).cpu().numpy() for i in range(len(ops))]
+                gb.close()
+            finally:
+                engine.set_option("bucketed_reducers", 1)
+        for i, (name, _, oop) in enumerate(ops):
+            want = orc.reduce(oop, v, want_o, want_f, stype=vst)
+            assert_reducer_equal(results[1][i], want, name, vst, f"bucketed {name} vst={vst}")
+            assert_reducer_equal(results[0][i], want, name, vst, f"plain {name} vst={vst}")

@@ -34,3 +34,9 @@ def test_patched_reference_reducers_match_its_own_cpu_path():
     group() and with sort.b200 on (the whole DT[:, reducers, by(k)] on the engine)"""
     out = _run("check_hook_reducers.py")
     assert out.count("engine == CPU for 12 reducers") == 2, out
+
+
+def test_patched_reference_views_and_residency():
+    """ArrayView_ColumnImpl::materialize through dtb_gather; the residency bracket around evaluate()"""
+    out = _run("check_hook_views.py")
+    assert "view columns on the engine == CPU path: ok" in out and "residency bracket): ok" in out, out
