@@ -309,6 +309,51 @@ def other_configs(torch, engine, _lib, n, peak):
     return out
 
 
+def c5_record(torch, dist, engine, _lib, ddist, rank, world, steps=3):
+    """BASELINE config C5 shape at N > 1: int64 keys (1e8 distinct), float64 values, 1.25e9 rows per GPU (1e10 rows
+    at N = 8), groupby-sum with the rows left where they are: local group + reduce, then the per-group partials
+    (key, sum) are range-partitioned over the ranks with one NCCL all-to-all and merged.  Returns the record (rank 0)."""
+    rows, G = 1_250_000_000, 100_000_000
+    gen = torch.Generator(device="cuda"); gen.manual_seed(7 + rank)
+    k = torch.randint(0, G, (rows,), generator=gen, device="cuda", dtype=torch.int64)
+    v = torch.rand(rows, generator=gen, device="cuda", dtype=torch.float64)
+
+    def step():
+        gb = engine.Groupby([k], [0], _lib.NA_FIRST, reducers=[(_lib.OP_SUM, v)])
+        part = gb.reduced(0)
+        gkeys = engine.gather(k, gb.first_rows())
+        gb.close()
+        return ddist.merge_partials_alltoall(gkeys, part, _lib.OP_SUM)
+    step()
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a2a_ms = []
+    e0.record()
+    for _ in range(steps):
+        mk, mv = step()
+        a2a_ms.append(ddist.LAST_EXCHANGE_EVENTS)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    x_ms = sum(a.elapsed_time(b) for a, b in a2a_ms) / steps
+    t = torch.tensor([ms, x_ms, float(ddist.LAST_EXCHANGE_BYTES), float(mv.sum()), float(v.sum()), float(mk.numel())],
+                     dtype=torch.float64, device="cuda")
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    ms, x_ms, bytes_max = float(tmax[0]), float(tmax[1]), float(tmax[2])
+    ok = abs(float(tsum[3]) - float(tsum[4])) <= 1e-6 * abs(float(tsum[4]))
+    del k, v
+    torch.cuda.empty_cache()
+    return {"workload": "C5 shape: int64 key (1e8 distinct), float64 value, groupby-sum over a row-partitioned frame; "
+                        "local group+reduce, NCCL all-to-all of the (key, partial) lists by key range, merge",
+            "rows_per_gpu": rows, "rows_total": rows * world, "ms_per_step": ms, "rows_per_s": rows * world / ms * 1e3,
+            "groups_total": int(float(tsum[5])),
+            "alltoall": {"bytes_sent_per_rank": bytes_max, "ms": x_ms,
+                         "GBps_per_direction": bytes_max / (x_ms / 1e3) / 1e9 if x_ms > 0 else None,
+                         "nvlink5_peak_GBps_per_direction": 900.0},
+            "check_sums_add_up": bool(ok), "steps": steps}
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -519,6 +564,18 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.empty_cache()
         engine.set_option("trim_scratch", 1)
         line["other_configs"] = other_configs(torch, engine, _lib, n, peak)
+    # ---- C5 shape (N > 1 only): 1.25e9 int64-key rows per GPU, all-to-all of the partials ---------------
+    if world > 1 and not args.no_extra:
+        del k, v
+        torch.cuda.empty_cache()
+        engine.set_option("trim_scratch", 1)
+        try:
+            c5 = c5_record(torch, dist, engine, _lib, ddist, rank, world)
+        except Exception as e:                              # pragma: no cover
+            c5 = {"error": str(e)[:300]}
+        if rank == 0:
+            line["other_configs"] = {"C5": c5}
+
     # ---- the drop-in number: the PATCHED reference's own query with the engine options off / on -----
     patched = os.path.join(ROOT, "integration", "_ref_patched")
     if rank == 0 and world == 1 and not args.no_extra and os.path.exists(os.path.join(patched, "datatable", "__init__.py")):

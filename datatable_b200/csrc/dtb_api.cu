@@ -431,8 +431,11 @@ static void plan_passes(int total_bits, int width, PassPlan& pp) {
 static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t n,
                       cudaStream_t s, int32_t* order_dev /*optional caller buffer*/,
                       int32_t* offsets_dev /*optional caller buffer, n+1*/, GroupResult& res,
-                      bool want_direct = false, FusedReducers* fr = nullptr)
+                      bool want_direct = false, FusedReducers* fr = nullptr, bool wide = false)
 {
+  // wide == dtb_group64: up to 2^32 - 1 rows.  The passes carry row ids and output slots as 32-bit words
+  // whose arithmetic is unsigned throughout, so ids >= 2^31 are just bit patterns in the int32 buffers;
+  // the caller zero-extends order / offsets to int64 (ARR64, rowindex_array.cc:50-60).
   // want_direct == the handle path: the RowIndex outlives the call and must be an owned allocation
   t_stats = dtb_call_stats{0, 0, 0, 0, 0};
   const double tl0 = now_ms();
@@ -447,7 +450,9 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     }
     if (n > 0 && !keys[c].data) { set_error("key column data is NULL"); return DTB_EINVAL; }
   }
-  if (n > (int64_t)INT32_MAX) { set_error("nrows > INT32_MAX needs an ARR64 RowIndex: not implemented"); return DTB_ENOTIMPL; }
+  if (n > (int64_t)INT32_MAX && !wide) { set_error("nrows > INT32_MAX needs an ARR64 RowIndex: use dtb_group64"); return DTB_ENOTIMPL; }
+  if (n > (int64_t)0xFFFFFFFFll - 65536) { set_error("nrows >= 2^32 is beyond one GPU's passes (32-bit output slots): partition the frame"); return DTB_ENOTIMPL; }
+  if (wide && (want_direct || fr)) { set_error("internal: the ARR64 path has no fused reducers"); return DTB_EINVAL; }
   DTB_TRY(ensure_context());
 
   const bool do_groups = !(flags[0] & DTB_FLAG_SORT_ONLY);
@@ -1482,6 +1487,60 @@ int dtb_cache_begin(void) {
 
 int dtb_cache_end(void) {
   if (t_cache.depth > 0 && --t_cache.depth == 0) { cudaDeviceSynchronize(); t_cache.clear(); }
+  return DTB_OK;
+}
+
+int dtb_group64(const dtb_col* keys, int nkeys, const int* flags, int na_pos, int64_t nrows, dtb_stream stream,
+                void* order_out, void* offsets_out, int64_t offsets_cap, int64_t* ngroups_out, int64_t* norder_out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  if (!order_out && nrows > 0) { set_error("order_out is NULL"); return DTB_EINVAL; }
+  if (nkeys >= 1 && flags && !(flags[0] & DTB_FLAG_SORT_ONLY) && !offsets_out) {
+    set_error("offsets_out is NULL but groups were requested"); return DTB_EINVAL;
+  }
+  GroupResult res;
+  int rc = group_core(keys, nkeys, flags, na_pos, nrows, s, nullptr, nullptr, res, false, nullptr, /*wide=*/true);
+  if (rc != DTB_OK) return rc;
+  const int64_t norder = res.n - res.nskip;
+  if (norder_out) *norder_out = norder;
+  if (ngroups_out) *ngroups_out = res.ngroups;
+  // zero-extend the 32-bit row ids / offsets to the int64 layout of an ARR64 RowIndex and int64 offsets
+  if (norder > 0) {
+    DevOut d_ord; DTB_TRY(d_ord.bind(order_out, sizeof(int64_t) * (size_t)norder, s));
+    DTB_TRY(launch_widen_u32((const uint32_t*)res.order.p + res.nskip, norder, (int64_t*)d_ord.dptr, s));
+    if (d_ord.staged()) DTB_TRY(d_ord.finish(sizeof(int64_t) * (size_t)norder, s));
+  }
+  if (res.ngroups >= 0) {
+    if (offsets_cap < res.ngroups + 1) {
+      cudaStreamSynchronize(s);
+      set_error("offsets_out holds " + std::to_string(offsets_cap) + " entries, need " + std::to_string(res.ngroups + 1));
+      return DTB_ENOSPACE;
+    }
+    DevOut d_off; DTB_TRY(d_off.bind(offsets_out, sizeof(int64_t) * (size_t)(res.ngroups + 1), s));
+    DTB_TRY(launch_widen_u32((const uint32_t*)res.offsets.p, res.ngroups + 1, (int64_t*)d_off.dptr, s));
+    if (d_off.staged()) DTB_TRY(d_off.finish(sizeof(int64_t) * (size_t)(res.ngroups + 1), s));
+  }
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return DTB_OK;
+}
+
+int dtb_lower_bound(dtb_col sorted, int64_t nrows, dtb_col values, int64_t nvalues, dtb_stream stream, void* out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  if (sorted.stype != values.stype || !stype_supported(sorted.stype)) { set_error("lower_bound: columns must share a supported stype"); return DTB_EINVAL; }
+  if (nrows < 0 || nvalues < 0 || (nvalues > 0 && (!values.data || !out))) { set_error("bad dtb_lower_bound arguments"); return DTB_EINVAL; }
+  DTB_TRY(ensure_context());
+  if (nvalues == 0) return DTB_OK;
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  const int esz = stype_bytes(sorted.stype);
+  DevIn d_s, d_v;
+  DTB_TRY(d_s.bind(sorted.data, (size_t)nrows * esz, s));
+  DTB_TRY(d_v.bind(values.data, (size_t)nvalues * esz, s));
+  DevOut d_out; DTB_TRY(d_out.bind(out, (size_t)nvalues * 8, s));
+  DTB_TRY(launch_lower_bound(d_s.dptr, sorted.stype, nrows, d_v.dptr, nvalues, (int64_t*)d_out.dptr, s));
+  if (d_out.staged()) { DTB_TRY(d_out.finish((size_t)nvalues * 8, s)); DTB_CUDA_CHECK(cudaStreamSynchronize(s)); }
   return DTB_OK;
 }
 

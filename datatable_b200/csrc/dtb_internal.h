@@ -199,6 +199,7 @@ int launch_gather(const void* src, int stype, int64_t nrows_src, const void* ord
                   int order_is64, int64_t n, void* out, cudaStream_t s);
 
 int launch_iota32(int32_t* out, int64_t n, cudaStream_t s);
+int launch_widen_u32(const uint32_t* in, int64_t n, int64_t* out, cudaStream_t s);   // ARR32 bit patterns -> ARR64
 
 // ---------------------------------------------------------------------------
 // SURVEY.md 8(f) rows (dtb_next.cu): ordered reducers, set operations, mode, join
@@ -218,6 +219,7 @@ int launch_set_select(const int32_t* order, const int32_t* offsets, int64_t ng, 
 int launch_set_emit(const int32_t* pos, int64_t nsel, const int32_t* order, const int32_t* offsets, int32_t* out_rows,
                     cudaStream_t s);
 int launch_largest_group(const int32_t* offsets, int64_t ng, int64_t skip, unsigned long long* d_result, cudaStream_t s);
+int launch_lower_bound(const void* sorted, int stype, int64_t n, const void* values, int64_t m, int64_t* out, cudaStream_t s);
 int launch_join(int nkeys, const void* const* xcols, const int* xst, const void* const* jcols, const int* jst,
                 int64_t nx, int64_t nj, int32_t* out, cudaStream_t s);
 

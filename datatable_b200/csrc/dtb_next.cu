@@ -466,4 +466,32 @@ int launch_join(int nkeys, const void* const* xcols, const int* xst, const void*
   return DTB_OK;
 }
 
+// ===========================================================================
+// lower bound: out[i] = number of rows of the ascending column `sorted` that are < values[i]
+// (the cut points of a key-range exchange between GPUs, datatable_b200/dist.py)
+// ===========================================================================
+template <typename T>
+__global__ void lower_bound_kernel(const T* __restrict__ sorted, int64_t n, const T* __restrict__ values, int64_t m,
+                                   int64_t* __restrict__ out)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const T x = values[i];
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted[mid] < x) lo = mid + 1; else hi = mid; }
+  out[i] = lo;
+}
+
+int launch_lower_bound(const void* sorted, int stype, int64_t n, const void* values, int64_t m, int64_t* out, cudaStream_t s)
+{
+  if (m == 0) return DTB_OK;
+  const int grid = grid_for(m);
+#define CALL(T) lower_bound_kernel<T><<<grid, 256, 0, s>>>((const T*)sorted, n, (const T*)values, m, out)
+  DTB_DISPATCH_STYPE(stype, CALL)
+#undef CALL
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
 }  // namespace dtb

@@ -39,7 +39,7 @@ compose_keys_kernel(KeyPlan kp, int64_t n, const int32_t* __restrict__ idx, KeyT
 {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t row = idx ? (int64_t)idx[i] : i;     // later rounds see the rows in the current order
+    const int64_t row = idx ? (int64_t)(u32)idx[i] : i;     // later rounds see the rows in the current order (ids are 32-bit patterns)
     u64 x = 0;
     for (int c = 0; c < kp.nkeys; c++)
       x |= norm_load_dynamic(kp.k[c], row) << kp.k[c].lshift;
@@ -614,6 +614,21 @@ int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_
   }
   return key_bytes == 4 ? run_pass_raw<u32>(io, kp, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift)
                         : run_pass_raw<u64>(io, kp, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift);
+}
+
+__global__ void widen_u32_kernel(const u32* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int64_t)in[i];
+}
+
+int launch_widen_u32(const uint32_t* in, int64_t n, int64_t* out, cudaStream_t s) {
+  if (n == 0) return DTB_OK;
+  int64_t want = (n + 255) / 256;
+  int grid = (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : want);
+  widen_u32_kernel<<<grid, 256, 0, s>>>(in, n, out);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
 }
 
 __global__ void iota32_kernel(int32_t* out, int64_t n) {

@@ -155,8 +155,17 @@ def groupby_partitioned(k, v, op=_lib.OP_SUM, group=None, exchange="allgather"):
 # ---------------------------------------------------------------------------
 # key-range all-to-all
 # ---------------------------------------------------------------------------
+def _lower_bound(sorted_keys, values):
+    """Rows of the ascending tensor `sorted_keys` below each value: the engine's own kernel (dtb_lower_bound)."""
+    out = torch.empty(values.numel(), dtype=torch.int64, device=sorted_keys.device)
+    s, v = engine.Col(sorted_keys), engine.Col(values.to(sorted_keys.dtype).contiguous())
+    _lib.check(_lib.lib.dtb_lower_bound(s.c(), s.nrows, v.c(), v.nrows, engine._stream(), ctypes.c_void_p(out.data_ptr())))
+    return out
+
+
 def _splitters(sorted_keys, world, group=None):
-    """world-1 global splitters from evenly spaced samples of every rank's sorted keys."""
+    """world-1 global splitters from evenly spaced samples of every rank's sorted keys.  The <= 4*world^2
+    samples are gathered and ordered on the host (plumbing, a few hundred values)."""
     n = sorted_keys.numel()
     nsamp = 4 * world
     if n > 0:
@@ -169,19 +178,25 @@ def _splitters(sorted_keys, world, group=None):
     allhave = torch.empty(world, dtype=torch.int64, device=sorted_keys.device)
     dist.all_gather_into_tensor(allsamp, samp, group=group)
     dist.all_gather_into_tensor(allhave, have, group=group)
-    keep = allhave.repeat_interleave(nsamp).bool()
-    pool = torch.sort(allsamp[keep]).values                  # <= 4*world^2 values: plumbing, not the hot path
-    if pool.numel() == 0:
+    samp_h, have_h = allsamp.cpu().numpy(), allhave.cpu().numpy()
+    pool = sorted(samp_h.reshape(world, nsamp)[have_h.astype(bool)].reshape(-1).tolist())
+    if not pool:
         return torch.zeros(world - 1, dtype=sorted_keys.dtype, device=sorted_keys.device)
-    q = (torch.arange(1, world, device=pool.device) * pool.numel()) // world
-    return pool[q]
+    spl = [pool[(r * len(pool)) // world] for r in range(1, world)]
+    return torch.tensor(spl, dtype=sorted_keys.dtype, device=sorted_keys.device)
 
 
-def _exchange(sorted_keys, payloads, world, group=None):
+LAST_EXCHANGE_BYTES = 0        # bytes this rank sent in the last all-to-all (bench.py reports NVLink GB/s)
+LAST_EXCHANGE_EVENTS = None    # (start, end) CUDA events around the payload all-to-alls of the last exchange
+
+
+def _exchange(sorted_keys, payloads, world, group=None, kernels=None):
     """Cut the locally sorted run at the global splitters and all-to-all the pieces.
     Returns (received keys, received payloads): source-rank-major, each piece still sorted."""
+    global LAST_EXCHANGE_BYTES, LAST_EXCHANGE_EVENTS
     spl = _splitters(sorted_keys, world, group)
-    cuts = torch.searchsorted(sorted_keys, spl, right=False)      # rows with key < splitter go left
+    lb = getattr(kernels, "lower_bound", None) or _lower_bound
+    cuts = lb(sorted_keys, spl)                                   # rows with key < splitter go left
     bounds = torch.cat([torch.zeros(1, dtype=cuts.dtype, device=cuts.device), cuts,
                         torch.tensor([sorted_keys.numel()], dtype=cuts.dtype, device=cuts.device)])
     send = (bounds[1:] - bounds[:-1]).to(torch.int64)
@@ -189,12 +204,22 @@ def _exchange(sorted_keys, payloads, world, group=None):
     dist.all_to_all_single(recv, send, group=group)
     send_l, recv_l = send.tolist(), recv.tolist()
     nrecv = sum(recv_l)
+    rank = dist.get_rank(group)
+    LAST_EXCHANGE_BYTES = (sum(send_l) - send_l[rank]) * (sorted_keys.element_size() + sum(p.element_size() for p in payloads))
 
     def a2a(x):
         out = torch.empty(nrecv, dtype=x.dtype, device=x.device)
         dist.all_to_all_single(out, x.contiguous(), output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
         return out
-    return a2a(sorted_keys), [a2a(p) for p in payloads]
+    timed = sorted_keys.is_cuda
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    out = a2a(sorted_keys), [a2a(p) for p in payloads]
+    if timed:
+        e1.record()
+        LAST_EXCHANGE_EVENTS = (e0, e1)
+    return out
 
 
 def merge_partials_alltoall(gkeys, part, op, group=None, kernels=_EngineKernels):
@@ -203,7 +228,7 @@ def merge_partials_alltoall(gkeys, part, op, group=None, kernels=_EngineKernels)
     world = dist.get_world_size(group)
     if world == 1:
         return gkeys, part
-    rk, (rp,) = _exchange(gkeys, [part], world, group)
+    rk, (rp,) = _exchange(gkeys, [part], world, group, kernels)
     if rk.numel() == 0:
         return rk, rp
     order, offsets, ng = kernels.group(rk)
@@ -225,7 +250,7 @@ def sort_partitioned(k, row_offset, group=None, kernels=_EngineKernels):
     ids = order.to(torch.int64) + int(row_offset)
     if world == 1:
         return ks, ids
-    rk, (rid,) = _exchange(ks, [ids], world, group)
+    rk, (rid,) = _exchange(ks, [ids], world, group, kernels)
     if rk.numel() == 0:
         return rk, rid
     order2 = kernels.sort(rk)

@@ -125,6 +125,33 @@ def group(cols, flags=None, na_pos=NA_FIRST):
     return order, offs[:ng.value + 1], ng.value
 
 
+def group64(cols, flags=None, na_pos=NA_FIRST):
+    """group() with the ARR64 layout (dtb_group64): int64 RowIndex and int64 Groupby offsets; for frames of
+    more than INT32_MAX rows (up to 2^32 on one GPU) or callers that want 64-bit indices."""
+    cols = [Col(c) for c in cols]
+    nk = len(cols)
+    n = cols[0].nrows
+    flags = list(flags) if flags is not None else [0] * nk
+    device = all(c.on_device for c in cols)
+    do_groups = not (flags[0] & FLAG_SORT_ONLY)
+    ckeys = (dtb_col * nk)(*[c.c() for c in cols])
+    cflags = (ctypes.c_int * nk)(*flags)
+    order, optr = _alloc(n, INT64, device)
+    ng = ctypes.c_int64(-1)
+    no = ctypes.c_int64(0)
+    if do_groups:
+        # the number of groups is not known in advance: a first sizing pass is avoided by allocating n + 1
+        offs, fptr = _alloc(n + 1, INT64, device)
+    else:
+        offs, fptr = None, 0
+    check(lib.dtb_group64(ckeys, nk, cflags, na_pos, n, _stream(), ctypes.c_void_p(optr),
+                          ctypes.c_void_p(fptr), n + 1 if do_groups else 0, ctypes.byref(ng), ctypes.byref(no)))
+    order = order[:no.value]
+    if ng.value < 0:
+        return order, None, None
+    return order, offs[:ng.value + 1], ng.value
+
+
 class Groupby:
     """Device-resident result of group(): owns the RowIndex and the Groupby offsets in HBM
     (dtb_groupby handle).  Mirrors the pair the reference keeps in EvalContext

@@ -126,7 +126,7 @@ DTB_API int dtb_init(int device);
  *   keys[nkeys], flags[nkeys] : key columns (by-columns first) and their
  *                               SortFlag bits
  *   na_pos                    : DTB_NA_*
- *   nrows                     : rows per column (<= INT32_MAX)
+ *   nrows                     : rows per column (<= INT32_MAX; more: dtb_group64)
  *   order_out                 : int32[nrows]  -- the ARR32 RowIndex payload
  *                               (sort.cc:598-608); with DTB_NA_REMOVE only the
  *                               first *norder_out entries are written
@@ -141,6 +141,19 @@ DTB_API int dtb_init(int device);
  * Bit-exact with the reference for order and offsets.
  */
 DTB_API int dtb_group(const dtb_col* keys, int nkeys, const int* flags, int na_pos,
+              int64_t nrows, dtb_stream stream,
+              void* order_out, void* offsets_out, int64_t offsets_cap,
+              int64_t* ngroups_out, int64_t* norder_out);
+
+/*
+ * dtb_group64 -- dtb_group with the ARR64 layout: order_out is int64[nrows] (RowIndex ARR64,
+ * rowindex_array.cc:50-60; the reference's new sorter emits it above INT32_MAX rows, sort/sorter.cc:74-81)
+ * and offsets_out is int64[offsets_cap] (the reference's Groupby is int32-only, sort.h:119-124 "TODO: Add
+ * support for 64-bit groups" -- this is the variant SURVEY.md 8b asks for).  nrows < 2^32 - 65536 on one
+ * GPU (beyond that the frame is row-partitioned across GPUs, datatable_b200/dist.py); works for any
+ * smaller nrows too.  Same ordering, groups and NA rules as dtb_group.
+ */
+DTB_API int dtb_group64(const dtb_col* keys, int nkeys, const int* flags, int na_pos,
               int64_t nrows, dtb_stream stream,
               void* order_out, void* offsets_out, int64_t offsets_cap,
               int64_t* ngroups_out, int64_t* norder_out);
@@ -270,6 +283,14 @@ DTB_API int dtb_dense_scatter(const void* keys, int key_stype, const void* vals,
                       int64_t table_size, void* table, void* present, dtb_stream stream);
 DTB_API int dtb_dense_compact(const void* table, const void* present, int64_t table_size, int64_t kmin,
                       int key_stype, void* out_keys, void* out_vals, int64_t* ngroups_out, dtb_stream stream);
+
+/*
+ * dtb_lower_bound -- out[i] (int64) = number of rows of the ascending, NA-free column `sorted` that are
+ * smaller than values[i]: the cut points of the key-range exchange between GPUs (no reference analogue;
+ * SURVEY.md 8e).  Both columns share one stype.
+ */
+DTB_API int dtb_lower_bound(dtb_col sorted, int64_t nrows, dtb_col values, int64_t nvalues,
+                    dtb_stream stream, void* out);
 
 /*
  * Residency bracket for HOST buffers: between dtb_cache_begin() and the matching dtb_cache_end() (calls

@@ -32,6 +32,10 @@ class OracleKernels:
     def take(src, idx):
         return src[idx.long()]
 
+    @staticmethod
+    def lower_bound(sorted_keys, values):
+        return torch.from_numpy(np.searchsorted(sorted_keys.numpy(), values.numpy(), side="left").astype(np.int64))
+
     # numpy stand-ins of dtb_dense_scatter / dtb_dense_compact (include/dtb200.h)
     @staticmethod
     def dense_scatter(gkeys, part, kmin, table, present):

@@ -427,3 +427,48 @@ def test_bucketed_multi_reducer_vs_oracle_and_plain():
             want = orc.reduce(oop, v, want_o, want_f, stype=vst)
             assert_reducer_equal(results[1][i], want, name, vst, f"bucketed {name} vst={vst}")
             assert_reducer_equal(results[0][i], want, name, vst, f"plain {name} vst={vst}")
+
+
+def test_group64_equals_group_and_crosses_int32():
+    """dtb_group64 (ARR64 RowIndex + int64 offsets): identical to dtb_group below 2^31 rows, and a
+    2^31 + 1e7-row frame (which no int32 RowIndex can address) checked by sortedness, stability,
+    the permutation checksum and the Groupby invariants."""
+    import torch
+    from datatable_b200 import engine, _lib
+    rng = np.random.default_rng(5)
+    for n, sts in ((100_003, (INT32,)), (70_001, (INT64, FLOAT64))):
+        cols = [make_col(rng, st, n, "few", 0.1) for st in sts]
+        dcols = [engine.Col(torch.from_numpy(c).cuda(), st) for c, st in zip(cols, sts)]
+        o32, f32, ng32 = engine.group(dcols, [0] * len(sts), _lib.NA_FIRST)
+        o64, f64, ng64 = engine.group64(dcols, [0] * len(sts), _lib.NA_FIRST)
+        assert o64.dtype == torch.int64 and f64.dtype == torch.int64 and ng64 == ng32
+        assert torch.equal(o64, o32.long()) and torch.equal(f64, f32.long())
+        oh, fh, ngh = engine.group64(cols, [_lib.FLAG_SORT_ONLY] * len(sts), _lib.NA_LAST)      # host buffers, sort only
+        ow, _, _ = engine.group(cols, [_lib.FLAG_SORT_ONLY] * len(sts), _lib.NA_LAST)
+        assert fh is None and np.array_equal(oh, ow.astype(np.int64))
+    free, _ = torch.cuda.mem_get_info()
+    n = 2**31 + 10_000_000
+    if free < 130 * 2**30:
+        pytest.skip("needs ~110 GB of free HBM")
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    k = torch.randint(0, 1000, (n,), generator=g, device="cuda", dtype=torch.int32)
+    order, offs, ng = engine.group64([k], [0], _lib.NA_FIRST)
+    assert ng == 1000 and order.numel() == n and int(offs[0]) == 0 and int(offs[-1]) == n
+    assert bool((offs[1:] > offs[:-1]).all())
+    total, prev_k, prev_o = 0, None, None
+    step = 200_000_000
+    for c0 in range(0, n, step):
+        o = order[c0:c0 + step]
+        assert int(o.min()) >= 0 and int(o.max()) < n
+        ks = k[o]
+        total += int(o.sum())
+        ok = (ks[1:] > ks[:-1]) | ((ks[1:] == ks[:-1]) & (o[1:] > o[:-1]))
+        assert bool(ok.all()), "not sorted / not stable"
+        if prev_k is not None:
+            assert int(ks[0]) > prev_k or (int(ks[0]) == prev_k and int(o[0]) > prev_o)
+        prev_k, prev_o = int(ks[-1]), int(o[-1])
+        del ks, ok
+    assert total == n * (n - 1) // 2, "RowIndex is not a permutation of 0..n-1"
+    # group boundaries: offsets[g] is where key g starts
+    firsts = k[order[offs[:-1]]]
+    assert torch.equal(firsts, torch.arange(1000, device="cuda", dtype=torch.int32))
