@@ -27,7 +27,6 @@ void count_launch(int n) { t_stats.kernels_launched += n; }
 static int64_t opt_radix_bits = 0;     // 0 = default (8-bit digits)
 static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
-static int64_t opt_hybrid = 0;         // 1 = hybrid top-bits + tie-fix sort for wide single keys (sort-only)
 static thread_local int opt_trust_offsets = 0;  // internal: dtb_groupby_reduce passes the handle's own offsets to dtb_reduce
 static int64_t opt_bucketed = 1;       // 1 = columns with >= 2 L2 atomics per row take the bucketed multi-reducer (dtb_bucket.cu)
 static int64_t opt_overlap = 0;        // 1 = run fused direct reducers on a side stream under the sort passes
@@ -608,52 +607,9 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     if (opt_overlap) { DTB_TRY(t_side.ensure()); rs = t_side.stream; }
     DTB_TRY(facc.alloc(sizeof(u64) * (size_t)ftable * 2 * (size_t)fr->n, s));
   }
-  // ---- hybrid sort of a wide single key (sort-only, option "hybrid_sort"): 4 passes over a 31-bit
-  //      order-preserving top of the key, then the rows that still tie are ordered by their low bits
-  //      (dtb_tiefix.cu); falls back to the plain passes when the keys are too clustered (second
-  //      attempt of the loop below).  Measured at n = 1e9 float64: 77-92 ms against 66 ms for the plain
-  //      8 passes -- with 31 top bits ~40 % of 1e9 rows still tie (n / 2^31), so it is OFF by default;
-  //      it pays off below ~1e8 rows. -------------------------------------------------------------
-  const KeyPlan full_kp = rounds[0].kp;
-  const bool hybrid_ok = opt_hybrid && nrounds == 1 && fused_raw && !do_groups && full_kp.total_bits > 40 &&
-                         n >= 65536;
   const int32_t* idx_cur = nullptr;        // rows in the order established by the previous rounds
   void* sorted_keys = nullptr;             // last round's sorted composite keys
   int last_key_bytes = 4;
-  DevBuf hyb_tab;                          // device: uint16 rank[4096] then uint32 hist[4096]
-  HybridKey hy; memset(&hy, 0, sizeof(hy));
-  for (int attempt = 0; attempt < 2; attempt++) {
-  bool hybrid = hybrid_ok && attempt == 0;
-  rounds[0].kp = full_kp;
-  if (hybrid) {
-    // dense rank of the populated leading-12-bit values (order preserving), on the host: 4096 counters
-    const int T = full_kp.total_bits;
-    DTB_TRY(hyb_tab.alloc(4096 * sizeof(unsigned short) + 4096 * sizeof(u32), s));
-    u32* d_hist = reinterpret_cast<u32*>(hyb_tab.as<unsigned short>() + 4096);
-    KeyNorm k0 = full_kp.k[0]; k0.lshift = 0;
-    { ProfScope ps("top12_histogram", s); DTB_TRY(launch_top12_histogram(k0, T, n, d_hist, s)); }
-    std::vector<u32> h_hist(4096);
-    DTB_CUDA_CHECK(cudaMemcpyAsync(h_hist.data(), d_hist, 4096 * sizeof(u32), cudaMemcpyDeviceToHost, s));
-    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
-    std::vector<unsigned short> h_rank(4096, 0);
-    int npop = 0;
-    for (int i = 0; i < 4096; i++) { h_rank[i] = (unsigned short)npop; if (h_hist[i]) npop++; }
-    const int rbits = bitlen((u64)(npop > 1 ? npop - 1 : 1));
-    hy.rank = hyb_tab.as<unsigned short>();
-    hy.top_shift = T - 12;
-    hy.mid_bits = 31 - rbits;
-    if (hy.mid_bits > T - 12) hy.mid_bits = T - 12;
-    hy.low_bits = T - 12 - hy.mid_bits;
-    hy.na_top = (na_pos == DTB_NA_LAST) ? 0x80000001u : 0u;
-    if (hy.low_bits <= 0) hybrid = false;                       // nothing left for the tie fix: plain path
-    else {
-      DTB_CUDA_CHECK(cudaMemcpyAsync(hyb_tab.p, h_rank.data(), 4096 * sizeof(unsigned short), cudaMemcpyHostToDevice, s));
-      DTB_CUDA_CHECK(cudaStreamSynchronize(s));               // h_rank is a stack-lifetime buffer
-      rounds[0].kp.total_bits = 32;
-      if (opt_verbose) fprintf(stderr, "[dtb200]   hybrid sort: %d populated leading values, mid=%d low=%d bits\n",
-                               npop, hy.mid_bits, hy.low_bits);
-    }
-  }
   idx_cur = nullptr; sorted_keys = nullptr;
   for (int ri = 0; ri < nrounds; ri++) {
     const KeyPlan& rk = rounds[ri].kp;
@@ -667,7 +623,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     if (width > 10) width = 10;
     if (width < 4) width = 4;                                   // 64 bits / 4 = MAX_PASSES
     PassPlan pp; plan_passes(rk.total_bits, width, pp);
-    const bool want_sorted_keys = hybrid || (last_round && groups_k && rounds[ri].has_by && !count_table);
+    const bool want_sorted_keys = last_round && groups_k && rounds[ri].has_by && !count_table;
     // 64-bit keys whose sorted values are not needed afterwards: the passes over the low T-32 bits run
     // on 64-bit keys, the last of them writes only the upper 32 bits, and the remaining passes run on
     // 32-bit keys (8 instead of 12 bytes per row and pass in flight).  Never more passes than before.
@@ -709,7 +665,6 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       io.src_kind = (p == 0) ? src_kind : 0;
       io.keys_in = kin;
       io.keys_stage = (p == 0 && src_kind == 1) ? keyA.p : nullptr;
-      io.hybrid = hybrid ? &hy : nullptr;
       io.narrow_out = (p == narrow_after) ? (rk.total_bits - 32) : 0;
       const int kb = (narrow_after >= 0 && p > narrow_after) ? 4 : key_bytes;   // key width this pass reads
       io.idx_in = iin;
@@ -740,28 +695,6 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       iin = iout;
     }
     idx_cur = round_out;
-  }
-  if (!hybrid) break;
-  {
-    // ties on the 31-bit top -> order by the low bits; the NA rows have their own top and sit in a
-    // contiguous block at the front (or back): they are all equal and are skipped
-    const int64_t nna = (int64_t)h_stats[0].nacount;
-    const int64_t begin = (na_pos == DTB_NA_LAST) ? 0 : nna;
-    const int64_t end = (na_pos == DTB_NA_LAST) ? n - nna : n;
-    const u32 long_cap = 1u << 20;
-    DevBuf tf; DTB_TRY(tf.alloc(sizeof(u32) * ((size_t)long_cap + 4), s));
-    u32* counters = tf.as<u32>() + long_cap;
-    KeyNorm k0 = full_kp.k[0]; k0.lshift = 0;
-    {
-      ProfScope ps("tie_fix", s);
-      DTB_TRY(launch_tie_fix((const u32*)sorted_keys, order, begin, end, k0, hy.low_bits, tf.as<u32>(), long_cap, counters, s));
-    }
-    u32 h_cnt[2] = {0, 0};
-    DTB_CUDA_CHECK(cudaMemcpyAsync(h_cnt, counters, sizeof(h_cnt), cudaMemcpyDeviceToHost, s));
-    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (opt_verbose) fprintf(stderr, "[dtb200]   hybrid sort: %u long runs, fallback=%u\n", h_cnt[0], h_cnt[1]);
-    if (!h_cnt[1]) break;                                       // done; otherwise redo with the plain passes
-  }
   }
 
   DTB_TL("passes enqueued");
@@ -1013,7 +946,6 @@ int dtb_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "profile")) { opt_profile = value; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { opt_overlap = value; return DTB_OK; }
   if (!strcmp(name, "bucketed_reducers")) { opt_bucketed = value ? 1 : 0; return DTB_OK; }
-  if (!strcmp(name, "hybrid_sort")) { opt_hybrid = value; return DTB_OK; }
   if (!strcmp(name, "trim_scratch")) {
     if (t_arena.depth == 0 && t_arena.device >= 0) {
       int cur = 0; cudaGetDevice(&cur);
@@ -1046,7 +978,6 @@ int dtb_get_option(const char* name, int64_t* value) {
   if (!strcmp(name, "profile")) { *value = opt_profile; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { *value = opt_overlap; return DTB_OK; }
   if (!strcmp(name, "bucketed_reducers")) { *value = opt_bucketed; return DTB_OK; }
-  if (!strcmp(name, "hybrid_sort")) { *value = opt_hybrid; return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
 }

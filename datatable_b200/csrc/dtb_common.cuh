@@ -84,25 +84,6 @@ __device__ __forceinline__ u64 norm_load_dynamic(const KeyNorm& k, int64_t i) {
   return norm_apply(valid, u, k);
 }
 
-// ---- hybrid sort of wide keys: a 31-bit order-preserving "top" of the 41..64-bit normalised key ----
-// top = (dense rank of the key's leading 12 bits) ++ (the next mid_bits bits), + 1; NA rows get their
-// own top (0 = first, 2^31+1 = last).  The leading 12 bits of real-world wide keys carry little
-// entropy (sign + exponent of doubles: a few dozen populated values), so ranking them densely leaves
-// ~25 mantissa bits in the top and the rows that tie on it are few and short-lived.
-struct HybridKey {
-  const unsigned short* rank;   // device: dense rank of every leading-12-bit value (4096 entries)
-  int top_shift;                // key >> top_shift = leading 12 bits
-  int mid_bits;                 // bits taken verbatim below the leading 12
-  int low_bits;                 // bits left for the tie fix (0 = hybrid off)
-  u32 na_top;
-};
-__device__ __forceinline__ u32 hybrid_top(u64 x, bool valid, const HybridKey& h) {
-  if (!valid) return h.na_top;
-  const u32 r = h.rank[(u32)(x >> h.top_shift)];
-  const u32 mid = (u32)(x >> h.low_bits) & ((1u << h.mid_bits) - 1u);
-  return ((r << h.mid_bits) | mid) + 1u;
-}
-
 // ---- key sources for the radix kernels ---------------------------------------
 template <typename KeyT>
 struct PackedSrc {
@@ -134,33 +115,23 @@ struct RawSrc {
   const typename RawKey<T>::load_t* p;
   KeyNorm k;
   u32 edge32, na32, inc32;
-  HybridKey hy;                    // hybrid sort of wide keys (dtb_tiefix.cu); hy.low_bits == 0: off
-  __host__ void init(const KeyNorm& kn, const HybridKey* h = nullptr) {
+  __host__ void init(const KeyNorm& kn) {
     p = (const typename RawKey<T>::load_t*)kn.data; k = kn;
-    if (h) hy = *h; else { hy.low_bits = 0; hy.rank = nullptr; hy.top_shift = 0; hy.mid_bits = 0; hy.na_top = 0; }
     edge32 = (u32)kn.edge; na32 = (u32)kn.na_value; inc32 = (u32)kn.inc;
   }
   __device__ __forceinline__ KeyT load(int64_t i) const {
     if constexpr (Raw32<T>::ok && sizeof(KeyT) == 4) {
       u32 u; const bool valid = Raw32<T>::get(p[i], u);
       const u32 d = k.desc ? (edge32 - u) : (u - edge32);
-      return valid ? ((d >> k.cshift) + inc32) : na32;        // <= 32-bit keys never take the hybrid path
+      return valid ? ((d >> k.cshift) + inc32) : na32;
     } else {
       u64 u; const bool valid = RawKey<T>::get(p[i], u);
-      const u64 x = norm_apply(valid, u, k);
-      if (hy.low_bits == 0) return (KeyT)x;
-      return (KeyT)hybrid_top(x, valid, hy);
+      return (KeyT)norm_apply(valid, u, k);
     }
   }
 };
 
 // ---- relaxed gpu-scope accesses for look-back status words ---------------------
-__device__ __forceinline__ u32 ld_relaxed_u32(const u32* p) {
-  u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(u32* p, u32 v) {
-  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
   u64 v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
 }

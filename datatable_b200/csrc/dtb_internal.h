@@ -98,7 +98,6 @@ struct PassIO {
   int32_t*    idx_out;
   void*       keys_stage;   // src_kind 1 only, optional: buffer that receives the normalised keys in the
                             // count kernel; the scatter kernel of the pass then reads them from there
-  const void* hybrid = nullptr;   // src_kind 1 only: HybridKey* -- sort key = hybrid_top(key) (dtb_tiefix.cu)
   int         narrow_out = 0;     // 64-bit keys, > 0: keys_out receives (key >> narrow_out) as uint32 (later passes run on 32-bit keys)
 };
 
@@ -222,12 +221,5 @@ int launch_largest_group(const int32_t* offsets, int64_t ng, int64_t skip, unsig
 int launch_lower_bound(const void* sorted, int stype, int64_t n, const void* values, int64_t m, int64_t* out, cudaStream_t s);
 int launch_join(int nkeys, const void* const* xcols, const int* xst, const void* const* jcols, const int* jst,
                 int64_t nx, int64_t nj, int32_t* out, cudaStream_t s);
-
-// Hybrid sort of wide single keys: order rows that tie on the top key bits by their low bits
-// (dtb_tiefix.cu).  counters: device uint32[2] = {long runs, fallback flag}.
-int launch_tie_fix(const uint32_t* top_keys, int32_t* order, int64_t begin, int64_t end, const KeyNorm& k,
-                   int low_bits, uint32_t* long_list, uint32_t long_cap, uint32_t* counters, cudaStream_t s);
-// Histogram of the leading 12 bits of the normalised key of one raw column (hist: uint32[4096], zeroed here).
-int launch_top12_histogram(const KeyNorm& k, int total_bits, int64_t n, uint32_t* hist, cudaStream_t s);
 
 }  // namespace dtb

@@ -212,13 +212,6 @@ struct PassArgs {
   int            narrow;        // 64-bit keys only, > 0: write (key >> narrow) as uint32 -- the low bits are consumed
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const u32 d = (u32)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier -----------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, u32 count) {
   const u32 a = (u32)__cvta_generic_to_shared(bar);
@@ -580,7 +573,7 @@ static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shif
 {
   const KeyNorm& k = kp.k[0];
 #define DTB_CASE(T)                                                                          \
-  { RawSrc<T, KeyT> src; src.init(k, (const HybridKey*)io.hybrid);                           \
+  { RawSrc<T, KeyT> src; src.init(k);                                                        \
     return run_pass<KeyT>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift); }
   switch (k.stype) {
     case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_CASE(int8_t)

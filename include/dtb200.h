@@ -316,12 +316,11 @@ DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream st
  *                  (9-10 bits use the 1024-bin kernels: fewer passes, each ~2x as expensive)
  *   "verbose"      1 = print the pass plan to stderr
  *   "profile"      1 = bracket every kernel with CUDA events on the call's stream
- *   "hybrid_sort"  1 = sort-only calls on one key wider than 40 bits sort a 31-bit order-preserving
- *                  top of the key with 4 passes and order the remaining ties by the low bits (falls
- *                  back to the plain passes when the keys are too clustered); 0 (default) = always
- *                  the plain passes (faster at 1e9 rows, where ~40 % of the rows tie on 31 bits)
  *   "overlap_reducers" 1 = dtb_groupby_create_reduce runs the direct-address reducers on a side stream
  *                  concurrently with the sort passes (default 0: same stream, measured equally fast)
+ *   "bucketed_reducers" 1 (default) = value columns that would cost two or more L2 atomics per row (mean, or
+ *                  several reducers of one column) take the bucketed multi-reducer (dtb_bucket.cu); 0 = always
+ *                  one streaming pass per reducer
  *   "trim_scratch" (set only) release the calling thread's cached HBM scratch slab
  */
 DTB_API int dtb_set_option(const char* name, int64_t value);

@@ -366,36 +366,6 @@ def test_digit_width_option_gives_identical_results(bits):
         engine.set_option("radix_bits", 0)
 
 
-def test_hybrid_wide_key_sort_paths():
-    """Wide single keys (sort-only) take the hybrid path: top 32 bits by radix passes, ties by low bits.
-    All three regimes must give the oracle's exact stable order: (a) random doubles (short tie runs),
-    (b) heavy duplicates (long runs whose low bits agree), (c) values clustered inside one top-32-bit
-    bucket (long runs that differ in the low bits -> fallback to the plain passes)."""
-    from datatable_b200 import engine, _lib
-    from oracle import oracle as orc
-    rng = np.random.default_rng(2024)
-    n = 300_000
-    a = rng.standard_normal(n)
-    a[::500] = np.nan
-    b = rng.integers(0, 50, n).astype(np.float64) * 0.37 + 1e-3
-    b[::77] = np.nan
-    c = 1.0 + rng.permutation(n).astype(np.float64) * 2.0 ** -50
-    d = rng.integers(-2**62, 2**62, n, dtype=np.int64)
-    d[::5] = d[0]
-    d[1::11] = -2**63
-    engine.set_option("hybrid_sort", 1)
-    try:
-        for name, k in (("random", a), ("duplicates", b), ("clustered", c), ("int64", d)):
-            for fl, na_pos in ((SORT_ONLY, 1), (SORT_ONLY | DESCENDING, 2), (SORT_ONLY, 3)):
-                want = orc.group([k], [fl], na_pos)[0]
-                got = engine.group([k], [fl], na_pos)[0]
-                assert np.array_equal(got, want), f"hybrid sort {name} flags={fl} na_pos={na_pos}"
-    finally:
-        engine.set_option("hybrid_sort", 0)
-    got = engine.group([a], [SORT_ONLY], 1)[0]
-    assert np.array_equal(got, orc.group([a], [SORT_ONLY], 1)[0])
-
-
 def test_bucketed_multi_reducer_vs_oracle_and_plain():
     """Several reducers of one value column over a 2^12..2^20 key domain take the bucketed multi-reducer
     (dtb_bucket.cu): every value stype x every op against the oracle, and against the one-atomic-per-row path."""
