@@ -28,9 +28,9 @@ namespace dtb {
 constexpr int BK_BITS = 11;                       // keys per bucket = 2048
 constexpr int BK_KEYS = 1 << BK_BITS;
 constexpr int BK_MAXB = 512;                      // buckets: group key domain <= 2^20
-constexpr int BK_THREADS = 256;
-constexpr int BK_IPT = 16;
-constexpr int BK_TILE = BK_THREADS * BK_IPT;      // 4096 rows per scatter tile
+constexpr int BK_THREADS = 512;                   // = BK_MAXB: thread t owns bucket t in the tile scan
+constexpr int BK_IPT = 8;                         // (16 rows x 256 threads ran at 24 % occupancy: 48 registers of row
+constexpr int BK_TILE = BK_THREADS * BK_IPT;      //  state per thread; profiles/r2_c4_launches_1e9.txt) 4096 rows per tile
 constexpr int64_t BK_CHUNK = 262144;              // rows per aggregate CTA
 
 static inline int bk_grid(int64_t n, int threads) {
@@ -84,7 +84,7 @@ int launch_bucket_starts(const u32* xkeys, int gshift, int64_t n, int nb, u32* h
 
 // ---- partition one value column by bucket ---------------------------------------------------------
 template <typename L>
-__global__ void __launch_bounds__(BK_THREADS)
+__global__ void __launch_bounds__(BK_THREADS, 3)
 bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __restrict__ v, int64_t n, int nb,
                       u32* __restrict__ cursor, unsigned short* __restrict__ xlow_out, L* __restrict__ v_out)
 {
@@ -112,9 +112,9 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __rest
     r[i] = (x[i] != 0xffffffffu) ? (unsigned short)atomicAdd(&cnt[x[i] >> BK_BITS], 1u) : (unsigned short)0;
   __syncthreads();
 
-  // exclusive scan of cnt[] over the buckets (2 per thread), one global reservation per non-empty bucket
-  const u32 c0 = cnt[2 * tid], c1 = cnt[2 * tid + 1];
-  u32 incl = c0 + c1;
+  // exclusive scan of cnt[] over the buckets (one per thread), one global reservation per non-empty bucket
+  const u32 c0 = cnt[tid];
+  u32 incl = c0;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
   if (lane == 31) wsum[warp] = incl;
@@ -122,11 +122,10 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __rest
   u32 wpre = 0;
 #pragma unroll
   for (int w = 0; w < BK_THREADS / 32; w++) if (w < warp) wpre += wsum[w];
-  const u32 e0 = wpre + incl - c0 - c1, e1 = e0 + c0;
+  const u32 e0 = wpre + incl - c0;
   __syncthreads();
-  cnt[2 * tid] = e0; cnt[2 * tid + 1] = e1;
-  if (c0) gbase[2 * tid] = atomicAdd(&cursor[2 * tid], c0) - e0;
-  if (c1) gbase[2 * tid + 1] = atomicAdd(&cursor[2 * tid + 1], c1) - e1;
+  cnt[tid] = e0;
+  if (c0) gbase[tid] = atomicAdd(&cursor[tid], c0) - e0;
   __syncthreads();
 
 #pragma unroll
@@ -183,8 +182,9 @@ bucket_aggregate_kernel(const unsigned short* __restrict__ xlow, const typename 
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
       const int k = xlow[i];
       u64 u; const bool valid = RawKey<T>::get(v[i], u);          // u: sign-extended int or float image
-      if (!valid) { if (sw[BK_CNTNA]) atomicAdd(&sw[BK_CNTNA][k], 1ull); continue; }
-      if (sw[BK_CNT]) atomicAdd(&sw[BK_CNT][k], 1ull);
+      // counts are 32-bit shared-memory atomics on the low word of the slot (a chunk holds 262144 rows)
+      if (!valid) { if (sw[BK_CNTNA]) atomicAdd(reinterpret_cast<u32*>(&sw[BK_CNTNA][k]), 1u); continue; }
+      if (sw[BK_CNT]) atomicAdd(reinterpret_cast<u32*>(&sw[BK_CNT][k]), 1u);
       if (sw[BK_SUMI]) atomicAdd(&sw[BK_SUMI][k], u);
       if (sw[BK_SUMF]) {
         double d;
@@ -195,8 +195,9 @@ bucket_aggregate_kernel(const unsigned short* __restrict__ xlow, const typename 
       }
       if (sw[BK_MIN] || sw[BK_MAX]) {
         const u64 key = ISF ? u : (u ^ 0x8000000000000000ull);    // same encodings as dtb_reduce.cu:p_add
-        if (sw[BK_MIN]) atomicMin(&sw[BK_MIN][k], ISF ? key : key - 1);
-        if (sw[BK_MAX]) atomicMax(&sw[BK_MAX][k], key);
+        // after the first few rows of a key most rows improve neither bound: look before the atomic
+        if (sw[BK_MIN]) { const u64 km = ISF ? key : key - 1; if (km < sw[BK_MIN][k]) atomicMin(&sw[BK_MIN][k], km); }
+        if (sw[BK_MAX]) { if (key > sw[BK_MAX][k]) atomicMax(&sw[BK_MAX][k], key); }
       }
     }
     __syncthreads();
