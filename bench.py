@@ -564,6 +564,32 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.empty_cache()
         engine.set_option("trim_scratch", 1)
         line["other_configs"] = other_configs(torch, engine, _lib, n, peak)
+    # ---- strong-scaling line (N > 1): the SAME 1e9-row C2 frame split over the ranks ------------------------
+    strong = None
+    if world > 1 and not args.no_extra:
+        ns = n // world
+        ks, vs_ = k[:ns], v[:ns]
+
+        def sstep():
+            gb = engine.Groupby([ks], [0], _lib.NA_FIRST, reducers=[(_lib.OP_SUM, vs_)])
+            sums = gb.reduced(0)
+            gk = engine.gather(ks, gb.first_rows())
+            gb.close()
+            return ddist.merge_partials_dense(gk, sums, _lib.OP_SUM)
+        sstep(); sstep()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(3):
+            sstep()
+        s1.record()
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1) / 3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        strong = {"workload": WORKLOAD + f" -- strong scaling: {ns * world} rows in total, {ns} per GPU",
+                  "ms_per_step": float(t.item()), "rows_per_s": ns * world / float(t.item()) * 1e3, "steps": 3}
+        del ks, vs_
+
     # ---- C5 shape (N > 1 only): 1.25e9 int64-key rows per GPU, all-to-all of the partials ---------------
     if world > 1 and not args.no_extra:
         del k, v
@@ -574,7 +600,7 @@ def run_b200(args, rank, local_rank, world):
         except Exception as e:                              # pragma: no cover
             c5 = {"error": str(e)[:300]}
         if rank == 0:
-            line["other_configs"] = {"C5": c5}
+            line["other_configs"] = {"C5": c5, "C2_strong": strong}
 
     # ---- the drop-in number: the PATCHED reference's own query with the engine options off / on -----
     patched = os.path.join(ROOT, "integration", "_ref_patched")

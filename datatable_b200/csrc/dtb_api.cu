@@ -826,17 +826,17 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
         const int nb = 1 << (dbits0 > 11 ? dbits0 - 11 : 0);
         int maxb = 1;
         for (auto& bc : bcols) maxb = stype_bytes(bc.stype) > maxb ? stype_bytes(bc.stype) : maxb;
-        DTB_TRY(bstart.alloc(sizeof(u32) * (size_t)(512 + nb + 8), s));
+        DTB_TRY(bstart.alloc(bucket_starts_bytes(n) + sizeof(u32) * (size_t)(nb + 8), s));
         DTB_TRY(bscr.alloc(bucket_scratch_bytes(n, maxb), s));
         if (!bxk.p) {                                  // single raw key column: its normalised keys, once
           DTB_TRY(bxk.alloc(sizeof(u32) * (size_t)n, s));
           ProfScope ps("compose_keys", s); DTB_TRY(launch_compose_keys(rounds[0].kp, n, nullptr, bxk.p, 4, s));
         }
-        u32* hist = bstart.as<u32>(); u32* start = hist + 512;
-        DTB_TRY(launch_bucket_starts(bxk.as<u32>(), rounds[0].kp.group_shift, n, nb, hist, start, s));
+        u32* slab_starts = bstart.as<u32>(); u32* start = slab_starts + bucket_starts_bytes(n) / sizeof(u32);
+        DTB_TRY(launch_bucket_starts(bxk.as<u32>(), rounds[0].kp.group_shift, n, nb, slab_starts, start, s));
         for (auto& bc : bcols)
-          DTB_TRY(launch_bucketed_reduce(bxk.as<u32>(), rounds[0].kp.group_shift, dbits0, bc.data, bc.stype, n, start,
-                                         bc.w, bscr.p, s));
+          DTB_TRY(launch_bucketed_reduce(bxk.as<u32>(), rounds[0].kp.group_shift, dbits0, bc.data, bc.stype, n, slab_starts,
+                                         start, bc.w, bscr.p, s));
       }
     }
     for (int i = 0; i < fr->n; i++) {

@@ -38,27 +38,34 @@ static inline int bk_grid(int64_t n, int threads) {
   return (int)(want > NUM_SMS_B200 * 16 ? NUM_SMS_B200 * 16 : (want < 1 ? 1 : want));
 }
 
-// ---- rows per bucket -> start[0..nb], cursor[0..nb) -----------------------------------------
+// ---- rows per (slab, bucket) -> start[slab][bucket] ------------------------------------------------
+// A slab is a contiguous range of tiles.  Every slab gets its own output range inside every bucket
+// (buckets stay contiguous: slab 0's rows, then slab 1's, ...), so that the scatter tiles of one slab
+// reserve their runs from a cursor only they share: with ONE cursor per bucket the 244 k tiles of a 1e9-row
+// column issued 244 k same-address L2 atomics-with-return per bucket (7.4 ms per column, LSU half idle).
 __global__ void __launch_bounds__(512)
-bucket_count_kernel(const u32* __restrict__ xkeys, int gshift, int64_t n, u32* __restrict__ hist)
+bucket_count_kernel(const u32* __restrict__ xkeys, int gshift, int64_t n, int64_t slab_rows, u32* __restrict__ hist /*[nslabs][BK_MAXB]*/)
 {
   __shared__ u32 h[BK_MAXB];
   for (int i = threadIdx.x; i < BK_MAXB; i += blockDim.x) h[i] = 0;
   __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  const int64_t r0 = (int64_t)blockIdx.x * slab_rows;
+  const int64_t r1 = (r0 + slab_rows < n) ? r0 + slab_rows : n;
+  for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x)
     atomicAdd(&h[(xkeys[i] >> gshift) >> BK_BITS], 1u);
   __syncthreads();
-  for (int i = threadIdx.x; i < BK_MAXB; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
+  for (int i = threadIdx.x; i < BK_MAXB; i += blockDim.x) hist[(size_t)blockIdx.x * BK_MAXB + i] = h[i];
 }
 
+// start[slab][b] = rows of buckets < b (all slabs) + rows of bucket b in slabs < slab; bstart[b] = start[0][b], bstart[nb] = n
 __global__ void __launch_bounds__(BK_MAXB)
-bucket_scan_kernel(const u32* __restrict__ hist, int nb, u32* __restrict__ start /*[nb+1]*/)
+bucket_scan_kernel(u32* __restrict__ hist /*in: counts, out: starts*/, int nslabs, int nb, u32* __restrict__ bstart /*[nb+1]*/)
 {
   __shared__ u32 s[BK_MAXB];
   const int t = threadIdx.x;
-  const u32 c = t < nb ? hist[t] : 0;
-  s[t] = c;
+  u32 tot = 0;
+  if (t < nb) for (int c = 0; c < nslabs; c++) tot += hist[(size_t)c * BK_MAXB + t];
+  s[t] = tot;
   __syncthreads();
   for (int d = 1; d < BK_MAXB; d <<= 1) {
     const u32 a = t >= d ? s[t - d] : 0;
@@ -66,17 +73,30 @@ bucket_scan_kernel(const u32* __restrict__ hist, int nb, u32* __restrict__ start
     s[t] += a;
     __syncthreads();
   }
-  if (t < nb) start[t] = s[t] - c;
-  if (t == nb - 1) start[nb] = s[t];
+  if (t < nb) {
+    u32 run = s[t] - tot;
+    bstart[t] = run;
+    for (int c = 0; c < nslabs; c++) { const u32 v = hist[(size_t)c * BK_MAXB + t]; hist[(size_t)c * BK_MAXB + t] = run; run += v; }
+    if (t == nb - 1) bstart[nb] = s[t];
+  }
 }
 
-int launch_bucket_starts(const u32* xkeys, int gshift, int64_t n, int nb, u32* hist, u32* start, cudaStream_t s)
+int64_t bucket_slab_rows(int64_t n) {
+  // ~4 slabs per SM, whole tiles per slab
+  int64_t r = (n + NUM_SMS_B200 * 4 - 1) / (NUM_SMS_B200 * 4);
+  r = (r + BK_TILE - 1) / BK_TILE * BK_TILE;
+  return r < BK_TILE ? BK_TILE : r;
+}
+int bucket_num_slabs(int64_t n) { const int64_t r = bucket_slab_rows(n); return (int)((n + r - 1) / r); }
+
+// hist: u32[nslabs * 512] (becomes the per-slab cursors' initial values), bstart: u32[nb + 1]
+int launch_bucket_starts(const u32* xkeys, int gshift, int64_t n, int nb, u32* hist, u32* bstart, cudaStream_t s)
 {
-  DTB_CUDA_CHECK(cudaMemsetAsync(hist, 0, sizeof(u32) * BK_MAXB, s));
+  const int nslabs = bucket_num_slabs(n);
   prof_begin("bucket_count", s);
-  bucket_count_kernel<<<bk_grid(n, 512 * 8), 512, 0, s>>>(xkeys, gshift, n, hist);
+  bucket_count_kernel<<<nslabs, 512, 0, s>>>(xkeys, gshift, n, bucket_slab_rows(n), hist);
   prof_end(s);
-  bucket_scan_kernel<<<1, BK_MAXB, 0, s>>>(hist, nb, start);
+  bucket_scan_kernel<<<1, BK_MAXB, 0, s>>>(hist, nslabs, nb, bstart);
   count_launch(2);
   DTB_CUDA_CHECK(cudaGetLastError());
   return DTB_OK;
@@ -85,8 +105,8 @@ int launch_bucket_starts(const u32* xkeys, int gshift, int64_t n, int nb, u32* h
 // ---- partition one value column by bucket ---------------------------------------------------------
 template <typename L>
 __global__ void __launch_bounds__(BK_THREADS, 3)
-bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __restrict__ v, int64_t n, int nb,
-                      u32* __restrict__ cursor, unsigned short* __restrict__ xlow_out, L* __restrict__ v_out)
+bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __restrict__ v, int64_t n, int64_t slab_rows,
+                      u32* __restrict__ cursors /*[nslabs][BK_MAXB]*/, unsigned short* __restrict__ xlow_out, L* __restrict__ v_out)
 {
   __shared__ u32 cnt[BK_MAXB];                 // rows of the bucket in this tile; then: tile slot of its first row
   __shared__ u32 gbase[BK_MAXB];               // (reserved global slot) - (tile slot) of the bucket
@@ -96,6 +116,7 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __rest
   u32* sx = reinterpret_cast<u32*>(bk_stage + sizeof(L) * BK_TILE);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = (int64_t)blockIdx.x * BK_TILE;
+  u32* cursor = cursors + (size_t)(base / slab_rows) * BK_MAXB;       // the slab's own reservation cursors
   const int tile_n = (int)((n - base) < (int64_t)BK_TILE ? (n - base) : (int64_t)BK_TILE);
   for (int i = tid; i < BK_MAXB; i += BK_THREADS) cnt[i] = 0;
   __syncthreads();
@@ -142,7 +163,6 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __rest
     xlow_out[dst] = (unsigned short)(xx & (BK_KEYS - 1));
     v_out[dst] = sv[p];
   }
-  (void)nb;
 }
 
 // ---- aggregate ---------------------------------------------------------------------------------------
@@ -216,13 +236,15 @@ bucket_aggregate_kernel(const unsigned short* __restrict__ xlow, const typename 
 }
 
 size_t bucket_scratch_bytes(int64_t n, int value_bytes) {
-  return ((size_t)n * 2 + 255) / 256 * 256 + ((size_t)n * value_bytes + 255) / 256 * 256 + sizeof(u32) * (BK_MAXB + 8);
+  return ((size_t)n * 2 + 255) / 256 * 256 + ((size_t)n * value_bytes + 255) / 256 * 256 + bucket_starts_bytes(n);
 }
+size_t bucket_starts_bytes(int64_t n) { return sizeof(u32) * ((size_t)bucket_num_slabs(n) * BK_MAXB + 8); }
 
 // acc_w[w]: global table of (1 << dbits) u64 for every requested word (NULL otherwise), already set to the
-// word's identity (~0 for BK_MIN, 0 otherwise).  start: [nb+1] from launch_bucket_starts.
+// word's identity (~0 for BK_MIN, 0 otherwise).  slab_starts / bstart: from launch_bucket_starts.
 int launch_bucketed_reduce(const u32* xkeys, int gshift, int dbits, const void* value, int stype, int64_t n,
-                           const u32* start, unsigned long long* const* acc_w, void* scratch, cudaStream_t s)
+                           const u32* slab_starts, const u32* start, unsigned long long* const* acc_w, void* scratch,
+                           cudaStream_t s)
 {
   if (n == 0) return DTB_OK;
   const int nb = 1 << (dbits > BK_BITS ? dbits - BK_BITS : 0);
@@ -231,15 +253,16 @@ int launch_bucketed_reduce(const u32* xkeys, int gshift, int dbits, const void* 
   unsigned short* xlow = (unsigned short*)scratch;
   char* vpart = (char*)scratch + ((size_t)n * 2 + 255) / 256 * 256;
   u32* cursor = (u32*)(vpart + ((size_t)n * esz + 255) / 256 * 256);
-  DTB_CUDA_CHECK(cudaMemcpyAsync(cursor, start, sizeof(u32) * (size_t)nb, cudaMemcpyDeviceToDevice, s));
+  const int64_t slab_rows = bucket_slab_rows(n);
+  DTB_CUDA_CHECK(cudaMemcpyAsync(cursor, slab_starts, sizeof(u32) * (size_t)bucket_num_slabs(n) * BK_MAXB, cudaMemcpyDeviceToDevice, s));
   const unsigned tiles = (unsigned)((n + BK_TILE - 1) / BK_TILE);
   if (esz == 8) DTB_CUDA_CHECK(cudaFuncSetAttribute(bucket_scatter_kernel<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * BK_TILE));
   prof_begin("bucket_scatter", s);
   switch (esz) {
-    case 1: bucket_scatter_kernel<uint8_t><<<tiles, BK_THREADS, (sizeof(uint8_t) + 4) * BK_TILE, s>>>(xkeys, gshift, (const uint8_t*)value, n, nb, cursor, xlow, (uint8_t*)vpart); break;
-    case 2: bucket_scatter_kernel<uint16_t><<<tiles, BK_THREADS, (sizeof(uint16_t) + 4) * BK_TILE, s>>>(xkeys, gshift, (const uint16_t*)value, n, nb, cursor, xlow, (uint16_t*)vpart); break;
-    case 4: bucket_scatter_kernel<u32><<<tiles, BK_THREADS, (sizeof(u32) + 4) * BK_TILE, s>>>(xkeys, gshift, (const u32*)value, n, nb, cursor, xlow, (u32*)vpart); break;
-    case 8: bucket_scatter_kernel<u64><<<tiles, BK_THREADS, (sizeof(u64) + 4) * BK_TILE, s>>>(xkeys, gshift, (const u64*)value, n, nb, cursor, xlow, (u64*)vpart); break;
+    case 1: bucket_scatter_kernel<uint8_t><<<tiles, BK_THREADS, (sizeof(uint8_t) + 4) * BK_TILE, s>>>(xkeys, gshift, (const uint8_t*)value, n, slab_rows, cursor, xlow, (uint8_t*)vpart); break;
+    case 2: bucket_scatter_kernel<uint16_t><<<tiles, BK_THREADS, (sizeof(uint16_t) + 4) * BK_TILE, s>>>(xkeys, gshift, (const uint16_t*)value, n, slab_rows, cursor, xlow, (uint16_t*)vpart); break;
+    case 4: bucket_scatter_kernel<u32><<<tiles, BK_THREADS, (sizeof(u32) + 4) * BK_TILE, s>>>(xkeys, gshift, (const u32*)value, n, slab_rows, cursor, xlow, (u32*)vpart); break;
+    case 8: bucket_scatter_kernel<u64><<<tiles, BK_THREADS, (sizeof(u64) + 4) * BK_TILE, s>>>(xkeys, gshift, (const u64*)value, n, slab_rows, cursor, xlow, (u64*)vpart); break;
     default: set_error("unsupported stype"); return DTB_ENOTIMPL;
   }
   prof_end(s);

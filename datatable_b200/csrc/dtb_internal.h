@@ -187,11 +187,14 @@ int launch_group_keys(const void* sorted_keys, int key_bytes, const int32_t* off
 // by group-key bucket, shared-memory accumulators.  Words a column can ask for:
 enum { BK_SUMI = 0, BK_SUMF = 1, BK_CNT = 2, BK_MIN = 3, BK_MAX = 4, BK_CNTNA = 5, BK_NWORDS = 6 };
 constexpr int BK_MAX_DBITS = 20, BK_MIN_DBITS = 12;
-// rows per bucket of the group keys xkeys[i] >> gshift: hist[512] scratch, start[nb+1]
-int launch_bucket_starts(const uint32_t* xkeys, int gshift, int64_t n, int nb, uint32_t* hist, uint32_t* start, cudaStream_t s);
+// rows per (slab of tiles, bucket) of the group keys xkeys[i] >> gshift: slab_starts u32[bucket_starts_bytes(n)/4]
+// (first output slot of every slab inside every bucket), bstart u32[nb+1] (bucket boundaries)
+size_t bucket_starts_bytes(int64_t n);
+int launch_bucket_starts(const uint32_t* xkeys, int gshift, int64_t n, int nb, uint32_t* slab_starts, uint32_t* bstart, cudaStream_t s);
 size_t bucket_scratch_bytes(int64_t n, int value_bytes);
 int launch_bucketed_reduce(const uint32_t* xkeys, int gshift, int dbits, const void* value, int stype, int64_t n,
-                           const uint32_t* start, unsigned long long* const* acc_w, void* scratch, cudaStream_t s);
+                           const uint32_t* slab_starts, const uint32_t* bstart, unsigned long long* const* acc_w,
+                           void* scratch, cudaStream_t s);
 void fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t s);
 
 int launch_gather(const void* src, int stype, int64_t nrows_src, const void* order,

@@ -51,3 +51,58 @@ def test_fuzz_group_reduce_vs_oracle(seed):
         assert_reducer_equal(gb.reduced(1).cpu().numpy(), orc.reduce(OPS["max"], v, want_o, want_f, stype=vst), "max", vst, ctx=f"seed {seed} fused max")
         assert np.array_equal(gb.reduced(2).cpu().numpy(), np.diff(want_f).astype(np.int64))
         gb.close()
+
+
+def test_reduce_rejects_offsets_that_are_not_a_groupby():
+    """dtb_reduce validates caller-supplied offsets (groupby.h:41-47: offsets[0] = 0, strictly increasing):
+    an empty group would silently shift every later group of its tile."""
+    import torch
+    from datatable_b200 import engine, _lib
+    v = np.arange(10, dtype=np.float64)
+    order = np.arange(10, dtype=np.int32)
+    for bad in ([0, 3, 3, 10], [1, 3, 10], [0, 7, 5, 10]):
+        offs = np.array(bad, dtype=np.int32)
+        with pytest.raises(_lib.DtbValueError, match="not a Groupby"):
+            engine.reduce(_lib.OP_SUM, v, order, offs)
+        with pytest.raises(_lib.DtbValueError, match="not a Groupby"):
+            engine.reduce(_lib.OP_SUM, torch.from_numpy(v).cuda(), torch.from_numpy(order).cuda(), torch.from_numpy(offs).cuda())
+    got = engine.reduce(_lib.OP_SUM, v, order, np.array([0, 3, 10], dtype=np.int32))
+    assert got.tolist() == [3.0, 42.0]
+
+
+def test_constant_by_column_with_full_width_sort_column():
+    """by(constant column) + sort(32-/64-bit column): the by-columns contribute 0 bits, so group_shift would equal
+    the key width (a shift by the full width is undefined): the engine must return ONE group and the plain sort."""
+    from datatable_b200 import engine, _lib
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    n = 50_000
+    c = np.full(n, 7, dtype=np.int32)
+    for x in (rng.integers(-2**31 + 1, 2**31 - 1, n, dtype=np.int64).astype(np.int32),
+              rng.integers(-2**63 + 1, 2**63 - 1, n, dtype=np.int64)):
+        want_o, want_f, want_ng = orc.group([c, x], [0, orc.SORT_ONLY], orc.NA_FIRST)
+        o, f, ng = engine.group([c, x], [0, _lib.FLAG_SORT_ONLY], _lib.NA_FIRST)
+        assert ng == want_ng == 1 and np.array_equal(f, want_f) and np.array_equal(o, want_o)
+        gb = engine.Groupby([__import__("torch").from_numpy(c).cuda(), __import__("torch").from_numpy(x).cuda()],
+                            [0, _lib.FLAG_SORT_ONLY], _lib.NA_FIRST)
+        assert gb.ngroups == 1 and np.array_equal(gb.order().cpu().numpy(), want_o)
+        gb.close()
+
+
+def test_one_thread_two_devices():
+    """The scratch arena follows the calling thread's current device: alternate two GPUs."""
+    import torch
+    from datatable_b200 import engine, _lib
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(8)
+    k = rng.integers(0, 1000, 300_000).astype(np.int32)
+    want = np.argsort(k, kind="stable").astype(np.int32)
+    try:
+        for dev in (0, 1, 0, 1):
+            torch.cuda.set_device(dev)
+            kd = torch.from_numpy(k).to(f"cuda:{dev}")
+            o, f, ng = engine.group([kd], [0], _lib.NA_FIRST)
+            assert o.device.index == dev and np.array_equal(o.cpu().numpy(), want)
+    finally:
+        torch.cuda.set_device(0)
