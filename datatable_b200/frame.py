@@ -213,6 +213,45 @@ class Frame:
     def to_dict(self):
         return dict(zip(self.names, self.to_list()))
 
+    # -- Arrow ingest / export (the reference reads Arrow through Frame(pa.Table), frame/__init__.cc; here the
+    #    fixed-width columns become the NA-sentinel buffers the engine consumes) -----------
+    @classmethod
+    def from_arrow(cls, table):
+        """pyarrow.Table / RecordBatch -> Frame: bool/int8-64/float32-64 columns, nulls -> the reference's NA
+        sentinels (bool8 = int8 with -128).  Zero-copy for null-free numeric columns."""
+        import pyarrow as pa
+        cols, sts = {}, {}
+        for name, col in zip(table.column_names, table.columns):
+            arr = col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col
+            t = arr.type
+            if pa.types.is_boolean(t):
+                a = np.asarray(arr.cast(pa.int8()).fill_null(-128).to_numpy(zero_copy_only=False), dtype=np.int8)
+                st = BOOL
+            elif pa.types.is_integer(t) and t.bit_width <= 64 and pa.types.is_signed_integer(t):
+                st = {8: INT8, 16: INT16, 32: INT32, 64: INT64}[t.bit_width]
+                a = arr.fill_null(_NA_VALUE[st]).to_numpy(zero_copy_only=False) if arr.null_count else arr.to_numpy()
+            elif pa.types.is_floating(t) and t.bit_width in (32, 64):
+                st = FLOAT32 if t.bit_width == 32 else FLOAT64
+                a = arr.to_numpy(zero_copy_only=False)          # nulls become NaN == NA
+            else:
+                raise _lib.DtbNotImplError(f"Arrow column `{name}` of type {t} is outside the GPU hot path")
+            cols[name], sts[name] = np.ascontiguousarray(a), st
+        return cls(cols, stypes=sts)
+
+    def to_arrow(self):
+        """Frame -> pyarrow.Table with NA sentinels turned back into nulls."""
+        import pyarrow as pa
+        out = {}
+        for n in self._cols:
+            a, st = self.to_numpy(n), self._stypes[n]
+            if st in (FLOAT32, FLOAT64):
+                out[n] = pa.array(a, mask=np.isnan(a))
+            elif st == BOOL:
+                out[n] = pa.array(a.astype(np.bool_), mask=(a == -128))
+            else:
+                out[n] = pa.array(a, mask=(a == _NA_VALUE[st]))
+        return pa.table(out)
+
     def to_device(self):
         """Copy every column into HBM (the analogue of a device-backed Buffer)."""
         fr = Frame()
