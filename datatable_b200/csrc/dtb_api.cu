@@ -28,6 +28,7 @@ static int64_t opt_radix_bits = 0;     // 0 = default (8-bit digits)
 static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
 static thread_local int opt_trust_offsets = 0;  // internal: dtb_groupby_reduce passes the handle's own offsets to dtb_reduce
+static int64_t opt_stage_keys = 1;     // 1 = the first count kernel materialises the normalised keys of a raw key column
 static int64_t opt_bucketed = 1;       // 1 = columns with >= 2 L2 atomics per row take the bucketed multi-reducer (dtb_bucket.cu)
 static int64_t opt_overlap = 0;        // 1 = run fused direct reducers on a side stream under the sort passes
 
@@ -664,7 +665,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       PassIO io;
       io.src_kind = (p == 0) ? src_kind : 0;
       io.keys_in = kin;
-      io.keys_stage = (p == 0 && src_kind == 1) ? keyA.p : nullptr;
+      io.keys_stage = (p == 0 && src_kind == 1 && opt_stage_keys) ? keyA.p : nullptr;
       io.narrow_out = (p == narrow_after) ? (rk.total_bits - 32) : 0;
       const int kb = (narrow_after >= 0 && p > narrow_after) ? 4 : key_bytes;   // key width this pass reads
       io.idx_in = iin;
@@ -946,6 +947,7 @@ int dtb_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "profile")) { opt_profile = value; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { opt_overlap = value; return DTB_OK; }
   if (!strcmp(name, "bucketed_reducers")) { opt_bucketed = value ? 1 : 0; return DTB_OK; }
+  if (!strcmp(name, "stage_keys")) { opt_stage_keys = value ? 1 : 0; return DTB_OK; }
   if (!strcmp(name, "trim_scratch")) {
     if (t_arena.depth == 0 && t_arena.device >= 0) {
       int cur = 0; cudaGetDevice(&cur);
@@ -978,6 +980,7 @@ int dtb_get_option(const char* name, int64_t* value) {
   if (!strcmp(name, "profile")) { *value = opt_profile; return DTB_OK; }
   if (!strcmp(name, "overlap_reducers")) { *value = opt_overlap; return DTB_OK; }
   if (!strcmp(name, "bucketed_reducers")) { *value = opt_bucketed; return DTB_OK; }
+  if (!strcmp(name, "stage_keys")) { *value = opt_stage_keys; return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
 }
