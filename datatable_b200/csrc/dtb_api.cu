@@ -28,7 +28,7 @@ static int64_t opt_radix_bits = 0;     // 0 = default (8-bit digits)
 static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
 static thread_local int opt_trust_offsets = 0;  // internal: dtb_groupby_reduce passes the handle's own offsets to dtb_reduce
-static int64_t opt_stage_keys = 1;     // 1 = the first count kernel materialises the normalised keys of a raw key column
+static int64_t opt_stage_keys = 0;     // 1 = the first count kernel also materialises the normalised keys of a raw key column (round-1 behaviour)
 static int64_t opt_bucketed = 1;       // 1 = columns with >= 2 L2 atomics per row take the bucketed multi-reducer (dtb_bucket.cu)
 static int64_t opt_overlap = 0;        // 1 = run fused direct reducers on a side stream under the sort passes
 

@@ -85,10 +85,16 @@ __device__ __forceinline__ u64 norm_load_dynamic(const KeyNorm& k, int64_t i) {
 }
 
 // ---- key sources for the radix kernels ---------------------------------------
+// load_raw / norm are split so that a kernel can issue all the loads of a tile before it touches any of
+// them (with load() alone ptxas reused one register for the raw element and serialised the 16 loads of
+// the scatter pass behind one another: +2.3 ms per 1e9 int32 rows).
 template <typename KeyT>
 struct PackedSrc {
+  typedef KeyT raw_t;
   const KeyT* p;
   __device__ __forceinline__ KeyT load(int64_t i) const { return p[i]; }
+  __device__ __forceinline__ raw_t load_raw(int64_t i) const { return p[i]; }
+  __device__ __forceinline__ KeyT norm(raw_t r) const { return r; }
 };
 
 // Raw column normalised on the fly.  Columns of at most 32 bits producing 32-bit keys take an
@@ -119,16 +125,19 @@ struct RawSrc {
     p = (const typename RawKey<T>::load_t*)kn.data; k = kn;
     edge32 = (u32)kn.edge; na32 = (u32)kn.na_value; inc32 = (u32)kn.inc;
   }
-  __device__ __forceinline__ KeyT load(int64_t i) const {
+  typedef typename RawKey<T>::load_t raw_t;
+  __device__ __forceinline__ raw_t load_raw(int64_t i) const { return p[i]; }
+  __device__ __forceinline__ KeyT norm(raw_t r) const {
     if constexpr (Raw32<T>::ok && sizeof(KeyT) == 4) {
-      u32 u; const bool valid = Raw32<T>::get(p[i], u);
+      u32 u; const bool valid = Raw32<T>::get(r, u);
       const u32 d = k.desc ? (edge32 - u) : (u - edge32);
       return valid ? ((d >> k.cshift) + inc32) : na32;
     } else {
-      u64 u; const bool valid = RawKey<T>::get(p[i], u);
+      u64 u; const bool valid = RawKey<T>::get(r, u);
       return (KeyT)norm_apply(valid, u, k);
     }
   }
+  __device__ __forceinline__ KeyT load(int64_t i) const { return norm(load_raw(i)); }
 };
 
 // ---- relaxed gpu-scope accesses for look-back status words ---------------------

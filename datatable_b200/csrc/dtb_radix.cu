@@ -291,10 +291,18 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
   // ---- load keys (warp-striped: item i of lane l sits at warp_base + i*32 + l) ----
   KeyT key[IPT];
   const int wbase = warp * 32 * IPT;
+  {
+    typename Src::raw_t raw[IPT];                                // every load of the tile in flight first ...
 #pragma unroll
-  for (int i = 0; i < IPT; i++) {
-    const int lp = wbase + i * 32 + lane;
-    key[i] = (FULL || lp < tile_n) ? a.src.load(base + lp) : (KeyT)0;
+    for (int i = 0; i < IPT; i++) {
+      const int lp = wbase + i * 32 + lane;
+      raw[i] = (FULL || lp < tile_n) ? a.src.load_raw(base + lp) : (typename Src::raw_t)0;
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; i++) {                              // ... then normalised (identity for packed keys)
+      const int lp = wbase + i * 32 + lane;
+      key[i] = (FULL || lp < tile_n) ? a.src.norm(raw[i]) : (KeyT)0;
+    }
   }
   // first output slot of the thread's digits (loaded by the caller before the keys, parked here until
   // the scan phase: the store waits for those loads only after the key loads are in flight)

@@ -318,9 +318,10 @@ DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream st
  *   "profile"      1 = bracket every kernel with CUDA events on the call's stream
  *   "overlap_reducers" 1 = dtb_groupby_create_reduce runs the direct-address reducers on a side stream
  *                  concurrently with the sort passes (default 0: same stream, measured equally fast)
- *   "stage_keys"   1 (default) = the first count kernel of a single raw key column also writes the normalised keys,
- *                  and the first scatter reads those; 0 = the first scatter normalises the raw column itself
- *                  (measured at 1e9 rows: count -0.6 ms, scatter +2.3 ms for int32 keys; -1.1 / +3.4 ms for float64)
+ *   "stage_keys"   0 (default) = the first count and scatter kernels of a single raw key column normalise it on
+ *                  the fly (no normalised-key array is written); 1 = the first count kernel materialises the
+ *                  normalised keys and the first scatter reads those (round-1 behaviour; measured at 1e9 rows:
+ *                  +0.5 ms and +8 GB of DRAM traffic for int32 keys, +0.9 ms for float64)
  *   "bucketed_reducers" 1 (default) = value columns that would cost two or more L2 atomics per row (mean, or
  *                  several reducers of one column) take the bucketed multi-reducer (dtb_bucket.cu); 0 = always
  *                  one streaming pass per reducer
