@@ -34,6 +34,28 @@ __device__ __forceinline__ unsigned rank_ballot(unsigned d, unsigned short* hist
   return r;
 }
 
+// mode 2 "redux": the same peer masks from redux.sync.or of one-hot lane bits (does REDUX run beside VOTE?)
+// mode 3 "mixed": low half of the bits by vote.ballot, high half by redux.sync.or
+template <int NB, int NVOTE>
+__device__ __forceinline__ unsigned rank_mixed(unsigned d, unsigned short* hist, unsigned lt, unsigned lanebit) {
+  unsigned peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < NB; b++) {
+    const bool p = (d >> b) & 1;
+    unsigned m;
+    if (b < NVOTE) m = __ballot_sync(0xffffffffu, p);
+    else m = __reduce_or_sync(0xffffffffu, p ? lanebit : 0u);
+    peers &= p ? m : ~m;
+  }
+  const unsigned short cnt = hist[d];
+  const unsigned before = peers & lt;
+  const unsigned r = (unsigned)cnt + __popc(before);
+  __syncwarp();
+  if (before == 0) hist[d] = cnt + (unsigned short)__popc(peers);
+  __syncwarp();
+  return r;
+}
+
 __device__ __forceinline__ unsigned rank_atomic(unsigned d, unsigned* cnt, unsigned lt) {
   unsigned r = atomicAdd(&cnt[d], 1u);
   __syncwarp();
@@ -67,6 +89,8 @@ __global__ void __launch_bounds__(256, 4) k(unsigned* out, int iters) {
     const unsigned d = (x >> 13) & (NBINS - 1);
     unsigned r;
     if (MODE == 0) r = rank_ballot<NB>(d, reinterpret_cast<unsigned short*>(tab + warp * NBINS), lt);
+    else if (MODE == 2) r = rank_mixed<NB, 0>(d, reinterpret_cast<unsigned short*>(tab + warp * NBINS), lt, 1u << lane);
+    else if (MODE == 3) r = rank_mixed<NB, (NB + 1) / 2>(d, reinterpret_cast<unsigned short*>(tab + warp * NBINS), lt, 1u << lane);
     else           r = rank_atomic(d, tab + warp * NBINS, lt);
     acc += r;
   }
@@ -101,27 +125,31 @@ template <int NB> void run(unsigned* out, unsigned* bad) {
   cudaFuncSetAttribute(check<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * smem);
   cudaFuncSetAttribute(k<0, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(k<1, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<2, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaFuncSetAttribute(k<3, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   check<NB><<<148, 256, 2 * smem>>>(bad, 400);
   unsigned hbad = 0; cudaMemcpy(&hbad, bad, 4, cudaMemcpyDeviceToHost);
-  for (int mode = 0; mode < 2; mode++) {
+  for (int mode = 0; mode < 4; mode++) {
     float ms = 0;
     for (int rep = 0; rep < 2; rep++) {
       cudaEventRecord(a);
       if (mode == 0) k<0, NB><<<148 * 4, 256, smem>>>(out, iters);
-      else           k<1, NB><<<148 * 4, 256, smem>>>(out, iters);
+      else if (mode == 1) k<1, NB><<<148 * 4, 256, smem>>>(out, iters);
+      else if (mode == 2) k<2, NB><<<148 * 4, 256, smem>>>(out, iters);
+      else           k<3, NB><<<148 * 4, 256, smem>>>(out, iters);
       cudaEventRecord(b); cudaEventSynchronize(b);
       cudaEventElapsedTime(&ms, a, b);
     }
     const double wops = 148.0 * 4 * 8 * iters;
     printf("bits=%2d %-7s %8.3f ms  %6.1f SM-cycles per 32-row round (32 warps/SM)  mismatches=%u\n", NB,
-           mode ? "atomic" : "ballot", ms, ms * 1e-3 * 1.965e9 / (wops / 148), hbad);
+           mode == 0 ? "ballot" : mode == 1 ? "atomic" : mode == 2 ? "redux" : "mixed", ms, ms * 1e-3 * 1.965e9 / (wops / 148), hbad);
   }
 }
 
 int main() {
   unsigned* out; cudaMalloc(&out, 148 * 4 * 256 * 4);
   unsigned* bad; cudaMalloc(&bad, 4);
-  run<6>(out, bad); run<7>(out, bad); run<8>(out, bad); run<9>(out, bad); run<10>(out, bad); run<11>(out, bad);
+  run<6>(out, bad); run<7>(out, bad); run<8>(out, bad);
   printf("err=%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
