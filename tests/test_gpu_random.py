@@ -442,3 +442,26 @@ def test_group64_equals_group_and_crosses_int32():
     # group boundaries: offsets[g] is where key g starts
     firsts = k[order[offs[:-1]]]
     assert torch.equal(firsts, torch.arange(1000, device="cuda", dtype=torch.int32))
+
+
+def test_stage_keys_option_gives_identical_results():
+    """Option stage_keys (materialise the normalised keys in the first count kernel, round-1 behaviour) and the
+    default (normalise on the fly in count and scatter) must produce the same RowIndex / offsets."""
+    import torch
+    from datatable_b200 import engine, _lib
+    rng = np.random.default_rng(12)
+    n = 300_017
+    for st in (INT8, INT16, INT32, INT64, FLOAT32, FLOAT64):
+        k = make_col(rng, st, n, "wide" if st in (FLOAT32, FLOAT64) else "unit", 0.05)
+        kd = engine.Col(torch.from_numpy(k).cuda(), st)
+        res = []
+        for sk in (0, 1):
+            engine.set_option("stage_keys", sk)
+            try:
+                for fl, nap in (([0], _lib.NA_FIRST), ([_lib.FLAG_SORT_ONLY | _lib.FLAG_DESCENDING], _lib.NA_LAST)):
+                    o, f, ng = engine.group([kd], fl, nap)
+                    res.append((sk, o.cpu().numpy(), None if f is None else f.cpu().numpy()))
+            finally:
+                engine.set_option("stage_keys", 0)
+        for a, b in zip(res[:2], res[2:]):
+            assert np.array_equal(a[1], b[1]) and (a[2] is None) == (b[2] is None) and (a[2] is None or np.array_equal(a[2], b[2]))
