@@ -112,4 +112,31 @@ inline std::vector<TOut> reduce(int op, const Column& col, const RowIndex& ri, c
   return out;
 }
 
+// Column::sort_grouped (sort.cc:1499-1530): the rows of every group reordered by `col` (NA first), as a new
+// RowIndex; Median_ColumnImpl / op_nunique read it (reduce<...>(DTB_OP_MEDIAN / DTB_OP_NUNIQUE, col, ri2, gby)).
+inline RowIndex sort_grouped(const Column& col, const RowIndex& ri, const Groupby& gby, dtb_stream stream = nullptr)
+{
+  size_t i0 = 0, n = 0;
+  if (gby.size()) gby.get_group(gby.size() - 1, &i0, &n);
+  std::vector<int32_t> out(n);
+  check(dtb_sort_grouped(dtb_col{col.get_data_readonly(), int(col.stype()), 0}, int64_t(col.nrows()),
+                         ri.size() ? ri.indices32() : nullptr, gby.offsets_r(), int64_t(gby.size()), stream, out.data()));
+  return RowIndex(std::move(out));
+}
+
+// natural_join (frame/join.cc:392-470): for every row of the X key columns the matching row of the keyed
+// (sorted, unique) J key columns, or the NA index INT32_MIN.
+inline RowIndex natural_join(const std::vector<Column>& xkeys, const std::vector<Column>& jkeys, dtb_stream stream = nullptr)
+{
+  if (xkeys.empty() || xkeys.size() != jkeys.size()) throw ValueError(DTB_EINVAL, "key columns mismatch");
+  std::vector<dtb_col> xs, js;
+  for (size_t c = 0; c < xkeys.size(); ++c) {
+    xs.push_back(dtb_col{xkeys[c].get_data_readonly(), int(xkeys[c].stype()), 0});
+    js.push_back(dtb_col{jkeys[c].get_data_readonly(), int(jkeys[c].stype()), 0});
+  }
+  std::vector<int32_t> out(xkeys[0].nrows());
+  check(dtb_join(xs.data(), js.data(), int(xs.size()), int64_t(xkeys[0].nrows()), int64_t(jkeys[0].nrows()), stream, out.data()));
+  return RowIndex(std::move(out));
+}
+
 }  // namespace dtb

@@ -1,6 +1,7 @@
 // C++ host mirror (include/dtb200.hpp) exercised the way the reference's group() is used
 // (src/core/expr/eval_context.cc:249-288): built by __graft_entry__.build(), run by
 // tests/test_gpu_cpp.py on the GPU box.  Prints "OK" on success.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +42,25 @@ int main() {
       }
       g++;
     }
+    // median per group: sort_grouped + DTB_OP_MEDIAN (head_reduce_unary.cc:421-468), checked against std::sort
+    dtb::RowIndex ri2 = dtb::sort_grouped(vc, ri, gb);
+    std::vector<double> med = dtb::reduce<double>(DTB_OP_MEDIAN, vc, ri2, gb);
+    for (size_t gg = 0; gg < gb.size(); gg += 97) {
+      size_t i0, i1; gb.get_group(gg, &i0, &i1);
+      std::vector<double> w;
+      for (size_t p = i0; p < i1; p++) w.push_back(v[size_t(ri[p])]);
+      std::sort(w.begin(), w.end());
+      const size_t m = w.size();
+      const double want_med = (m & 1) ? w[m / 2] : (w[m / 2] + w[m / 2 - 1]) / 2;
+      if (med[gg] != want_med) { printf("FAIL: median of group %zu\n", gg); return 1; }
+    }
+    // natural join of the key column against its own sorted unique values (frame/join.cc:392-470)
+    std::vector<int32_t> uniq;
+    for (size_t gg = 0; gg < gb.size(); gg++) { size_t i0, i1; gb.get_group(gg, &i0, &i1); uniq.push_back(k[size_t(ri[i0])]); }
+    dtb::Column jc(uniq.data(), dtb::SType::INT32, uniq.size());
+    dtb::RowIndex jr = dtb::natural_join({kc}, {jc});
+    for (size_t i = 0; i < n; i += 1013)
+      if (jr[i] < 0 || uniq[size_t(jr[i])] != k[i]) { printf("FAIL: join at row %zu\n", i); return 1; }
     // unsupported stype -> NotImplError, like sort.cc:673
     bool threw = false;
     try { dtb::Column sc(k.data(), static_cast<dtb::SType>(11), n); dtb::group({sc}, {dtb::SortFlag::NONE}); }
