@@ -354,12 +354,40 @@ def c5_record(torch, dist, engine, _lib, ddist, rank, world, steps=3):
             "check_sums_add_up": bool(ok), "steps": steps}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One process per GPU: run (and first-touch the pinned host buffers) on the CPU socket the GPU hangs off,
+    so that the 12 GB/step of H2D traffic does not cross the inter-socket link.  Best effort; returns the node or None."""
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        if hasattr(props, "pci_bus_id"):
+            bdf = f"{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{getattr(props, 'pci_device_id', 0):02x}.0"
+        else:
+            out = subprocess.run(["nvidia-smi", f"--id={local_rank}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = out[-12:]                                       # 00000000:1B:00.0 -> 0000:1B:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf.lower()}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (datatable_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import datatable_b200 as dtb
@@ -520,7 +548,8 @@ def run_b200(args, rank, local_rank, world):
         line["e2e"] = {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                        "steps": args.e2e_steps,
                        "h2d_bytes_per_step": int(n * 12), "d2h_bytes_per_step": int(R.nrows * 12),
-                       "api": "datatable_b200.Frame[:, sum(f.v), by(f.k)] on pinned host columns"}
+                       "api": "datatable_b200.Frame[:, sum(f.v), by(f.k)] on pinned host columns",
+                       "host_numa_binding": None if world == 1 else f"each rank bound to its GPU's NUMA node (rank 0: node {numa_node})"}
         del kh, vh, DT
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------
