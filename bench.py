@@ -416,7 +416,7 @@ def run_b200(args, rank, local_rank, world):
         if world > 1:
             gkeys = engine.gather(k, gb.first_rows())
             launches[0] += 2
-            gkeys, sums = ddist.merge_partials_dense(gkeys, sums, _lib.OP_SUM)
+            gkeys, sums = ddist.merge_partials_dense(gkeys, sums, _lib.OP_SUM, key_range=(0, G - 1))   # dictionary-coded keys
             launches[0] += ddist.LAST_MERGE_LAUNCHES
             if profiling[0]:
                 _lib.profile_records(reset=True)
@@ -604,7 +604,7 @@ def run_b200(args, rank, local_rank, world):
             sums = gb.reduced(0)
             gk = engine.gather(ks, gb.first_rows())
             gb.close()
-            return ddist.merge_partials_dense(gk, sums, _lib.OP_SUM)
+            return ddist.merge_partials_dense(gk, sums, _lib.OP_SUM, key_range=(0, G - 1))
         sstep(); sstep()
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

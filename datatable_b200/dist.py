@@ -103,37 +103,44 @@ LAST_MERGE_LAUNCHES = 0        # engine kernels launched by the last merge on th
 _SUM_LIKE = (_lib.OP_SUM, _lib.OP_COUNT, _lib.OP_COUNTNA, _lib.OP_NROWS)
 
 
-def merge_partials_dense(gkeys, part, op, group=None, kernels=_EngineKernels):
+def merge_partials_dense(gkeys, part, op, group=None, kernels=_EngineKernels, key_range=None):
     """Merge every rank's (ascending group keys, SUM-like partials) through dense per-key tables that
     NCCL all-reduces in place; every rank ends with the full (keys, merged partials) lists.
 
-    One small all-reduce learns the global key range (its two scalars are the only host round trip),
-    one all-reduce sums the tables.  Falls back to `merge_partials` for MIN/MAX partials (NA partials
-    do not all-reduce) and for key ranges beyond DENSE_MAX."""
+    key_range=(kmin, kmax): the caller's bound on the group keys of ALL ranks (e.g. a dictionary-coded
+    column); without it one small all-reduce learns the global range (two scalars: the only extra host
+    round trip).  The partial table and the presence table travel in ONE all-reduce (presence as 0/1 in
+    the partials' dtype).  Falls back to `merge_partials` for MIN/MAX partials (NA partials do not
+    all-reduce) and for key ranges beyond DENSE_MAX."""
     global LAST_MERGE_LAUNCHES
     world = dist.get_world_size(group)
     if world == 1:
         LAST_MERGE_LAUNCHES = 0
         return gkeys, part
     dev = gkeys.device
-    big = torch.iinfo(torch.int64).max
-    if gkeys.numel():
-        rng = torch.stack([-gkeys[0].to(torch.int64), gkeys[-1].to(torch.int64)])
+    if key_range is not None:
+        kmin, hi = int(key_range[0]), int(key_range[1])
     else:
-        rng = torch.tensor([-big, -big], dtype=torch.int64, device=dev)
-    dist.all_reduce(rng, op=dist.ReduceOp.MAX, group=group)
-    neg_lo, hi = rng.tolist()
-    kmin = -neg_lo
+        big = torch.iinfo(torch.int64).max
+        if gkeys.numel():
+            rng = torch.stack([-gkeys[0].to(torch.int64), gkeys[-1].to(torch.int64)])
+        else:
+            rng = torch.tensor([-big, -big], dtype=torch.int64, device=dev)
+        dist.all_reduce(rng, op=dist.ReduceOp.MAX, group=group)
+        neg_lo, hi = rng.tolist()
+        kmin = -neg_lo
     span = hi - kmin + 1
     if op not in _SUM_LIKE or part.element_size() != 8 or span > DENSE_MAX or span <= 0:
         LAST_MERGE_LAUNCHES = 8
         return merge_partials(gkeys, part, op, group, kernels) if span > 0 else (gkeys, part)
     size = (span + 1023) // 1024 * 1024
-    table = torch.zeros(size, dtype=part.dtype, device=dev)
+    both = torch.zeros(2 * size, dtype=part.dtype, device=dev)        # [partials | presence], one collective
+    table = both[:size]
     present = torch.zeros(size, dtype=torch.int32, device=dev)
     kernels.dense_scatter(gkeys, part, kmin, table, present)
-    dist.all_reduce(table, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(present, op=dist.ReduceOp.SUM, group=group)
+    both[size:] = present                                             # 0 / 1 in the partials' dtype
+    dist.all_reduce(both, op=dist.ReduceOp.SUM, group=group)
+    present = (both[size:] != 0).to(torch.int32)
     LAST_MERGE_LAUNCHES = 5          # scatter + block sums + scan + compact + emit
     return kernels.dense_compact(table, present, kmin, gkeys.dtype)
 

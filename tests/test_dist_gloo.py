@@ -67,6 +67,9 @@ def _worker(rank, world, port, q):
                                       kernels=OracleKernels)
         dk, dv = ddist.merge_partials_dense(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
                                             kernels=OracleKernels)
+        rk, rv = ddist.merge_partials_dense(torch.from_numpy(gkeys), torch.from_numpy(part), _lib.OP_SUM,
+                                            kernels=OracleKernels, key_range=(0, 399))   # caller-known key range: no range collective
+        assert torch.equal(rk, dk) and torch.allclose(rv, dv, rtol=1e-12)
         # MIN partials do not all-reduce: the dense entry point must fall back to the all-gather merge
         pmin = orc.reduce(orc.MIN, v, o, f)
         nk, nv = ddist.merge_partials_dense(torch.from_numpy(gkeys), torch.from_numpy(pmin), _lib.OP_MIN,
