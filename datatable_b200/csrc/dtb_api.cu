@@ -24,7 +24,7 @@ void count_launch(int n) { t_stats.kernels_launched += n; }
 // ---------------------------------------------------------------------------
 // options (analogue of dt.options.sort.*, sort.cc:259-349)
 // ---------------------------------------------------------------------------
-static int64_t opt_radix_bits = 0;     // 0 = default (8-bit digits)
+static int64_t opt_radix_bits = 0;     // 0 = default (8-bit digits); 4..8 = largest digit width
 static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
 static thread_local int opt_trust_offsets = 0;  // internal: dtb_groupby_reduce passes the handle's own offsets to dtb_reduce
@@ -542,7 +542,6 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   int max_bits = 0;
   for (auto& r : rounds) if (r.kp.total_bits > max_bits) max_bits = r.kp.total_bits;
   const int buf_key_bytes = max_bits <= 32 ? 4 : 8;
-  // digit width: 8 bits, or 10 bits when that saves a whole pass (option "radix_bits" overrides)
 
   if (opt_verbose) {
     fprintf(stderr, "[dtb200] group: n=%lld keys=%d bits=%d rounds=%d\n", (long long)n, nkeys, kp.total_bits, nrounds);
@@ -616,12 +615,8 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     const KeyPlan& rk = rounds[ri].kp;
     const bool last_round = (ri == nrounds - 1);
     const int key_bytes = rk.total_bits <= 32 ? 4 : 8;
-    int width = (int)opt_radix_bits;
-    // Measured on C2 (20-bit keys): two 10-bit passes (1024 bins: 48 KB of tables to clear per tile,
-    // 16-byte output runs) take 24.2 ms against 19.0 ms for three 7/7/6-bit passes, so the default
-    // stays at 8-bit digits; the 1024-bin kernels remain selectable through the option.
-    if (width <= 0) width = 8;
-    if (width > 10) width = 10;
+    int width = (int)opt_radix_bits;                            // digits of at most 8 bits (256 bins), see dtb_radix.cu
+    if (width <= 0 || width > 8) width = 8;
     if (width < 4) width = 4;                                   // 64 bits / 4 = MAX_PASSES
     PassPlan pp; plan_passes(rk.total_bits, width, pp);
     const bool want_sorted_keys = last_round && groups_k && rounds[ri].has_by && !count_table;
@@ -940,7 +935,7 @@ int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream stream) {
 int dtb_set_option(const char* name, int64_t value) {
   if (!name) { set_error("option name is NULL"); return DTB_EINVAL; }
   if (!strcmp(name, "radix_bits")) {
-    if (value != 0 && (value < 4 || value > 10)) { set_error("radix_bits must be 0 (default) or 4..10"); return DTB_EINVAL; }
+    if (value != 0 && (value < 4 || value > 8)) { set_error("radix_bits must be 0 (default) or 4..8"); return DTB_EINVAL; }
     opt_radix_bits = value; return DTB_OK;
   }
   if (!strcmp(name, "verbose")) { opt_verbose = value; return DTB_OK; }

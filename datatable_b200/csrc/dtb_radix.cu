@@ -95,9 +95,11 @@ int launch_compose_keys(const KeyPlan& kp, int64_t n, const int32_t* idx, void* 
 // ===========================================================================
 // Pass geometry
 // ===========================================================================
-// Two digit widths are built: up to 8 bits (256 bins, the default) and up to 10 bits (1024 bins,
-// option "radix_bits").  Measured on 20-bit keys at n = 1e9: two 10-bit passes take 24 ms, three
-// 7/7/6-bit passes 19 ms -- the wider tables cost more shared-memory work than the pass they save.
+// Digits are at most 8 bits (256 bins).  Wider digits were built and measured twice and removed: round 1, two
+// 10-bit ballot-ranked passes over 1024 bins: 24 ms against 19 ms for three 7/7/6-bit passes on 20-bit keys at
+// n = 1e9; round 2, 1024/2048 bins ranked with shared-memory atomics: 17 ms of scatter against 11 ms
+// (profiles/r2_exp_b_wide_digits.log) -- 16-byte output runs and 16-32 KB of per-warp tables cost more LSU
+// wavefronts than the pass they save.
 constexpr int PASS_THREADS = 256;
 constexpr int PASS_IPT = 16;
 constexpr int PASS_TILE = PASS_THREADS * PASS_IPT;            // 4096 rows
@@ -269,9 +271,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, u32 parity) {
 
 template <typename KeyT, int NBINS> struct PassCfg {
   static constexpr int WARPS = PASS_THREADS / 32;
-  // 256 bins: row ids are prefetched into shared memory with cp.async; 1024 bins: the tables take that
-  // space and the row ids are read straight from global memory in the reorder phase.
-  static constexpr bool USE_RIDX = (NBINS == 256);
+  // the incoming row ids of the tile are staged in shared memory by one TMA bulk copy
+  static constexpr bool USE_RIDX = true;
   static constexpr int MINB = (sizeof(KeyT) == 4) ? 4 : 3;
   static constexpr size_t SMEM = sizeof(unsigned short) * WARPS * NBINS + sizeof(u32) * (NBINS + 4)
                                + (sizeof(KeyT) + sizeof(int32_t)) * PASS_TILE
@@ -545,14 +546,10 @@ static int run_scatter(Src src, const PassIO& io, int64_t n, int shift, u32 mask
   a.narrow = io.narrow_out;
   constexpr size_t smem = PassCfg<KeyT, NBINS>::SMEM;
   // NB = ballots per row in the rank phase = digit width, rounded up to a built variant
-  void (*kern)(const PassArgs<KeyT, Src>) = nullptr;
-  if constexpr (NBINS == 256) {
-    const int bits = __builtin_popcount(mask);
-    kern = bits <= 6 ? scatter_kernel<KeyT, Src, NBINS, MINB, 6>
-         : bits == 7 ? scatter_kernel<KeyT, Src, NBINS, MINB, 7> : scatter_kernel<KeyT, Src, NBINS, MINB, 8>;
-  } else {
-    kern = scatter_kernel<KeyT, Src, NBINS, MINB, 10>;
-  }
+  const int bits = __builtin_popcount(mask);
+  void (*kern)(const PassArgs<KeyT, Src>) =
+      bits <= 6 ? scatter_kernel<KeyT, Src, NBINS, MINB, 6>
+    : bits == 7 ? scatter_kernel<KeyT, Src, NBINS, MINB, 7> : scatter_kernel<KeyT, Src, NBINS, MINB, 8>;
   DTB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   prof_begin("radix_scatter", s);
   kern<<<(unsigned)ntiles, PASS_THREADS, smem, s>>>(a);
@@ -602,8 +599,7 @@ static int run_pass(Src src, const PassIO& io, int64_t n, int shift, int bits, u
   if (io.idx_in && (reinterpret_cast<uintptr_t>(io.idx_in) & 15)) {
     set_error("internal: row-id buffer must be 16-byte aligned"); return DTB_EINVAL;
   }
-  if (bits <= 8) return run_pass_nb<KeyT, Src, 256>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift);
-  return run_pass_nb<KeyT, Src, 1024>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift);
+  return run_pass_nb<KeyT, Src, 256>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift);
 }
 
 template <typename KeyT>
@@ -629,7 +625,7 @@ static int run_pass_raw(const PassIO& io, const KeyPlan& kp, int64_t n, int shif
 
 size_t radix_pass_work_bytes(int64_t n) {
   const size_t ntiles = (size_t)((n + PASS_TILE - 1) / PASS_TILE);
-  const size_t nbins = 1024;                            // sized for the wider digit
+  const size_t nbins = 256;
   return sizeof(u32) * ((size_t)radix_num_chunks(n) * nbins + 2 * nbins)
        + sizeof(unsigned short) * (ntiles + CHUNK_TILES) * nbins;
 }
@@ -638,7 +634,7 @@ int launch_radix_pass(const PassIO& io, const KeyPlan& kp, int key_bytes, int64_
                       int shift, int bits, uint32_t* work, uint32_t* hmax, cudaStream_t s,
                       cudaEvent_t after_counts, uint32_t* group_count, int group_shift)
 {
-  if (bits < 1 || bits > 10) { set_error("internal: digit width must be 1..10 bits"); return DTB_EINVAL; }
+  if (bits < 1 || bits > 8) { set_error("internal: digit width must be 1..8 bits"); return DTB_EINVAL; }
   if (io.src_kind == 0) {
     if (key_bytes == 4) { PackedSrc<u32> src{(const u32*)io.keys_in};
       return run_pass<u32>(src, io, n, shift, bits, work, hmax, s, after_counts, group_count, group_shift); }

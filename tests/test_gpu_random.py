@@ -346,10 +346,10 @@ def test_rows_beyond_2_pow_30():
     gb.close()
 
 
-@pytest.mark.parametrize("bits", [4, 6, 7, 8, 10])
+@pytest.mark.parametrize("bits", [4, 6, 7, 8])
 def test_digit_width_option_gives_identical_results(bits):
     """The RowIndex / offsets must not depend on the digit width of the passes (6/7/8-ballot variants of
-    the 256-bin kernel, 1024-bin kernel)."""
+    the 256-bin kernel)."""
     from datatable_b200 import engine
     from oracle import oracle as orc
     rng = np.random.default_rng(bits)
