@@ -544,10 +544,18 @@ def run_b200(args, rank, local_rank, world):
             t = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt_e2e = float(t.item())
+        # the transfer alone (same pinned buffers, same copies, no compute): the floor of this leg
+        h0 = time.perf_counter()
+        for _ in range(2):
+            kd_ = kh.cuda(non_blocking=True); vd_ = vh.cuda(non_blocking=True)
+            torch.cuda.synchronize()
+            del kd_, vd_
+        h2d_only_ms = 1e3 * (time.perf_counter() - h0) / 2
         e2e_ms = 1e3 * dt_e2e / args.e2e_steps
         line["e2e"] = {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                        "steps": args.e2e_steps,
                        "h2d_bytes_per_step": int(n * 12), "d2h_bytes_per_step": int(R.nrows * 12),
+                       "h2d_only_ms": h2d_only_ms, "h2d_GBps": n * 12 / h2d_only_ms / 1e6,
                        "api": "datatable_b200.Frame[:, sum(f.v), by(f.k)] on pinned host columns",
                        "host_numa_binding": None if world == 1 else f"each rank bound to its GPU's NUMA node (rank 0: node {numa_node})"}
         del kh, vh, DT
