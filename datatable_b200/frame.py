@@ -421,9 +421,23 @@ def _evaluate(DT, j, by_, sort_):
             # the reducers of j are known before group() runs: hand them over so that the engine can
             # overlap them with the sort (dtb_groupby_create_reduce)
             # (median / nunique read the rows sorted inside their group: evaluated after group(), below)
-            reds = [(e.op, None if e.arg is None else dcol(e.arg.name)) for e in exprs
-                    if isinstance(e, Reducer) and e.op not in _SORTED_OPS]
-            gb = engine.Groupby(keycols, flags, na_pos, reducers=reds)
+            fused = [e for e in exprs if isinstance(e, Reducer) and e.op not in _SORTED_OPS]
+            # Host frame whose value columns are still on their way over PCIe: group() first (the sort runs
+            # under the upload), the reducers afterwards through the handle, each waiting only for its own
+            # column.  Handing the reducers to group() would make the stream wait for every value column
+            # before the sort starts.  Columns with several reducers keep the fused call (bucketed multi-reducer).
+            args_pending = [e.arg.name for e in fused if e.arg is not None and e.arg.name in pending and e.arg.name not in cache]
+            per_col = {nm: sum(2 if e.op == _lib.OP_MEAN else 1 for e in fused if e.arg is not None and e.arg.name == nm)
+                       for nm in args_pending}
+            late = bool(args_pending) and all(c < 2 for c in per_col.values())
+            late_results = {}
+            if late:
+                gb = engine.Groupby(keycols, flags, na_pos)
+                for e in fused:
+                    late_results[id(e)] = gb.reduce(e.op, None if e.arg is None else dcol(e.arg.name))
+            else:
+                reds = [(e.op, None if e.arg is None else dcol(e.arg.name)) for e in fused]
+                gb = engine.Groupby(keycols, flags, na_pos, reducers=reds)
             ngroups = gb.ngroups
         else:
             order, offsets, ngroups = engine.group(keycols, flags, na_pos)
@@ -454,7 +468,7 @@ def _evaluate(DT, j, by_, sort_):
                     c = dcol(e.arg.name)                      # Median_ColumnImpl::pre_materialize_hook: sort_grouped first
                     add(name, gb.reduce_ordered(e.op, c, gb.sort_grouped(c)), _red_stype(dcol, e))
                 elif isinstance(e, Reducer):
-                    add(name, gb.reduced(ired), _red_stype(dcol, e))
+                    add(name, late_results[id(e)] if late else gb.reduced(ired), _red_stype(dcol, e))
                     ired += 1
                 else:
                     raise NotImplementedError("mixing reducers and plain columns under by() is outside the hot path")
