@@ -427,7 +427,7 @@ def _evaluate(DT, j, by_, sort_):
             # column.  Handing the reducers to group() would make the stream wait for every value column
             # before the sort starts.  Columns with several reducers keep the fused call (bucketed multi-reducer).
             args_pending = [e.arg.name for e in fused if e.arg is not None and e.arg.name in pending and e.arg.name not in cache]
-            per_col = {nm: sum(2 if e.op == _lib.OP_MEAN else 1 for e in fused if e.arg is not None and e.arg.name == nm)
+            per_col = {nm: _builtins.sum(2 if e.op == _lib.OP_MEAN else 1 for e in fused if e.arg is not None and e.arg.name == nm)
                        for nm in args_pending}
             late = bool(args_pending) and all(c < 2 for c in per_col.values())
             late_results = {}
