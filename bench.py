@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (C2 = 1e9)")
     ap.add_argument("--groups", type=int, default=1_000_000)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-rows", type=int, default=0,
                     help="rows per CPU step; 0 = the largest of 1e7/3e7/1e8/3e8/1e9 (<= --rows) whose run fits --cpu-budget")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds the whole CPU arm may take")
@@ -536,9 +536,12 @@ def run_b200(args, rank, local_rank, world):
         e2e_step()
         barrier()
         t0 = time.perf_counter()
+        e2e_each = []
         for _ in range(args.e2e_steps):
+            ts = time.perf_counter()
             R = e2e_step()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            e2e_each.append(1e3 * (time.perf_counter() - ts))
         dt_e2e = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
@@ -556,6 +559,7 @@ def run_b200(args, rank, local_rank, world):
                        "steps": args.e2e_steps,
                        "h2d_bytes_per_step": int(n * 12), "d2h_bytes_per_step": int(R.nrows * 12),
                        "h2d_only_ms": h2d_only_ms, "h2d_GBps": n * 12 / h2d_only_ms / 1e6,
+                       "ms_each_step_rank0": [round(x, 1) for x in e2e_each],
                        "api": "datatable_b200.Frame[:, sum(f.v), by(f.k)] on pinned host columns",
                        "host_numa_binding": None if world == 1 else f"each rank bound to its GPU's NUMA node (rank 0: node {numa_node})"}
         del kh, vh, DT
