@@ -404,10 +404,17 @@ def run_b200(args, rank, local_rank, world):
     main_prof = []            # profile records of the rank's own group()+reduce call (not of the merge)
     profiling = [False]
 
+    local_ev = []             # N > 1: CUDA events around every rank's own group()+reduce (the part before the merge)
+
     def step():
         # group(): RowIndex int32[n] + Groupby offsets int32[ng+1], both left in HBM behind the handle,
         # and the SUM reducer, evaluated inside the same engine call
+        if world > 1 and profiling[0]:
+            le0 = torch.cuda.Event(enable_timing=True); le0.record()
         gb = engine.Groupby([k], [0], _lib.NA_FIRST, reducers=[(_lib.OP_SUM, v)])
+        if world > 1 and profiling[0]:
+            le1 = torch.cuda.Event(enable_timing=True); le1.record()
+            local_ev.append((le0, le1))
         launches[0] += _lib.last_call_stats()["kernels_launched"]
         if profiling[0]:
             main_prof.extend(_lib.profile_records(reset=True))
@@ -451,7 +458,17 @@ def run_b200(args, rank, local_rank, world):
     engine.set_option("profile", 0)
     profiling[0] = False
     _lib.profile_records(reset=True)
+    per_rank = None
     if world > 1:
+        # every rank's own time in group()+reduce, so that the line shows how much of a step is the merge and
+        # the wait for the slowest rank (the driver computes the scaling efficiency from `value` alone)
+        mine = torch.tensor([sum(a.elapsed_time(b) for a, b in local_ev) / max(1, len(local_ev)), ms_total / args.steps],
+                            dtype=torch.float64, device="cuda")
+        allr = torch.empty(2 * world, dtype=torch.float64, device="cuda")
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.cpu().numpy().reshape(world, 2)
+        per_rank = {"local_group_reduce_ms": [round(float(x), 3) for x in allr[:, 0]],
+                    "step_ms": [round(float(x), 3) for x in allr[:, 1]]}
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
@@ -517,6 +534,8 @@ def run_b200(args, rank, local_rank, world):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
     }
+    if per_rank:
+        line["per_rank"] = per_rank
 
     # ---- e2e: public Frame API on pinned host columns ---------------------------------------
     if not args.no_e2e:

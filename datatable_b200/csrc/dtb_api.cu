@@ -28,6 +28,7 @@ static int64_t opt_radix_bits = 0;     // 0 = default (8-bit digits); 4..8 = lar
 static int64_t opt_verbose = 0;
 static int64_t opt_profile = 0;
 static thread_local int opt_trust_offsets = 0;  // internal: dtb_groupby_reduce passes the handle's own offsets to dtb_reduce
+static int64_t opt_fuse_hist = 1;      // 1 = single-column keys: statistics and the first pass's histogram from one read of the column
 static int64_t opt_stage_keys = 0;     // 1 = the first count kernel also materialises the normalised keys of a raw key column (round-1 behaviour)
 static int64_t opt_bucketed = 1;       // 1 = columns with >= 2 L2 atomics per row take the bucketed multi-reducer (dtb_bucket.cu)
 static int64_t opt_overlap = 0;        // 1 = run fused direct reducers on a side stream under the sort passes
@@ -483,7 +484,17 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     dptrs[c] = in[c].dptr;
   }
   DevBuf d_stats; DTB_TRY(d_stats.alloc(sizeof(ColStats) * nkeys, s));
-  for (int c = 0; c < nkeys; c++) {
+  // single key column: the statistics kernel also counts the low 8 bits of every tile, which becomes the first
+  // pass's histogram once edge / inc are known (no count kernel, one read of the column less)
+  const bool fuse_hist = nkeys == 1 && opt_fuse_hist && !opt_stage_keys;
+  DevBuf rawhist, rawna;
+  if (fuse_hist) {
+    DTB_TRY(rawhist.alloc(stats_hist_bytes(n), s));
+    DTB_TRY(rawna.alloc(stats_na_bytes(n), s));
+    ProfScope ps("col_stats", s);
+    DTB_TRY(launch_col_stats_hist(dptrs[0], keys[0].stype, n, d_stats.as<ColStats>(), rawhist.as<unsigned short>(),
+                                  rawna.as<unsigned short>(), s));
+  } else for (int c = 0; c < nkeys; c++) {
     ProfScope ps("col_stats", s);
     DTB_TRY(launch_col_stats(dptrs[c], keys[c].stype, n, d_stats.as<ColStats>() + c, s));
   }
@@ -662,6 +673,9 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       io.keys_in = kin;
       io.keys_stage = (p == 0 && src_kind == 1 && opt_stage_keys) ? keyA.p : nullptr;
       io.narrow_out = (p == narrow_after) ? (rk.total_bits - 32) : 0;
+      if (fuse_hist && ri == 0 && p == 0 && src_kind == 1 && pp.shift[0] == 0 && rk.k[0].cshift == 0 && rk.k[0].lshift == 0) {
+        io.raw_hist = rawhist.as<unsigned short>(); io.raw_na = rawna.as<unsigned short>();
+      }
       const int kb = (narrow_after >= 0 && p > narrow_after) ? 4 : key_bytes;   // key width this pass reads
       io.idx_in = iin;
       io.keys_out = (last && !want_sorted_keys) ? nullptr : kout;
@@ -820,19 +834,37 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       }
       if (!bcols.empty()) {
         const int nb = 1 << (dbits0 > 11 ? dbits0 - 11 : 0);
-        int maxb = 1;
-        for (auto& bc : bcols) maxb = stype_bytes(bc.stype) > maxb ? stype_bytes(bc.stype) : maxb;
+        // sweeps of up to BK_MAXCOLS columns / 32 value bytes per row (the partitioned copies live in scratch)
+        std::vector<std::pair<int, int>> sweeps;           // [first, last) into bcols
+        size_t scr = 0;
+        for (int c = 0; c < (int)bcols.size();) {
+          int e = c, bytes = 0;
+          while (e < (int)bcols.size() && e - c < BK_MAXCOLS && (e == c || bytes + stype_bytes(bcols[e].stype) <= 32))
+            bytes += stype_bytes(bcols[e++].stype);
+          const size_t need = bucket_scratch_bytes(n, bytes, e - c);
+          scr = need > scr ? need : scr;
+          sweeps.push_back({c, e});
+          c = e;
+        }
         DTB_TRY(bstart.alloc(bucket_starts_bytes(n) + sizeof(u32) * (size_t)(nb + 8), s));
-        DTB_TRY(bscr.alloc(bucket_scratch_bytes(n, maxb), s));
+        DTB_TRY(bscr.alloc(scr, s));
         if (!bxk.p) {                                  // single raw key column: its normalised keys, once
           DTB_TRY(bxk.alloc(sizeof(u32) * (size_t)n, s));
           ProfScope ps("compose_keys", s); DTB_TRY(launch_compose_keys(rounds[0].kp, n, nullptr, bxk.p, 4, s));
         }
         u32* slab_starts = bstart.as<u32>(); u32* start = slab_starts + bucket_starts_bytes(n) / sizeof(u32);
         DTB_TRY(launch_bucket_starts(bxk.as<u32>(), rounds[0].kp.group_shift, n, nb, slab_starts, start, s));
-        for (auto& bc : bcols)
-          DTB_TRY(launch_bucketed_reduce(bxk.as<u32>(), rounds[0].kp.group_shift, dbits0, bc.data, bc.stype, n, slab_starts,
-                                         start, bc.w, bscr.p, s));
+        for (auto& sw : sweeps) {
+          const void* vals[BK_MAXCOLS]; int sts[BK_MAXCOLS]; unsigned long long* words[BK_MAXCOLS][BK_NWORDS];
+          const int nc = sw.second - sw.first;
+          for (int c = 0; c < nc; c++) {
+            const BucketCol& bc = bcols[sw.first + c];
+            vals[c] = bc.data; sts[c] = bc.stype;
+            for (int w = 0; w < BK_NWORDS; w++) words[c][w] = bc.w[w];
+          }
+          DTB_TRY(launch_bucketed_reduce(bxk.as<u32>(), rounds[0].kp.group_shift, dbits0, nc, vals, sts, n, slab_starts,
+                                         start, words, bscr.p, s));
+        }
       }
     }
     for (int i = 0; i < fr->n; i++) {
@@ -943,6 +975,7 @@ int dtb_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "overlap_reducers")) { opt_overlap = value; return DTB_OK; }
   if (!strcmp(name, "bucketed_reducers")) { opt_bucketed = value ? 1 : 0; return DTB_OK; }
   if (!strcmp(name, "stage_keys")) { opt_stage_keys = value ? 1 : 0; return DTB_OK; }
+  if (!strcmp(name, "fuse_stats_hist")) { opt_fuse_hist = value ? 1 : 0; return DTB_OK; }
   if (!strcmp(name, "trim_scratch")) {
     if (t_arena.depth == 0 && t_arena.device >= 0) {
       int cur = 0; cudaGetDevice(&cur);
@@ -976,6 +1009,7 @@ int dtb_get_option(const char* name, int64_t* value) {
   if (!strcmp(name, "overlap_reducers")) { *value = opt_overlap; return DTB_OK; }
   if (!strcmp(name, "bucketed_reducers")) { *value = opt_bucketed; return DTB_OK; }
   if (!strcmp(name, "stage_keys")) { *value = opt_stage_keys; return DTB_OK; }
+  if (!strcmp(name, "fuse_stats_hist")) { *value = opt_fuse_hist; return DTB_OK; }
   set_error(std::string("unknown option ") + name);
   return DTB_EINVAL;
 }

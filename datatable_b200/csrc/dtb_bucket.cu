@@ -9,17 +9,18 @@
 //
 // When the normalised group key x spans 2^12 .. 2^20 values and no key is hot:
 //   count    : rows per bucket, bucket = x >> 11 (<= 512 buckets of 2048 consecutive keys)      [once per call]
-//   scatter  : rows of the value column are partitioned by bucket -- (x & 2047 as uint16, raw value) --
-//              tile by tile: shared-memory counters hand out the slots of a tile (order inside a bucket does
+//   scatter  : the rows of up to BK_MAXCOLS value columns are partitioned by bucket -- x & 2047 as uint16
+//              once, the raw values per column -- tile by tile: shared-memory counters hand out the slots of a tile (order inside a bucket does
 //              not matter to a reducer), one global atomic per (tile, bucket) reserves the output range,
 //              the tile is staged in shared memory and written out in bucket runs
-//   aggregate: a CTA walks a fixed-size chunk of the partitioned rows bucket by bucket, folds every
-//              requested word (int sum, float sum, count, min, max, NA count) into 2048-slot
-//              shared-memory tables and flushes the touched slots once per (chunk, bucket)
-// Bytes per row and column: read 4 (x) + V, write 2 + V, read 2 + V  (V = value bytes) -- against
+//   aggregate: a CTA walks a fixed-size chunk of the partitioned rows bucket by bucket; every 8192-row tile is
+//              counting-sorted by key in shared memory and the thread that owns a key folds its rows into
+//              registers -- every requested word (int sum, float sum, count, min, max, NA count) at once --
+//              and flushes them once per (chunk, bucket)
+// Bytes per row: read 4 (x) + sum V, write 2 + sum V, read (2 + V) per column  (V = value bytes) -- against
 // (4 + V) per reducer before; L2 atomics: ~2048 * words per 262144 rows instead of 1-2 per row.
 //
-// Bound: LSU wavefronts (shared-memory atomics with ~3.5-way bank conflicts) and HBM, about evenly.
+// Bound: LSU wavefronts (scattered shared-memory stores, ~3-way bank conflicts) and HBM, about evenly.
 #include <type_traits>
 #include "dtb_common.cuh"
 
@@ -102,18 +103,63 @@ int launch_bucket_starts(const u32* xkeys, int gshift, int64_t n, int nb, u32* h
   return DTB_OK;
 }
 
-// ---- partition one value column by bucket ---------------------------------------------------------
+// ---- partition value columns by bucket ---------------------------------------------------------------
+// All the value columns of a sweep share one rank: the rows' tile slots are computed once (shared-memory
+// counters, one reservation per (tile, bucket)), xlow is written once, and every column is then staged
+// through the same shared-memory buffer and written out in bucket runs.  (One launch per column repeated the
+// rank for every column: 7.5 ms per float64 column at 1e9 rows, profiles/r2_c4_launches_1e9.txt.)
+struct BucketCols {
+  int ncols;
+  int esz[BK_MAXCOLS];
+  const void* in[BK_MAXCOLS];
+  void* out[BK_MAXCOLS];
+};
+
 template <typename L>
-__global__ void __launch_bounds__(BK_THREADS, 3)
-bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __restrict__ v, int64_t n, int64_t slab_rows,
-                      u32* __restrict__ cursors /*[nslabs][BK_MAXB]*/, unsigned short* __restrict__ xlow_out, L* __restrict__ v_out)
+__device__ __forceinline__ void bucket_load_column(const void* v, u64 (&val)[BK_IPT], int64_t base, int tile_n) {
+#pragma unroll
+  for (int i = 0; i < BK_IPT; i++) {
+    const int p = threadIdx.x + i * BK_THREADS;
+    val[i] = p < tile_n ? (u64)reinterpret_cast<const L*>(v)[base + p] : 0ull;
+  }
+}
+__device__ __forceinline__ void bucket_load_column(int esz, const void* v, u64 (&val)[BK_IPT], int64_t base, int tile_n) {
+  switch (esz) {
+    case 1:  bucket_load_column<uint8_t>(v, val, base, tile_n); break;
+    case 2:  bucket_load_column<uint16_t>(v, val, base, tile_n); break;
+    case 4:  bucket_load_column<u32>(v, val, base, tile_n); break;
+    default: bucket_load_column<u64>(v, val, base, tile_n); break;
+  }
+}
+template <typename L>
+__device__ __forceinline__ void bucket_stage_column(unsigned char* stage, const u64 (&val)[BK_IPT], const unsigned short (&slot)[BK_IPT], int tile_n) {
+  L* sv = reinterpret_cast<L*>(stage);
+#pragma unroll
+  for (int i = 0; i < BK_IPT; i++) {
+    const int p = threadIdx.x + i * BK_THREADS;
+    if (p < tile_n) sv[slot[i]] = (L)val[i];
+  }
+}
+template <typename L>
+__device__ __forceinline__ void bucket_write_column(void* v_out, const unsigned char* stage, const u32* sx, const u32* gbase, int tile_n) {
+  const L* sv = reinterpret_cast<const L*>(stage);
+  for (int p = threadIdx.x; p < tile_n; p += BK_THREADS) reinterpret_cast<L*>(v_out)[gbase[sx[p] >> BK_BITS] + (u32)p] = sv[p];
+}
+
+// The next column's values are loaded into registers before the staged column is written out, and the
+// columns alternate between two staging buffers: one barrier per column (2 CTAs of 64 registers and 80 KB
+// per SM; 3 CTAs of 40 registers without the prefetch: 15.4 instead of 14.7 ms for C4's three columns).
+__global__ void __launch_bounds__(BK_THREADS, 2)
+bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, int64_t n, int64_t slab_rows,
+                      u32* __restrict__ cursors /*[nslabs][BK_MAXB]*/, unsigned short* __restrict__ xlow_out,
+                      const __grid_constant__ BucketCols cols, int stage_bytes)
 {
   __shared__ u32 cnt[BK_MAXB];                 // rows of the bucket in this tile; then: tile slot of its first row
   __shared__ u32 gbase[BK_MAXB];               // (reserved global slot) - (tile slot) of the bucket
   __shared__ u32 wsum[BK_THREADS / 32];
-  extern __shared__ __align__(16) unsigned char bk_stage[];      // staged tile: values, then group keys
-  L* sv = reinterpret_cast<L*>(bk_stage);
-  u32* sx = reinterpret_cast<u32*>(bk_stage + sizeof(L) * BK_TILE);
+  extern __shared__ __align__(16) unsigned char bk_stage[];      // group keys of the staged tile, then two value buffers
+  u32* sx = reinterpret_cast<u32*>(bk_stage);
+  unsigned char* stage0 = bk_stage + sizeof(u32) * BK_TILE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = (int64_t)blockIdx.x * BK_TILE;
   u32* cursor = cursors + (size_t)(base / slab_rows) * BK_MAXB;       // the slab's own reservation cursors
@@ -121,16 +167,16 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __rest
   for (int i = tid; i < BK_MAXB; i += BK_THREADS) cnt[i] = 0;
   __syncthreads();
 
-  u32 x[BK_IPT]; L val[BK_IPT]; unsigned short r[BK_IPT];
+  u32 x[BK_IPT]; unsigned short slot[BK_IPT]; u64 val[BK_IPT];
 #pragma unroll
   for (int i = 0; i < BK_IPT; i++) {
     const int p = tid + i * BK_THREADS;
     x[i] = p < tile_n ? (xkeys[base + p] >> gshift) : 0xffffffffu;
-    val[i] = p < tile_n ? v[base + p] : (L)0;
   }
+  bucket_load_column(cols.esz[0], cols.in[0], val, base, tile_n);
 #pragma unroll
   for (int i = 0; i < BK_IPT; i++)
-    r[i] = (x[i] != 0xffffffffu) ? (unsigned short)atomicAdd(&cnt[x[i] >> BK_BITS], 1u) : (unsigned short)0;
+    slot[i] = (x[i] != 0xffffffffu) ? (unsigned short)atomicAdd(&cnt[x[i] >> BK_BITS], 1u) : (unsigned short)0;
   __syncthreads();
 
   // exclusive scan of cnt[] over the buckets (one per thread), one global reservation per non-empty bucket
@@ -152,38 +198,69 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, const L* __rest
 #pragma unroll
   for (int i = 0; i < BK_IPT; i++) {
     if (x[i] != 0xffffffffu) {
-      const u32 slot = cnt[x[i] >> BK_BITS] + r[i];
-      sx[slot] = x[i]; sv[slot] = val[i];
+      slot[i] = (unsigned short)(cnt[x[i] >> BK_BITS] + slot[i]);
+      sx[slot[i]] = x[i];
     }
   }
   __syncthreads();
   for (int p = tid; p < tile_n; p += BK_THREADS) {
     const u32 xx = sx[p];
-    const u32 dst = gbase[xx >> BK_BITS] + (u32)p;
-    xlow_out[dst] = (unsigned short)(xx & (BK_KEYS - 1));
-    v_out[dst] = sv[p];
+    xlow_out[gbase[xx >> BK_BITS] + (u32)p] = (unsigned short)(xx & (BK_KEYS - 1));
+  }
+  for (int c = 0; c < cols.ncols; c++) {
+    const int esz = cols.esz[c];
+    unsigned char* stage = stage0 + (size_t)(c & 1) * stage_bytes;
+    switch (esz) {
+      case 1:  bucket_stage_column<uint8_t>(stage, val, slot, tile_n); break;
+      case 2:  bucket_stage_column<uint16_t>(stage, val, slot, tile_n); break;
+      case 4:  bucket_stage_column<u32>(stage, val, slot, tile_n); break;
+      default: bucket_stage_column<u64>(stage, val, slot, tile_n); break;
+    }
+    __syncthreads();       // also: every thread is done reading the other buffer (column c - 1)
+    if (c + 1 < cols.ncols) bucket_load_column(cols.esz[c + 1], cols.in[c + 1], val, base, tile_n);
+    switch (esz) {
+      case 1:  bucket_write_column<uint8_t>(cols.out[c], stage, sx, gbase, tile_n); break;
+      case 2:  bucket_write_column<uint16_t>(cols.out[c], stage, sx, gbase, tile_n); break;
+      case 4:  bucket_write_column<u32>(cols.out[c], stage, sx, gbase, tile_n); break;
+      default: bucket_write_column<u64>(cols.out[c], stage, sx, gbase, tile_n); break;
+    }
   }
 }
 
 // ---- aggregate ---------------------------------------------------------------------------------------
+// A CTA walks a fixed-size chunk of one partitioned column bucket by bucket, tile by tile.  Inside a tile the
+// rows are counting-sorted by their 11-bit key in shared memory (one native 32-bit shared-memory atomic per
+// row hands out the rank, one scattered store places the value); thread t then owns keys 4t..4t+3, whose rows
+// are now contiguous, and folds them into REGISTER accumulators: every requested word (int sum, float sum,
+// count, min, max, NA count) at once, no 64-bit shared-memory atomics (they are CAS loops on sm_100:
+// ATOMS.CAST.SPIN -- the first version of this kernel spent 1.85 LSU wavefronts per row in them), and the
+// valid-row count falls out of the walk.  The registers are flushed once per (chunk, bucket).
 struct BucketAcc { u64* w[BK_NWORDS]; };        // global accumulator tables, indexed by group key x (NULL = not requested)
 
+constexpr int BK_KPT = BK_KEYS / BK_THREADS;                  // 4 keys per thread
+
+constexpr int BK_AIPT = 16;                                   // rows per thread and tile (8: 7.3 ms per float64 column
+constexpr int BK_ATILE = BK_THREADS * BK_AIPT;                //  at 1e9 rows against 6.0 ms; re-reading the keys in the
+                                                              //  place phase to save registers: 8.1 ms)
 template <typename T>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(BK_THREADS, 2)
 bucket_aggregate_kernel(const unsigned short* __restrict__ xlow, const typename RawKey<T>::load_t* __restrict__ v,
-                        const u32* __restrict__ start, int nb, int64_t n, BucketAcc acc)
+                        const u32* __restrict__ start, int nb, int64_t n, const __grid_constant__ BucketAcc acc)
 {
   constexpr bool ISF = std::is_floating_point<T>::value;
-  extern __shared__ __align__(16) u64 sacc[];   // [requested word][BK_KEYS]
+  typedef typename RawKey<T>::load_t L;
+  static_assert(BK_KPT == 4, "thread t owns keys 4t..4t+3 (one uint4 of counters)");
+  extern __shared__ __align__(16) unsigned char ag_smem[];
+  L* sval = reinterpret_cast<L*>(ag_smem);                                  // the tile's values, sorted by key
+  u32* cnt = reinterpret_cast<u32*>(ag_smem + sizeof(L) * BK_ATILE);        // rows per key; then first slot of the key
+  __shared__ u32 wsum[BK_THREADS / 32];
   __shared__ int s_b;
-  u64* sw[BK_NWORDS];
-  int nw = 0;
-#pragma unroll
-  for (int w = 0; w < BK_NWORDS; w++) sw[w] = acc.w[w] ? sacc + (size_t)(nw++) * BK_KEYS : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool want_sumf = acc.w[BK_SUMF] != nullptr;
 
   const int64_t c0 = (int64_t)blockIdx.x * BK_CHUNK;
   const int64_t c1 = (c0 + BK_CHUNK < n) ? c0 + BK_CHUNK : n;
-  if (threadIdx.x == 0) {                       // bucket that holds row c0: largest b with start[b] <= c0
+  if (tid == 0) {                               // bucket that holds row c0: largest b with start[b] <= c0
     int lo = 0, hi = nb;
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((int64_t)start[mid] <= c0) lo = mid; else hi = mid; }
     s_b = lo;
@@ -194,99 +271,159 @@ bucket_aggregate_kernel(const unsigned short* __restrict__ xlow, const typename 
     if (bs >= c1) break;
     const int64_t lo = bs > c0 ? bs : c0, hi = be < c1 ? be : c1;
     if (lo >= hi) continue;
-    for (int k = threadIdx.x; k < BK_KEYS; k += blockDim.x) {
+    u64 sum_i[BK_KPT], kmin[BK_KPT], kmax[BK_KPT]; double sum_f[BK_KPT]; u32 nvalid[BK_KPT], nrows[BK_KPT];
 #pragma unroll
-      for (int w = 0; w < BK_NWORDS; w++) if (sw[w]) sw[w][k] = (w == BK_MIN) ? ~0ull : 0ull;
-    }
-    __syncthreads();
-    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      const int k = xlow[i];
-      u64 u; const bool valid = RawKey<T>::get(v[i], u);          // u: sign-extended int or float image
-      // counts are 32-bit shared-memory atomics on the low word of the slot (a chunk holds 262144 rows)
-      if (!valid) { if (sw[BK_CNTNA]) atomicAdd(reinterpret_cast<u32*>(&sw[BK_CNTNA][k]), 1u); continue; }
-      if (sw[BK_CNT]) atomicAdd(reinterpret_cast<u32*>(&sw[BK_CNT][k]), 1u);
-      if (sw[BK_SUMI]) atomicAdd(&sw[BK_SUMI][k], u);
-      if (sw[BK_SUMF]) {
-        double d;
-        if constexpr (std::is_same<T, float>::value) d = (double)__uint_as_float((u32)v[i]);
-        else if constexpr (std::is_same<T, double>::value) d = __longlong_as_double((long long)v[i]);
-        else d = (double)(int64_t)u;
-        atomicAdd(reinterpret_cast<double*>(&sw[BK_SUMF][k]), d);
+    for (int j = 0; j < BK_KPT; j++) { sum_i[j] = 0; sum_f[j] = 0.0; kmin[j] = ~0ull; kmax[j] = 0; nvalid[j] = 0; nrows[j] = 0; }
+
+    for (int64_t t0 = lo; t0 < hi; t0 += BK_ATILE) {
+      const int tile_n = (int)((hi - t0) < (int64_t)BK_ATILE ? (hi - t0) : (int64_t)BK_ATILE);
+      reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      u32 kr[BK_AIPT];                                             // key | rank << 11
+#pragma unroll
+      for (int i = 0; i < BK_AIPT; i++) {
+        const int p = tid + i * BK_THREADS;
+        kr[i] = p < tile_n ? (u32)xlow[t0 + p] : 0xffffffffu;
       }
-      if (sw[BK_MIN] || sw[BK_MAX]) {
-        const u64 key = ISF ? u : (u ^ 0x8000000000000000ull);    // same encodings as dtb_reduce.cu:p_add
-        // after the first few rows of a key most rows improve neither bound: look before the atomic
-        if (sw[BK_MIN]) { const u64 km = ISF ? key : key - 1; if (km < sw[BK_MIN][k]) atomicMin(&sw[BK_MIN][k], km); }
-        if (sw[BK_MAX]) { if (key > sw[BK_MAX][k]) atomicMax(&sw[BK_MAX][k], key); }
+#pragma unroll
+      for (int i = 0; i < BK_AIPT; i++)
+        if (kr[i] != 0xffffffffu) kr[i] |= atomicAdd(&cnt[kr[i]], 1u) << BK_BITS;
+      __syncthreads();
+      // exclusive scan over the 2048 keys: thread t owns keys 4t..4t+3
+      const uint4 c = reinterpret_cast<const uint4*>(cnt)[tid];
+      const u32 tsum = c.x + c.y + c.z + c.w;
+      u32 incl = tsum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      u32 wpre = 0;
+#pragma unroll
+      for (int w = 0; w < BK_THREADS / 32; w++) if (w < warp) wpre += wsum[w];
+      const u32 e = wpre + incl - tsum;
+      reinterpret_cast<uint4*>(cnt)[tid] = make_uint4(e, e + c.x, e + c.x + c.y, e + c.x + c.y + c.z);
+      __syncthreads();
+      // place: eight loads in flight per thread, then the scattered stores
+#pragma unroll
+      for (int h = 0; h < BK_AIPT; h += 8) {
+        L raw[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int p = tid + (h + i) * BK_THREADS;
+          raw[i] = p < tile_n ? v[t0 + p] : (L)0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (kr[h + i] != 0xffffffffu) sval[cnt[kr[h + i] & (BK_KEYS - 1)] + (kr[h + i] >> BK_BITS)] = raw[i];
       }
+      __syncthreads();
+      // walk the thread's four keys
+      u32 pos = e;
+      const u32 cj[BK_KPT] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+      for (int j = 0; j < BK_KPT; j++) {
+        nrows[j] += cj[j];
+        for (u32 q = 0; q < cj[j]; q++, pos++) {
+          const L raw = sval[pos];
+          u64 u; const bool valid = RawKey<T>::get(raw, u);       // u: sign-extended int or float image
+          if (!valid) continue;
+          nvalid[j]++;
+          if constexpr (ISF) {
+            double d;
+            if constexpr (std::is_same<T, float>::value) d = (double)__uint_as_float((u32)raw);
+            else d = __longlong_as_double((long long)raw);
+            sum_f[j] += d;
+          } else {
+            sum_i[j] += u;
+            if (want_sumf) sum_f[j] += (double)(int64_t)u;
+          }
+          const u64 key = ISF ? u : (u ^ 0x8000000000000000ull);    // same encodings as dtb_reduce.cu:p_add
+          const u64 km = ISF ? key : key - 1;
+          kmin[j] = km < kmin[j] ? km : kmin[j];
+          kmax[j] = key > kmax[j] ? key : kmax[j];
+        }
+      }
+      // no barrier here: the next tile's stores into sval sit behind two of its barriers
     }
-    __syncthreads();
-    const u64 xb = (u64)b << BK_BITS;
-    for (int k = threadIdx.x; k < BK_KEYS; k += blockDim.x) {
-      if (sw[BK_CNT])   { const u64 a = sw[BK_CNT][k];   if (a) atomicAdd(&acc.w[BK_CNT][xb + k], a); }
-      if (sw[BK_CNTNA]) { const u64 a = sw[BK_CNTNA][k]; if (a) atomicAdd(&acc.w[BK_CNTNA][xb + k], a); }
-      if (sw[BK_SUMI])  { const u64 a = sw[BK_SUMI][k];  if (a) atomicAdd(&acc.w[BK_SUMI][xb + k], a); }
-      if (sw[BK_SUMF])  { const double d = __longlong_as_double((long long)sw[BK_SUMF][k]);
-                          if (d != 0.0) atomicAdd(reinterpret_cast<double*>(acc.w[BK_SUMF]) + xb + k, d); }
-      if (sw[BK_MIN])   { const u64 a = sw[BK_MIN][k];   if (a != ~0ull) atomicMin(&acc.w[BK_MIN][xb + k], a); }
-      if (sw[BK_MAX])   { const u64 a = sw[BK_MAX][k];   if (a != 0ull)  atomicMax(&acc.w[BK_MAX][xb + k], a); }
+    const u64 xb = ((u64)b << BK_BITS) + (u64)tid * BK_KPT;
+#pragma unroll
+    for (int j = 0; j < BK_KPT; j++) {
+      if (nrows[j] == 0) continue;
+      if (acc.w[BK_CNT] && nvalid[j])              atomicAdd(&acc.w[BK_CNT][xb + j], (u64)nvalid[j]);
+      if (acc.w[BK_CNTNA] && nrows[j] != nvalid[j]) atomicAdd(&acc.w[BK_CNTNA][xb + j], (u64)(nrows[j] - nvalid[j]));
+      if (acc.w[BK_SUMI] && sum_i[j])              atomicAdd(&acc.w[BK_SUMI][xb + j], sum_i[j]);
+      if (acc.w[BK_SUMF] && sum_f[j] != 0.0)       atomicAdd(reinterpret_cast<double*>(acc.w[BK_SUMF]) + xb + j, sum_f[j]);
+      if (acc.w[BK_MIN] && kmin[j] != ~0ull)       atomicMin(&acc.w[BK_MIN][xb + j], kmin[j]);
+      if (acc.w[BK_MAX] && kmax[j] != 0ull)        atomicMax(&acc.w[BK_MAX][xb + j], kmax[j]);
     }
-    __syncthreads();
   }
 }
 
-size_t bucket_scratch_bytes(int64_t n, int value_bytes) {
-  return ((size_t)n * 2 + 255) / 256 * 256 + ((size_t)n * value_bytes + 255) / 256 * 256 + bucket_starts_bytes(n);
+static inline size_t bk_align(size_t b) { return (b + 255) / 256 * 256; }
+// scratch of one sweep: xlow u16[n] | the partitioned columns (sum_value_bytes per row) | the slabs' cursors
+size_t bucket_scratch_bytes(int64_t n, int sum_value_bytes, int ncols) {
+  return bk_align((size_t)n * 2) + (size_t)n * sum_value_bytes + 256 * (size_t)(ncols + 1) + bucket_starts_bytes(n);
 }
 size_t bucket_starts_bytes(int64_t n) { return sizeof(u32) * ((size_t)bucket_num_slabs(n) * BK_MAXB + 8); }
 
-// acc_w[w]: global table of (1 << dbits) u64 for every requested word (NULL otherwise), already set to the
-// word's identity (~0 for BK_MIN, 0 otherwise).  slab_starts / bstart: from launch_bucket_starts.
-int launch_bucketed_reduce(const u32* xkeys, int gshift, int dbits, const void* value, int stype, int64_t n,
-                           const u32* slab_starts, const u32* start, unsigned long long* const* acc_w, void* scratch,
-                           cudaStream_t s)
+// One sweep over ncols <= BK_MAXCOLS value columns: partition them by bucket (one rank for all), then fold each
+// into its accumulator tables.  acc_w[c][w]: global table of (1 << dbits) u64 for every requested word of
+// column c (NULL otherwise), already set to the word's identity (~0 for BK_MIN, 0 otherwise).
+// slab_starts / start: from launch_bucket_starts.
+int launch_bucketed_reduce(const u32* xkeys, int gshift, int dbits, int ncols, const void* const* values, const int* stypes,
+                           int64_t n, const u32* slab_starts, const u32* start, unsigned long long* const (*acc_w)[BK_NWORDS],
+                           void* scratch, cudaStream_t s)
 {
-  if (n == 0) return DTB_OK;
+  if (n == 0 || ncols == 0) return DTB_OK;
+  if (ncols > BK_MAXCOLS) { set_error("internal: too many columns in one bucket sweep"); return DTB_EINVAL; }
   const int nb = 1 << (dbits > BK_BITS ? dbits - BK_BITS : 0);
   if (nb > BK_MAXB) { set_error("internal: bucketed reducer needs a group key domain of at most 2^20"); return DTB_EINVAL; }
-  const int esz = stype_bytes(stype);
   unsigned short* xlow = (unsigned short*)scratch;
-  char* vpart = (char*)scratch + ((size_t)n * 2 + 255) / 256 * 256;
-  u32* cursor = (u32*)(vpart + ((size_t)n * esz + 255) / 256 * 256);
+  char* at = (char*)scratch + bk_align((size_t)n * 2);
+  BucketCols cols; cols.ncols = ncols;
+  int maxb = 1;
+  for (int c = 0; c < ncols; c++) {
+    const int esz = stype_bytes(stypes[c]);
+    if (!esz) { set_error("unsupported stype"); return DTB_ENOTIMPL; }
+    cols.esz[c] = esz; cols.in[c] = values[c]; cols.out[c] = at;
+    at += bk_align((size_t)n * esz);
+    maxb = esz > maxb ? esz : maxb;
+  }
+  u32* cursor = (u32*)at;
   const int64_t slab_rows = bucket_slab_rows(n);
   DTB_CUDA_CHECK(cudaMemcpyAsync(cursor, slab_starts, sizeof(u32) * (size_t)bucket_num_slabs(n) * BK_MAXB, cudaMemcpyDeviceToDevice, s));
   const unsigned tiles = (unsigned)((n + BK_TILE - 1) / BK_TILE);
-  if (esz == 8) DTB_CUDA_CHECK(cudaFuncSetAttribute(bucket_scatter_kernel<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * BK_TILE));
+  const int stage_bytes = maxb * BK_TILE;
+  const size_t sm_scatter = (size_t)4 * BK_TILE + (size_t)stage_bytes * (ncols > 1 ? 2 : 1);
+  DTB_CUDA_CHECK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * BK_TILE));
   prof_begin("bucket_scatter", s);
-  switch (esz) {
-    case 1: bucket_scatter_kernel<uint8_t><<<tiles, BK_THREADS, (sizeof(uint8_t) + 4) * BK_TILE, s>>>(xkeys, gshift, (const uint8_t*)value, n, slab_rows, cursor, xlow, (uint8_t*)vpart); break;
-    case 2: bucket_scatter_kernel<uint16_t><<<tiles, BK_THREADS, (sizeof(uint16_t) + 4) * BK_TILE, s>>>(xkeys, gshift, (const uint16_t*)value, n, slab_rows, cursor, xlow, (uint16_t*)vpart); break;
-    case 4: bucket_scatter_kernel<u32><<<tiles, BK_THREADS, (sizeof(u32) + 4) * BK_TILE, s>>>(xkeys, gshift, (const u32*)value, n, slab_rows, cursor, xlow, (u32*)vpart); break;
-    case 8: bucket_scatter_kernel<u64><<<tiles, BK_THREADS, (sizeof(u64) + 4) * BK_TILE, s>>>(xkeys, gshift, (const u64*)value, n, slab_rows, cursor, xlow, (u64*)vpart); break;
-    default: set_error("unsupported stype"); return DTB_ENOTIMPL;
-  }
-  prof_end(s);
-  count_launch();
-  BucketAcc acc; int nw = 0;
-  for (int w = 0; w < BK_NWORDS; w++) { acc.w[w] = acc_w[w]; nw += acc_w[w] != nullptr; }
-  const size_t smem = (size_t)nw * BK_KEYS * sizeof(u64);
-  const unsigned chunks = (unsigned)((n + BK_CHUNK - 1) / BK_CHUNK);
-  prof_begin("bucket_aggregate", s);
-#define DTB_AGG(T) { DTB_CUDA_CHECK(cudaFuncSetAttribute(bucket_aggregate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                     bucket_aggregate_kernel<T><<<chunks, 512, smem, s>>>(xlow, (const typename RawKey<T>::load_t*)vpart, start, nb, n, acc); }
-  switch (stype) {
-    case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_AGG(int8_t)  break;
-    case DTB_STYPE_INT16:                        DTB_AGG(int16_t) break;
-    case DTB_STYPE_INT32: case DTB_STYPE_DATE32: DTB_AGG(int32_t) break;
-    case DTB_STYPE_INT64: case DTB_STYPE_TIME64: DTB_AGG(int64_t) break;
-    case DTB_STYPE_FLOAT32:                      DTB_AGG(float)   break;
-    case DTB_STYPE_FLOAT64:                      DTB_AGG(double)  break;
-    default: set_error("unsupported stype"); return DTB_ENOTIMPL;
-  }
-#undef DTB_AGG
+  bucket_scatter_kernel<<<tiles, BK_THREADS, sm_scatter, s>>>(xkeys, gshift, n, slab_rows, cursor, xlow, cols, stage_bytes);
   prof_end(s);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
+
+  const unsigned chunks = (unsigned)((n + BK_CHUNK - 1) / BK_CHUNK);
+  for (int c = 0; c < ncols; c++) {
+    BucketAcc acc;
+    for (int w = 0; w < BK_NWORDS; w++) acc.w[w] = acc_w[c][w];
+    prof_begin("bucket_aggregate", s);
+    const size_t smem = (size_t)cols.esz[c] * BK_ATILE + sizeof(u32) * BK_KEYS;
+#define DTB_AGG(T) { DTB_CUDA_CHECK(cudaFuncSetAttribute(bucket_aggregate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                     bucket_aggregate_kernel<T><<<chunks, BK_THREADS, smem, s>>>(xlow, (const typename RawKey<T>::load_t*)cols.out[c], start, nb, n, acc); }
+    switch (stypes[c]) {
+      case DTB_STYPE_BOOL: case DTB_STYPE_INT8:    DTB_AGG(int8_t)  break;
+      case DTB_STYPE_INT16:                        DTB_AGG(int16_t) break;
+      case DTB_STYPE_INT32: case DTB_STYPE_DATE32: DTB_AGG(int32_t) break;
+      case DTB_STYPE_INT64: case DTB_STYPE_TIME64: DTB_AGG(int64_t) break;
+      case DTB_STYPE_FLOAT32:                      DTB_AGG(float)   break;
+      case DTB_STYPE_FLOAT64:                      DTB_AGG(double)  break;
+      default: set_error("unsupported stype"); return DTB_ENOTIMPL;
+    }
+#undef DTB_AGG
+    prof_end(s);
+    count_launch();
+    DTB_CUDA_CHECK(cudaGetLastError());
+  }
   return DTB_OK;
 }
 

@@ -2,11 +2,19 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 #include "dtb_internal.h"
 
 namespace dtb {
 
 constexpr int NUM_SMS_B200 = 148;
+
+// radix pass geometry (dtb_radix.cu; the fused statistics kernel of dtb_stats.cu counts by the same tiles)
+constexpr int PASS_THREADS = 256;
+constexpr int PASS_IPT = 16;
+constexpr int PASS_TILE = PASS_THREADS * PASS_IPT;            // 4096 rows
+constexpr int CHUNK_TILES = 16;
+constexpr int CHUNK_ROWS = PASS_TILE * CHUNK_TILES;           // 65536 rows per count CTA
 
 typedef unsigned long long u64;
 typedef unsigned int u32;
@@ -95,6 +103,7 @@ struct PackedSrc {
   __device__ __forceinline__ KeyT load(int64_t i) const { return p[i]; }
   __device__ __forceinline__ raw_t load_raw(int64_t i) const { return p[i]; }
   __device__ __forceinline__ KeyT norm(raw_t r) const { return r; }
+  __host__ KeyNorm key_norm() const { KeyNorm z; memset(&z, 0, sizeof(z)); return z; }   // packed keys carry no normalisation
 };
 
 // Raw column normalised on the fly.  Columns of at most 32 bits producing 32-bit keys take an
@@ -126,6 +135,7 @@ struct RawSrc {
     edge32 = (u32)kn.edge; na32 = (u32)kn.na_value; inc32 = (u32)kn.inc;
   }
   typedef typename RawKey<T>::load_t raw_t;
+  __host__ const KeyNorm& key_norm() const { return k; }
   __device__ __forceinline__ raw_t load_raw(int64_t i) const { return p[i]; }
   __device__ __forceinline__ KeyT norm(raw_t r) const {
     if constexpr (Raw32<T>::ok && sizeof(KeyT) == 4) {

@@ -49,6 +49,14 @@ struct ColStats {
 
 int launch_col_stats(const void* data, int stype, int64_t n, ColStats* d_stats,
                      cudaStream_t s);
+// The same statistics AND, from the same read of the column, the histogram of the low 8 bits of u (the
+// sign-extended integer / float image) of every 4096-row tile: tile_hist u16[ntiles][256], NA rows apart in
+// tile_na u16[ntiles].  Once edge / inc are known, the first radix pass folds it into its digit counts
+// (PassIO::raw_hist) instead of reading the column a second time.
+size_t stats_hist_bytes(int64_t n);          // bytes of tile_hist (tile_na follows, stats_na_bytes)
+size_t stats_na_bytes(int64_t n);
+int launch_col_stats_hist(const void* data, int stype, int64_t n, ColStats* d_stats, unsigned short* tile_hist,
+                          unsigned short* tile_na, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // Key normalisation parameters for one key column (restates _initB/_initI/_initF,
@@ -98,6 +106,11 @@ struct PassIO {
   int32_t*    idx_out;
   void*       keys_stage;   // src_kind 1 only, optional: buffer that receives the normalised keys in the
                             // count kernel; the scatter kernel of the pass then reads them from there
+  // first pass over a raw column whose normalisation keeps the low bits (cshift == 0): per-tile histogram of
+  // the low 8 bits of u from launch_col_stats_hist; the pass folds it (x = +-(u - edge) + inc, NA -> na_value)
+  // into its digit counts and does not run its count kernel
+  const unsigned short* raw_hist = nullptr;
+  const unsigned short* raw_na = nullptr;
   int         narrow_out = 0;     // 64-bit keys, > 0: keys_out receives (key >> narrow_out) as uint32 (later passes run on 32-bit keys)
 };
 
@@ -191,10 +204,11 @@ constexpr int BK_MAX_DBITS = 20, BK_MIN_DBITS = 12;
 // (first output slot of every slab inside every bucket), bstart u32[nb+1] (bucket boundaries)
 size_t bucket_starts_bytes(int64_t n);
 int launch_bucket_starts(const uint32_t* xkeys, int gshift, int64_t n, int nb, uint32_t* slab_starts, uint32_t* bstart, cudaStream_t s);
-size_t bucket_scratch_bytes(int64_t n, int value_bytes);
-int launch_bucketed_reduce(const uint32_t* xkeys, int gshift, int dbits, const void* value, int stype, int64_t n,
-                           const uint32_t* slab_starts, const uint32_t* bstart, unsigned long long* const* acc_w,
-                           void* scratch, cudaStream_t s);
+constexpr int BK_MAXCOLS = 4;                 // value columns partitioned in one sweep
+size_t bucket_scratch_bytes(int64_t n, int sum_value_bytes, int ncols);
+int launch_bucketed_reduce(const uint32_t* xkeys, int gshift, int dbits, int ncols, const void* const* values,
+                           const int* stypes, int64_t n, const uint32_t* slab_starts, const uint32_t* start,
+                           unsigned long long* const (*acc_w)[BK_NWORDS], void* scratch, cudaStream_t s);
 void fill_u64(unsigned long long* p, int64_t n, unsigned long long v, cudaStream_t s);
 
 int launch_gather(const void* src, int stype, int64_t nrows_src, const void* order,

@@ -100,11 +100,7 @@ int launch_compose_keys(const KeyPlan& kp, int64_t n, const int32_t* idx, void* 
 // n = 1e9; round 2, 1024/2048 bins ranked with shared-memory atomics: 17 ms of scatter against 11 ms
 // (profiles/r2_exp_b_wide_digits.log) -- 16-byte output runs and 16-32 KB of per-warp tables cost more LSU
 // wavefronts than the pass they save.
-constexpr int PASS_THREADS = 256;
-constexpr int PASS_IPT = 16;
-constexpr int PASS_TILE = PASS_THREADS * PASS_IPT;            // 4096 rows
-constexpr int CHUNK_TILES = 16;
-constexpr int CHUNK_ROWS = PASS_TILE * CHUNK_TILES;           // 65536 rows per count CTA
+// PASS_THREADS / PASS_IPT / PASS_TILE (4096 rows) / CHUNK_TILES / CHUNK_ROWS (65536 rows per count CTA): dtb_common.cuh
 
 int64_t radix_num_chunks(int64_t n) { return (n + CHUNK_ROWS - 1) / CHUNK_ROWS; }
 
@@ -160,6 +156,35 @@ count_kernel(const __grid_constant__ Src src, int64_t n, int shift, u32 mask, u3
   }
 #pragma unroll
   for (int j = 0; j < BPT; j++) counts[(size_t)blockIdx.x * NBINS + threadIdx.x + j * PASS_THREADS] = total[j];
+}
+
+// First pass over a raw column, counts from the statistics kernel's histogram of the low 8 bits of u
+// (launch_col_stats_hist): x = +-(u - edge) + inc keeps a function of those bits in its low 8 bits when no
+// constant low bits are dropped, so raw bin b lands in digit (+-(b - edge) + inc) & mask, the NA rows in
+// na_value & mask.  Same outputs as count_kernel; reads 512 bytes per tile instead of the tile's keys.
+__global__ void __launch_bounds__(256)
+fold_counts_kernel(const unsigned short* __restrict__ tile_hist, const unsigned short* __restrict__ tile_na, int64_t ntiles,
+                   u32 edge8, u32 inc8, int desc, u32 na_digit, u32 mask, u32* __restrict__ counts,
+                   unsigned short* __restrict__ tile_pre)
+{
+  __shared__ u32 dg[256];
+  const int t = threadIdx.x;
+  const int64_t t0 = (int64_t)blockIdx.x * CHUNK_TILES;
+  const int64_t t1 = (t0 + CHUNK_TILES < ntiles) ? t0 + CHUNK_TILES : ntiles;
+  const u32 d = (desc ? (edge8 - (u32)t + inc8) : ((u32)t - edge8 + inc8)) & mask;     // digit of raw bin t
+  u32 total = 0;
+  for (int64_t tile = t0; tile < t1; tile++) {
+    dg[t] = 0;
+    __syncthreads();
+    const u32 c = tile_hist[(size_t)tile * 256 + t];
+    if (c) atomicAdd(&dg[d], c);
+    if (t == 0) { const u32 na = tile_na[tile]; if (na) atomicAdd(&dg[na_digit], na); }
+    __syncthreads();
+    tile_pre[(size_t)tile * 256 + t] = (unsigned short)total;
+    total += dg[t];
+    __syncthreads();
+  }
+  counts[(size_t)blockIdx.x * 256 + t] = total;
 }
 
 // ===========================================================================
@@ -440,6 +465,9 @@ __device__ __forceinline__ void scatter_tile(const PassArgs<KeyT, Src>& a, unsig
 }
 
 // key of the sorted tile's slot q (32-bit keys are staged as (key, row id) pairs)
+// (Staging the first pass of keys below 2^20 as one word per row, key << 12 | tile position -- a 4-byte
+// scattered store instead of an 8-byte one -- was measured: +0.2 ms on EVERY pass for the extra uniform
+// branch and registers, no gain on the first.)
 template <typename KeyT>
 __device__ __forceinline__ KeyT staged_key(const KeyT* skey, int q) {
   if constexpr (sizeof(KeyT) == 4) return (KeyT)reinterpret_cast<const uint2*>(skey)[q].x;
@@ -499,24 +527,20 @@ scatter_kernel(const __grid_constant__ PassArgs<KeyT, Src> a)
       // Last pass: the tile is sorted by the full composite key (its rows arrive sorted by the lower
       // digits), so equal group keys are adjacent.  Every run of equal group keys adds its length to
       // count[group key]; the Groupby offsets are then a scan over that L2-resident table instead of a
-      // pass over 4n bytes of sorted keys.  A run [p, q] is counted as "+(q+1)" by its last row and
-      // "-p" by its first (mod 2^32): two atomics per run however many warps it spans -- one atomic
+      // pass over 4n bytes of sorted keys.  Only the run HEADS act: the row at tile slot p > 0 whose
+      // predecessor holds another key closes that run (+p) and opens its own (-p, mod 2^32); the tile's
+      // last row adds the tile length.  Two atomics per run however many warps it spans -- one atomic
       // per warp and run made few-key inputs serialise on a handful of L2 addresses.
-      const u32 NONE = 0xfffffffeu;                                 // no group key (they are < 2^22)
       const u32 x = valid ? (u32)(k >> a.group_shift) : 0xffffffffu;
       u32 xprev = __shfl_up_sync(0xffffffffu, x, 1);
-      u32 xnext = __shfl_down_sync(0xffffffffu, x, 1);
-      // the neighbour outside the warp's window (lanes 0 and 31 only); every lane loads (slot 0 when it
-      // needs nothing: a broadcast) so that no branch is needed
-      const bool need = (lane == 0 && valid && p > 0) || (lane == 31 && p + 1 < tile_n);
-      const int q = need ? ((lane == 0) ? p - 1 : p + 1) : 0;
-      u32 xb = (u32)(staged_key<KeyT>(skey, q) >> a.group_shift);
-      xb = need ? xb : NONE;
-      xprev = (lane == 0) ? xb : xprev;
-      xnext = (lane == 31) ? xb : xnext;
+      // lane 0 reads its predecessor from the staged tile; every lane loads (slot 0 when it needs nothing:
+      // a broadcast) so that no branch is needed
+      const int q = (lane == 0 && p > 0) ? p - 1 : 0;
+      const u32 xb = (u32)(staged_key<KeyT>(skey, q) >> a.group_shift);
+      xprev = (lane == 0) ? (p > 0 ? xb : x) : xprev;
       if (valid) {
-        const bool head = xprev != x, tail = xnext != x;
-        if (head || tail) atomicAdd(&a.group_count[x], (tail ? (u32)p + 1u : 0u) - (head ? (u32)p : 0u));
+        if (xprev != x) { atomicAdd(&a.group_count[x], 0u - (u32)p); atomicAdd(&a.group_count[xprev], (u32)p); }
+        if (p == tile_n - 1) atomicAdd(&a.group_count[x], (u32)tile_n);
       }
     }
     if (valid) {
@@ -572,8 +596,16 @@ static int run_pass_nb(Src src, const PassIO& io, int64_t n, int shift, int bits
   const u32 mask = (1u << bits) - 1;
 
   prof_begin("radix_count", s);
-  count_kernel<KeyT, Src, NBINS><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts,
-                                                                             (KeyT*)io.keys_stage);
+  if (io.raw_hist && (shift != 0 || io.keys_stage)) { set_error("internal: a folded histogram needs shift 0 and no key staging"); return DTB_EINVAL; }
+  if (io.raw_hist) {
+    static_assert(NBINS == 256, "the statistics kernel counts 256 bins per tile");
+    const KeyNorm& k = src.key_norm();
+    fold_counts_kernel<<<(unsigned)nchunks, 256, 0, s>>>(io.raw_hist, io.raw_na, ntiles, (u32)k.edge & 255u, (u32)k.inc & 255u,
+                                                       k.desc, (u32)k.na_value & mask, mask, counts, tile_counts);
+  } else {
+    count_kernel<KeyT, Src, NBINS><<<(unsigned)nchunks, PASS_THREADS, 0, s>>>(src, n, shift, mask, counts, tile_counts,
+                                                                               (KeyT*)io.keys_stage);
+  }
   prof_end(s);
   chunk_scan_kernel<<<NBINS, 256, 0, s>>>(counts, nchunks, NBINS, total);
   digit_base_kernel<NBINS><<<1, 256, 0, s>>>(total, base, hmax);

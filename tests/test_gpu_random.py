@@ -465,3 +465,37 @@ def test_stage_keys_option_gives_identical_results():
                 engine.set_option("stage_keys", 0)
         for a, b in zip(res[:2], res[2:]):
             assert np.array_equal(a[1], b[1]) and (a[2] is None) == (b[2] is None) and (a[2] is None or np.array_equal(a[2], b[2]))
+
+
+def test_fused_stats_histogram_gives_identical_results():
+    """Single-column keys: the statistics kernel's per-tile histogram of the low 8 bits folded into the first
+    pass's digit counts (default) against the separate count kernel (option fuse_stats_hist = 0), and both
+    against the oracle; includes keys with constant low bits (the fold does not apply) and an all-NA column."""
+    import torch
+    from datatable_b200 import engine, _lib
+    from oracle import oracle as orc
+    rng = np.random.default_rng(77)
+    n = 200_003
+    cols = [(st, make_col(rng, st, n, "wide" if st in (FLOAT32, FLOAT64) else "unit", 0.05))
+            for st in (BOOL, INT8, INT16, INT32, INT64, FLOAT32, FLOAT64)]
+    k8 = (rng.integers(-5000, 5000, n) * 8).astype(np.int32); k8[::13] = np.iinfo(np.int32).min
+    cols.append((INT32, k8))                                                     # three constant low bits
+    cols.append((INT64, np.full(n, np.iinfo(np.int64).min, dtype=np.int64)))     # all NA
+    cols.append((INT32, rng.integers(0, 1_000_000, n).astype(np.int32)))         # C2's shape: 20 bits, 7/7/6
+    for st, k in cols:
+        kd = engine.Col(torch.from_numpy(k).cuda(), st)
+        for fl, nap in (([0], _lib.NA_FIRST), ([DESCENDING], _lib.NA_LAST), ([SORT_ONLY | DESCENDING], _lib.NA_FIRST)):
+            res = []
+            for fuse in (1, 0):
+                engine.set_option("fuse_stats_hist", fuse)
+                try:
+                    o, f, ng = engine.group([kd], fl, nap)
+                    res.append((o.cpu().numpy(), None if f is None else f.cpu().numpy()))
+                finally:
+                    engine.set_option("fuse_stats_hist", 1)
+            assert np.array_equal(res[0][0], res[1][0]), (st, fl, nap)
+            assert (res[0][1] is None) == (res[1][1] is None) and (res[0][1] is None or np.array_equal(res[0][1], res[1][1]))
+            oo, of, _ = orc.group([k], fl, nap, stypes=[st])
+            assert np.array_equal(res[0][0], oo), (st, fl, nap)
+            if of is not None:
+                assert np.array_equal(res[0][1], of)
