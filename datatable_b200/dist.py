@@ -244,13 +244,35 @@ def merge_partials_alltoall(gkeys, part, op, group=None, kernels=_EngineKernels)
     return kernels.take(rk, first), merged
 
 
+def _float_image(k):
+    """Order-preserving signed-integer image of a float column: NaN (NA) first, -0.0 < +0.0 -- the order of the
+    reference's float sort (sort.cc:778-845).  Elementwise plumbing; the sorting runs on the image."""
+    it = torch.int64 if k.dtype == torch.float64 else torch.int32
+    b = k.view(it)
+    flip = torch.iinfo(it).max
+    img = torch.where(b < 0, b ^ flip, b)
+    return torch.where(torch.isnan(k), torch.full_like(img, torch.iinfo(it).min), img)
+
+
+def _float_unimage(img, dtype):
+    flip = torch.iinfo(img.dtype).max
+    b = torch.where(img < 0, img ^ flip, img)
+    out = b.view(dtype).clone()
+    out[img == torch.iinfo(img.dtype).min] = float("nan")
+    return out
+
+
 def sort_partitioned(k, row_offset, group=None, kernels=_EngineKernels):
-    """Global stable ordering of an integer key column row-partitioned over the ranks
+    """Global stable ordering of an integer or float key column row-partitioned over the ranks
     (rank r holds global rows [row_offset, row_offset + len(k))).
 
     Returns (keys, row_ids): this rank's slice of the globally sorted sequence -- rank 0 holds the
-    smallest keys -- with int64 GLOBAL row ids; concatenated over ranks this is the ARR64 RowIndex.
-    Ties keep ascending global row id (local sorts are stable, the exchange is source-rank-major)."""
+    smallest keys (NA / NaN first) -- with int64 GLOBAL row ids; concatenated over ranks this is the ARR64
+    RowIndex.  Ties keep ascending global row id (local sorts are stable, the exchange is source-rank-major).
+    Float keys travel as their order-preserving integer images."""
+    if k.dtype.is_floating_point:
+        ks, ids = sort_partitioned(_float_image(k), row_offset, group, kernels)
+        return _float_unimage(ks, k.dtype), ids
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     order = kernels.sort(k)
     ks = kernels.take(k, order)

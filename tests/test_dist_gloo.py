@@ -80,8 +80,10 @@ def _worker(rank, world, port, q):
         k64[::9] = k64[0]                             # ties across ranks: stability must hold globally
         row0 = 0 if rank == 0 else 5000
         sk, sid = ddist.sort_partitioned(torch.from_numpy(k64), row0, kernels=OracleKernels)
+        kf = rng.standard_normal(n); kf[::7] = np.nan; kf[::11] = -0.0; kf[1::11] = 0.0; kf[5] = np.inf; kf[6] = -np.inf
+        fk, fid = ddist.sort_partitioned(torch.from_numpy(kf), row0, kernels=OracleKernels)
         q.put((rank, k, v, mk.numpy(), mv.numpy(), ak.numpy(), av.numpy(), k64, sk.numpy(), sid.numpy(),
-               dk.numpy(), dv.numpy(), nk.numpy(), nv.numpy()))
+               dk.numpy(), dv.numpy(), nk.numpy(), nv.numpy(), kf, fk.numpy(), fid.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -119,3 +121,11 @@ def test_merge_partials_world2():
     got_ids = np.concatenate([r[9] for r in res]); got_keys = np.concatenate([r[8] for r in res])
     assert got_ids.dtype == np.int64
     assert np.array_equal(got_ids, want_ids) and np.array_equal(got_keys, kcat[want_ids])
+    # float keys: NaN first, -inf, ..., -0.0 < +0.0, ..., +inf; ties by global row id (the oracle's float order)
+    from oracle import oracle as orc
+    fcat = np.concatenate([r[14] for r in res])
+    want_f, _, _ = orc.group([fcat], [4], 1)                      # SORT_ONLY, NA first
+    got_fid = np.concatenate([r[16] for r in res]); got_fk = np.concatenate([r[15] for r in res])
+    assert np.array_equal(got_fid, want_f.astype(np.int64))
+    assert np.array_equal(got_fk.view(np.int64)[~np.isnan(got_fk)], fcat[want_f].view(np.int64)[~np.isnan(fcat[want_f])])
+    assert np.isnan(got_fk[:np.isnan(fcat).sum()]).all()
