@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU (C2 = 1e9)")
     ap.add_argument("--groups", type=int, default=1_000_000)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=9, help="end-to-end steps (the median step is reported, every step listed)")
     ap.add_argument("--cpu-rows", type=int, default=0,
                     help="rows per CPU step; 0 = the largest of 1e7/3e7/1e8/3e8/1e9 (<= --rows) whose run fits --cpu-budget")
     ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds the whole CPU arm may take")
@@ -539,6 +539,11 @@ def run_b200(args, rank, local_rank, world):
 
     # ---- e2e: public Frame API on pinned host columns ---------------------------------------
     if not args.no_e2e:
+        # N = 1: the pinned host columns are first-touched, and the copies issued, from the GPU's own NUMA node
+        # (as every rank does at N > 1); the affinity is restored before the CPU baseline leg takes all the cores
+        aff0 = os.sched_getaffinity(0)
+        if world == 1:
+            numa_node = bind_to_gpu_numa_node(torch, local_rank)
         kh = torch.empty(n, dtype=torch.int32, pin_memory=True); kh.copy_(k)
         vh = torch.empty(n, dtype=torch.float64, pin_memory=True); vh.copy_(v)
         torch.cuda.synchronize()
@@ -562,26 +567,41 @@ def run_b200(args, rank, local_rank, world):
             torch.cuda.synchronize()
             e2e_each.append(1e3 * (time.perf_counter() - ts))
         dt_e2e = time.perf_counter() - t0
+        steps_t = torch.tensor(e2e_each, dtype=torch.float64, device="cuda")
         if world > 1:
             t = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt_e2e = float(t.item())
-        # the transfer alone (same pinned buffers, same copies, no compute): the floor of this leg
+            dist.all_reduce(steps_t, op=dist.ReduceOp.MAX)          # a step takes as long as its slowest rank
+        e2e_each = [float(x) for x in steps_t.cpu()]
+        # the transfer alone (same pinned buffers, same copies into preallocated device buffers, no compute):
+        # the floor of this leg
+        kd_ = torch.empty(n, dtype=torch.int32, device="cuda"); vd_ = torch.empty(n, dtype=torch.float64, device="cuda")
+        kd_.copy_(kh, non_blocking=True); torch.cuda.synchronize()
         h0 = time.perf_counter()
         for _ in range(2):
-            kd_ = kh.cuda(non_blocking=True); vd_ = vh.cuda(non_blocking=True)
+            kd_.copy_(kh, non_blocking=True); vd_.copy_(vh, non_blocking=True)
             torch.cuda.synchronize()
-            del kd_, vd_
         h2d_only_ms = 1e3 * (time.perf_counter() - h0) / 2
-        e2e_ms = 1e3 * dt_e2e / args.e2e_steps
+        del kd_, vd_
+        # The boxes of this pool share their host (memory, PCIe root) with other tenants: single steps take 1.5-9x
+        # as long with nothing of ours running but the upload (scripts/e2e_timeline.py: the key column alone 159 ms
+        # instead of 73).  The figure is the MEDIAN step; the mean and every step's time are reported beside it.
+        e2e_mean_ms = 1e3 * dt_e2e / args.e2e_steps
+        e2e_ms = sorted(e2e_each)[len(e2e_each) // 2]
         line["e2e"] = {"value": world * n / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                       "estimator": "median step (max over ranks per step)", "mean_ms_per_step": e2e_mean_ms,
+                       "value_from_mean": world * n / (e2e_mean_ms / 1e3),
                        "steps": args.e2e_steps,
                        "h2d_bytes_per_step": int(n * 12), "d2h_bytes_per_step": int(R.nrows * 12),
                        "h2d_only_ms": h2d_only_ms, "h2d_GBps": n * 12 / h2d_only_ms / 1e6,
-                       "ms_each_step_rank0": [round(x, 1) for x in e2e_each],
+                       "ms_each_step": [round(x, 1) for x in e2e_each],
                        "api": "datatable_b200.Frame[:, sum(f.v), by(f.k)] on pinned host columns",
-                       "host_numa_binding": None if world == 1 else f"each rank bound to its GPU's NUMA node (rank 0: node {numa_node})"}
+                       "host_numa_binding": (f"bound to the GPU's NUMA node {numa_node} for this leg" if world == 1 else
+                                             f"each rank bound to its GPU's NUMA node (rank 0: node {numa_node})")}
         del kh, vh, DT
+        if world == 1:
+            os.sched_setaffinity(0, aff0)
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) ---------------------------
     # The reference's default sort collapses between 1e7 and 3e7 rows (on this pool's boxes

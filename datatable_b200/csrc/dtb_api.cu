@@ -939,6 +939,16 @@ struct dtb_groupby {
   std::vector<void*> reduced; // outputs of the reducers evaluated by dtb_groupby_create_reduce
 };
 
+// A reducer fed piecewise (dtb_groupby_reduce_begin / _add / _end): the accumulator tables live across calls.
+struct dtb_reduce_state {
+  dtb_groupby* g = nullptr;
+  int op = 0, stype = 0, out_stype = 0;
+  void* acc = nullptr;        // device u64[2 * table]
+  void* dmap = nullptr;       // plan_direct's map (shared-memory table / hot-key modes)
+  dtb::DirectPlan dp;
+  int64_t rows_added = 0;
+};
+
 extern "C" {
 
 const char* dtb_last_error(void) { return t_error.c_str(); }
@@ -1231,6 +1241,85 @@ int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_valu
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
   }
   return DTB_OK;
+}
+
+int dtb_groupby_reduce_begin(dtb_groupby* g, int op, int value_stype, dtb_stream stream, dtb_reduce_state** out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!g || !out) { set_error("groupby handle / out is NULL"); return DTB_EINVAL; }
+  *out = nullptr;
+  if (g->ngroups < 0) { set_error("the handle holds no Groupby (sort-only call)"); return DTB_EINVAL; }
+  if (!g->direct || op < DTB_OP_SUM || op >= DTB_OP_NROWS) {
+    set_error("piecewise reducers exist for the streaming path only (small key domain, device key columns, sum..countna)");
+    return DTB_ENOTIMPL;
+  }
+  const int out_st = reduce_out_stype_host(op, value_stype);
+  if (!out_st) {
+    set_error("Invalid column of stype " + std::to_string(value_stype) + " in reducer " + std::to_string(op));
+    return stype_supported(value_stype) ? DTB_EINVAL : DTB_ENOTIMPL;
+  }
+  DTB_TRY(ensure_context());
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  dtb_reduce_state* st = new dtb_reduce_state();
+  st->g = g; st->op = op; st->stype = value_stype; st->out_stype = out_st;
+  const size_t acc_bytes = sizeof(u64) * (size_t)g->table * 2, map_bytes = direct_map_bytes(g->table);
+  if (cudaMalloc(&st->acc, acc_bytes ? acc_bytes : 8) != cudaSuccess || cudaMalloc(&st->dmap, map_bytes ? map_bytes : 8) != cudaSuccess) {
+    cudaGetLastError(); cudaFree(st->acc); delete st; set_error("out of device memory"); return DTB_ENOMEM;
+  }
+  int rc = DTB_OK;
+  if (g->ngroups > 0) {
+    rc = plan_direct(g->table, (const uint32_t*)g->gkeys, (const int32_t*)g->offsets, g->ngroups, g->nrows, g->gmax, st->dmap, s, st->dp);
+    if (rc == DTB_OK) rc = launch_direct_init(op, st->dp, g->table, (u64*)st->acc, (u64*)st->acc + g->table, s);
+  }
+  if (rc != DTB_OK) { cudaFree(st->acc); cudaFree(st->dmap); delete st; return rc; }
+  *out = st;
+  return DTB_OK;
+}
+
+int dtb_groupby_reduce_add(dtb_reduce_state* st, const void* value_rows, int64_t row0, int64_t nrows, dtb_stream stream)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!st || !st->g) { set_error("reducer state is NULL"); return DTB_EINVAL; }
+  dtb_groupby* g = st->g;
+  if (row0 < 0 || nrows < 0 || row0 + nrows > g->nrows) { set_error("row range outside the frame"); return DTB_EINVAL; }
+  if (nrows == 0 || g->ngroups == 0) return DTB_OK;
+  if (!value_rows || !is_device_ptr(value_rows)) { set_error("piecewise reducers take device rows"); return DTB_EINVAL; }
+  KeyPlan kp = g->kp;                               // the key columns, advanced to row0
+  for (int c = 0; c < kp.nkeys; c++)
+    kp.k[c].data = (const char*)kp.k[c].data + (size_t)row0 * stype_bytes(kp.k[c].stype);
+  ProfScope ps("reduce_direct", s);
+  DTB_TRY(launch_direct_accumulate_rows(st->op, kp, st->dp, value_rows, st->stype, nrows, g->table,
+                                        (u64*)st->acc, (u64*)st->acc + g->table, s));
+  st->rows_added += nrows;
+  return DTB_OK;
+}
+
+int dtb_groupby_reduce_end(dtb_reduce_state* st, dtb_stream stream, void* out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!st || !st->g) { set_error("reducer state is NULL"); return DTB_EINVAL; }
+  dtb_groupby* g = st->g;
+  int rc = DTB_OK;
+  if (g->ngroups > 0) {
+    if (!out) { set_error("out is NULL"); rc = DTB_EINVAL; }
+    else if (st->rows_added != g->nrows) { set_error("the pieces do not cover the frame's rows exactly once"); rc = DTB_EINVAL; }
+    else {
+      ArenaScope scope(s);
+      rc = scope.rc;
+      DevOut d_out;
+      if (rc == DTB_OK) rc = d_out.bind(out, (size_t)g->ngroups * stype_bytes(st->out_stype), s);
+      if (rc == DTB_OK)
+        rc = launch_direct_finalize(st->op, st->stype, (const u64*)st->acc, (const u64*)st->acc + g->table,
+                                    (st->dp.kind == DIRECT_SMALL && st->dp.map) ? nullptr : (const uint32_t*)g->gkeys,
+                                    g->ngroups, d_out.dptr, s);
+      if (rc == DTB_OK && d_out.staged()) rc = d_out.finish((size_t)g->ngroups * stype_bytes(st->out_stype), s);
+      if (rc == DTB_OK && cudaStreamSynchronize(s) != cudaSuccess) { set_error("cudaStreamSynchronize failed"); rc = DTB_ECUDA; }
+    }
+  }
+  if (rc != DTB_OK) cudaStreamSynchronize(s);       // the tables may still be in use
+  cudaFree(st->acc); cudaFree(st->dmap);
+  delete st;
+  return rc;
 }
 
 int dtb_gather(dtb_col src, int64_t nrows_src, const void* order, int order_is64, int64_t n,

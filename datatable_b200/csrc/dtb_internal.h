@@ -190,6 +190,9 @@ int launch_direct_accumulate(int op, const KeyPlan& kp, const DirectPlan& dp,
                              const void* value, int stype, int64_t n, int64_t table,
                              unsigned long long* acc0, unsigned long long* acc1, cudaStream_t s);
 // gkeys == NULL: the accumulators are indexed by group (dense-mapped small table).
+int launch_direct_init(int op, const DirectPlan& dp, int64_t table, unsigned long long* acc0, unsigned long long* acc1, cudaStream_t s);
+int launch_direct_accumulate_rows(int op, const KeyPlan& kp, const DirectPlan& dp, const void* value, int stype, int64_t n,
+                                  int64_t table, unsigned long long* acc0, unsigned long long* acc1, cudaStream_t s);
 int launch_direct_finalize(int op, int stype, const unsigned long long* acc0, const unsigned long long* acc1,
                            const uint32_t* gkeys, int64_t ngroups, void* out, cudaStream_t s);
 int launch_nrows(const int32_t* offsets, int64_t ngroups, void* out, cudaStream_t s);

@@ -786,15 +786,31 @@ int launch_direct_accumulate(int op, const KeyPlan& kp, const DirectPlan& dp,
                              const void* value, int stype, int64_t n, int64_t table,
                              u64* acc0, u64* acc1, cudaStream_t s)
 {
-  const int out_st = reduce_out_stype(op, stype);
-  if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
-  t_dp = dp;
+  DTB_TRY(launch_direct_init(op, dp, table, acc0, acc1, s));
+  return launch_direct_accumulate_rows(op, kp, dp, value, stype, n, table, acc0, acc1, s);
+}
+
+// the accumulator tables' identities (once per reducer; the rows may then arrive in pieces)
+int launch_direct_init(int op, const DirectPlan& dp, int64_t table, u64* acc0, u64* acc1, cudaStream_t s)
+{
   if (dp.kind == DIRECT_SMALL) table = dp.nslots;                // only the used accumulators are initialised
   const int tgrid = (int)((table + 255) / 256 > NUM_SMS_B200 * 8 ? NUM_SMS_B200 * 8 : (table + 255) / 256);
   fill_u64_kernel<<<tgrid, 256, 0, s>>>(acc0, table, (op == DTB_OP_MIN) ? ~0ull : 0ull);
   count_launch();
   if (op == DTB_OP_MEAN) { fill_u64_kernel<<<tgrid, 256, 0, s>>>(acc1, table, 0ull); count_launch(); }
   DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+// folds n rows (kp's key columns and `value`, both starting at the piece's first row) into the tables
+int launch_direct_accumulate_rows(int op, const KeyPlan& kp, const DirectPlan& dp,
+                                  const void* value, int stype, int64_t n, int64_t table,
+                                  u64* acc0, u64* acc1, cudaStream_t s)
+{
+  const int out_st = reduce_out_stype(op, stype);
+  if (!out_st) { set_error("Invalid column type in reducer"); return DTB_EINVAL; }
+  t_dp = dp;
+  (void)table;
   if (n > 0) {
     int rc;
     if (kp.nkeys == 1) {

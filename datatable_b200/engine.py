@@ -209,6 +209,31 @@ class Groupby:
         check(lib.dtb_groupby_reduce(self._h, op, v.c(), v.nrows, _stream(), ctypes.c_void_p(optr)))
         return out
 
+    def reduce_pieces(self, op, stype, pieces):
+        """The reducer fed piecewise (dtb_groupby_reduce_begin / _add / _end).  pieces: [(CUDA tensor with rows
+        [row0, row0 + len), row0, CUDA event to wait for or None), ...] covering every row once.  Returns the result
+        (CUDA tensor) or None when the handle has no streaming path for this reducer (use reduce())."""
+        out_st = lib.dtb_reduce_out_stype(op, stype)
+        if not out_st:
+            raise _lib.DtbValueError(f"Invalid column of stype {stype} in reducer {op}")
+        st = ctypes.c_void_p(0)
+        rc = lib.dtb_groupby_reduce_begin(self._h, op, stype, _stream(), ctypes.byref(st))
+        if rc == _lib.ENOTIMPL:
+            return None
+        check(rc)
+        cur = torch.cuda.current_stream()
+        try:
+            for t, row0, ev in pieces:
+                if ev is not None:
+                    cur.wait_event(ev)
+                check(lib.dtb_groupby_reduce_add(st, ctypes.c_void_p(t.data_ptr()), int(row0), t.numel(), _stream()))
+        except Exception:
+            lib.dtb_groupby_reduce_end(st, _stream(), None)          # frees the state
+            raise
+        out = torch.empty(max(self.ngroups, 0), dtype=_torch_dtype(out_st), device="cuda")
+        check(lib.dtb_groupby_reduce_end(st, _stream(), ctypes.c_void_p(out.data_ptr())))
+        return out
+
     def reduced(self, i):
         """Result of the i-th reducer passed to the constructor (CUDA tensor, ngroups elements)."""
         op, out_st, _ = self._red[i]

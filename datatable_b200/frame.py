@@ -349,6 +349,22 @@ def _from_list(lst):
     return np.array([np.nan if x is None else float(x) for x in lst], dtype=np.float64), FLOAT64
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream():
+    """One upload stream per device for the life of the process.  torch's caching allocator keeps freed blocks per
+    stream: a fresh stream per query (the first version) could never reuse the previous query's staging buffers and
+    cudaMalloc'ed every uploaded column again (12 GB per C2 query until the device was full)."""
+    dev = torch.cuda.current_device()
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream()
+    return _COPY_STREAMS[dev]
+
+
+_PIECE_BYTES = 1 << 30        # host value columns of >= 2 GB are uploaded (and reduced) in 1 GB pieces
+
+
 def _evaluate(DT, j, by_, sort_):
     """EvalContext::evaluate (eval_context.cc:144-172) for the hot-path shapes."""
     # Host columns are uploaded once (pinned memory -> DMA), the whole query then runs on
@@ -372,16 +388,34 @@ def _evaluate(DT, j, by_, sort_):
             needed.append(nm)
     copy_stream = None
     pending = {}
+    pieces = {}               # large value columns travel in pieces, each with its own event (see the late path)
+    keynames = set()
+    for m in (by_, sort_):
+        if m is not None:
+            keynames.update(r.name for r in m.cols)
     for nm in dict.fromkeys(needed):
         c = DT._col(nm)
         t = c.data if engine.is_tensor(c.data) else torch.from_numpy(c.data)
         if t.is_cuda:
             continue
         if copy_stream is None:
-            copy_stream = torch.cuda.Stream()
+            copy_stream = _copy_stream()
+            copy_stream.wait_stream(torch.cuda.current_stream())    # buffers freed by earlier queries are reused in order
         with torch.cuda.stream(copy_stream):
-            d = t.cuda(non_blocking=True)                           # pinned host memory -> async DMA
-            ev = torch.cuda.Event(); ev.record(copy_stream)
+            if nm not in keynames and t.dim() == 1 and t.numel() * t.element_size() >= _PIECE_BYTES * 2:
+                d = torch.empty_like(t, device="cuda")
+                step = _builtins.max(1, _PIECE_BYTES // t.element_size())
+                pcs = []
+                for a in range(0, t.numel(), step):
+                    b = _builtins.min(a + step, t.numel())
+                    d[a:b].copy_(t[a:b], non_blocking=True)
+                    pev = torch.cuda.Event(); pev.record(copy_stream)
+                    pcs.append((a, b, pev))
+                pieces[nm] = pcs
+                ev = pcs[-1][2]
+            else:
+                d = t.cuda(non_blocking=True)                       # pinned host memory -> async DMA
+                ev = torch.cuda.Event(); ev.record(copy_stream)
         pending[nm] = (engine.Col(d, c.stype), ev)
 
     def dcol(name):
@@ -431,10 +465,27 @@ def _evaluate(DT, j, by_, sort_):
                        for nm in args_pending}
             late = bool(args_pending) and all(c < 2 for c in per_col.values())
             late_results = {}
+            early_keys = None
             if late:
                 gb = engine.Groupby(keycols, flags, na_pos)
+                # the group-key columns of the result (first row of every group, gathered, brought to the host)
+                # depend on group() alone: done now, under the upload of the value columns
+                first = gb.first_rows()
+                early_keys = []
+                for ref in by_.cols:
+                    c = dcol(ref.name)
+                    g_ = engine.gather(c, first)
+                    early_keys.append((ref.name, g_.cpu().numpy() if host_frame and engine.is_tensor(g_) else g_, c.stype))
                 for e in fused:
-                    late_results[id(e)] = gb.reduce(e.op, None if e.arg is None else dcol(e.arg.name))
+                    nm_ = None if e.arg is None else e.arg.name
+                    res_ = None
+                    if nm_ in pieces and nm_ not in cache:
+                        # fold every piece of the column as soon as it has arrived (dtb_groupby_reduce_add): after
+                        # the last byte only the last piece's share of the reducer is left
+                        col_ = pending[nm_][0]
+                        col_.data.record_stream(torch.cuda.current_stream())
+                        res_ = gb.reduce_pieces(e.op, col_.stype, [(col_.data[a:b], a, pev) for a, b, pev in pieces[nm_]])
+                    late_results[id(e)] = res_ if res_ is not None else gb.reduce(e.op, None if nm_ is None else dcol(nm_))
             else:
                 reds = [(e.op, None if e.arg is None else dcol(e.arg.name)) for e in fused]
                 gb = engine.Groupby(keycols, flags, na_pos, reducers=reds)
@@ -458,10 +509,14 @@ def _evaluate(DT, j, by_, sort_):
     if by_ is not None:
         if has_reducer:
             # group keys = first row of every group (get_group_rowindex, eval_context.cc:124-135)
-            first = gb.first_rows()
-            for ref in by_.cols:
-                c = dcol(ref.name)
-                add(ref.name, engine.gather(c, first), c.stype)
+            if early_keys is not None:
+                for nm_, data_, st_ in early_keys:
+                    add(nm_, data_, st_)
+            else:
+                first = gb.first_rows()
+                for ref in by_.cols:
+                    c = dcol(ref.name)
+                    add(ref.name, engine.gather(c, first), c.stype)
             ired = 0
             for name, e in zip(names, exprs):
                 if isinstance(e, Reducer) and e.op in _SORTED_OPS:

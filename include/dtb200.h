@@ -224,6 +224,23 @@ DTB_API int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nr
                        dtb_stream stream, void* out);
 
 /*
+ * The same reducer fed piecewise: the value column arrives in row ranges (e.g. the chunks of a host
+ * column on their way over PCIe, each folded as soon as it is in HBM -- the reference's reducers,
+ * column/sumprod.h / minmax.h / count.h, need the whole column before they start).  Streaming path only
+ * (see dtb_groupby_reduce: small key domain, device key columns) and DTB_OP_SUM .. DTB_OP_COUNTNA;
+ * otherwise _begin returns DTB_ENOTIMPL and the caller uses dtb_groupby_reduce on the whole column.
+ *   _begin : allocates and initialises the accumulator tables
+ *   _add   : value_rows = DEVICE pointer to rows [row0, row0 + nrows) of the value column, enqueued on `stream`
+ *            (the caller orders it after the piece's upload); every row exactly once over all calls
+ *   _end   : finalises into out (host or device, ngroups elements of dtb_reduce_out_stype) and frees the state
+ *            (also on error).  Results as dtb_groupby_reduce.
+ */
+typedef struct dtb_reduce_state dtb_reduce_state;
+DTB_API int dtb_groupby_reduce_begin(dtb_groupby* g, int op, int value_stype, dtb_stream stream, dtb_reduce_state** out);
+DTB_API int dtb_groupby_reduce_add(dtb_reduce_state* st, const void* value_rows, int64_t row0, int64_t nrows, dtb_stream stream);
+DTB_API int dtb_groupby_reduce_end(dtb_reduce_state* st, dtb_stream stream, void* out);
+
+/*
  * dtb_gather -- replaces materialisation of ArrayView_ColumnImpl<int32/int64>
  * (column/view.cc:88-155): out[i] = order[i] < 0 ? NA : src[order[i]].
  */

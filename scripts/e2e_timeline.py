@@ -13,11 +13,17 @@ vh = torch.empty(n, dtype=torch.float64, pin_memory=True); vh.copy_(v)
 del k, v
 torch.cuda.synchronize()
 DT = dtb.Frame(k=kh, v=vh)
-for it in range(3):
+def alloc_stats():
+    st = torch.cuda.memory_stats()
+    return st.get("num_device_alloc", 0), st.get("num_device_free", 0), st.get("num_alloc_retries", 0)
+for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 12):
+    a0 = alloc_stats()
     torch.cuda.synchronize(); t0 = time.perf_counter()
     R = DT[:, dtb.sum(f.v), by(f.k)]
     torch.cuda.synchronize(); t1 = time.perf_counter()
-    print(f"Frame API: {1e3*(t1-t0):.1f} ms", flush=True)
+    a1 = alloc_stats()
+    print(f"Frame API: {1e3*(t1-t0):.1f} ms   torch cudaMalloc/cudaFree/retries during the call: {a1[0]-a0[0]}/{a1[1]-a0[1]}/{a1[2]-a0[2]}"
+          f"   reserved {torch.cuda.memory_reserved()/2**30:.1f} GiB", flush=True)
 # manual pipeline with events
 for it in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
