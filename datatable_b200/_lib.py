@@ -24,7 +24,7 @@ EXPORTS = [
     "dtb_last_error", "dtb_abi_version", "dtb_stype_size", "dtb_reduce_out_stype", "dtb_init",
     "dtb_group", "dtb_group64", "dtb_groupby_create", "dtb_groupby_create_reduce", "dtb_groupby_reduced", "dtb_groupby_norder", "dtb_groupby_ngroups",
     "dtb_groupby_order", "dtb_groupby_offsets", "dtb_groupby_destroy", "dtb_groupby_reduce", "dtb_reduce",
-    "dtb_groupby_reduce_begin", "dtb_groupby_reduce_add", "dtb_groupby_reduce_end",
+    "dtb_groupby_reduce_begin", "dtb_groupby_reduce_add", "dtb_groupby_reduce_end", "dtb_slice_groups",
     "dtb_gather", "dtb_memcpy", "dtb_set_option", "dtb_get_option", "dtb_last_call_stats",
     "dtb_profile_count", "dtb_profile_get", "dtb_profile_reset",
     "dtb_dense_scatter", "dtb_dense_compact",
@@ -106,6 +106,8 @@ def _load():
     lib.dtb_groupby_reduce_begin.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p, c.POINTER(c.c_void_p)]
     lib.dtb_groupby_reduce_add.argtypes = [c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_void_p]
     lib.dtb_groupby_reduce_end.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.dtb_slice_groups.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int64, c.c_int64, c.c_void_p, c.c_void_p, c.c_int64,
+                                     c.c_void_p, c.POINTER(c.c_int64), c.POINTER(c.c_int64)]
     lib.dtb_reduce.argtypes = [c.c_int, dtb_col, c.c_int64, c.c_void_p, c.c_int, c.c_void_p,
                                c.c_int64, c.c_void_p, c.c_void_p]
     lib.dtb_gather.argtypes = [dtb_col, c.c_int64, c.c_void_p, c.c_int, c.c_int64, c.c_void_p, c.c_void_p]

@@ -1497,6 +1497,67 @@ int dtb_largest_group(const void* offsets, int64_t ngroups, int64_t skip, dtb_st
   return DTB_OK;
 }
 
+int dtb_slice_groups(const void* offsets, int64_t ngroups, int64_t start, int64_t stop, int64_t step,
+                     dtb_stream stream, void* rows_out, int64_t rows_capacity, void* offsets_out,
+                     int64_t* ngroups_out, int64_t* nrows_out)
+{
+  cudaStream_t s = (cudaStream_t)stream;
+  t_stats = dtb_call_stats{0, 0, 0, 0, 0};
+  if (!ngroups_out || !nrows_out || ngroups < 0 || rows_capacity < 0) { set_error("bad dtb_slice_groups arguments"); return DTB_EINVAL; }
+  *ngroups_out = 0; *nrows_out = 0;
+  if (ngroups > 0 && (!offsets || !offsets_out)) { set_error("offsets / offsets_out is NULL"); return DTB_EINVAL; }
+  if (step == DTB_SLICE_NA) step = 1;                                   // fexpr_literal_sliceint.cc:86
+  if (step != (int64_t)(int32_t)step) { set_error("slice step does not fit int32"); return DTB_EINVAL; }
+  if (step == 0 && (start == DTB_SLICE_NA || stop == DTB_SLICE_NA || stop <= 0 || stop > (int64_t)INT32_MAX)) {
+    set_error("a slice with step 0 needs a start and a positive count"); return DTB_EINVAL;    // the reference asserts it (:150-152)
+  }
+  DTB_TRY(ensure_context());
+  ArenaScope scope(s); if (scope.rc != DTB_OK) return scope.rc;
+  if (ngroups == 0) {
+    if (offsets_out) {
+      DevOut z; DTB_TRY(z.bind(offsets_out, sizeof(int32_t), s));
+      DTB_CUDA_CHECK(cudaMemsetAsync(z.dptr, 0, sizeof(int32_t), s));
+      DTB_TRY(z.finish(sizeof(int32_t), s));
+      DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+    }
+    return DTB_OK;
+  }
+  DevIn d_off; DTB_TRY(d_off.bind(offsets, sizeof(int32_t) * (size_t)(ngroups + 1), s));
+  DevOut d_oo; DTB_TRY(d_oo.bind(offsets_out, sizeof(int32_t) * (size_t)(ngroups + 1), s));
+  int32_t h_last = 0;                                                   // rows of the grouped frame
+  DTB_CUDA_CHECK(cudaMemcpyAsync(&h_last, (const int32_t*)d_off.dptr + ngroups, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  SliceParams p;
+  p.has_start = start != DTB_SLICE_NA; p.has_stop = stop != DTB_SLICE_NA;
+  p.start = p.has_start ? start : 0; p.stop = p.has_stop ? stop : 0; p.step = step; p.nrows = (long long)(u32)h_last;
+  DevBuf scr, gsel, tot;
+  DTB_TRY(scr.alloc(slice_scratch_bytes(ngroups), s));
+  DTB_TRY(gsel.alloc(sizeof(int32_t) * (size_t)ngroups, s));
+  DTB_TRY(tot.alloc(2 * sizeof(u64), s));
+  DTB_TRY(launch_slice_groups_plan((const int32_t*)d_off.dptr, ngroups, p, scr.p, (int32_t*)d_oo.dptr, gsel.as<int32_t>(),
+                                   tot.as<u64>(), s));
+  u64 h_tot[2] = {0, 0};
+  DTB_CUDA_CHECK(cudaMemcpyAsync(h_tot, tot.p, sizeof(h_tot), cudaMemcpyDeviceToHost, s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int64_t nout = (int64_t)h_tot[0], ng_out = (int64_t)h_tot[1];
+  *nrows_out = nout; *ngroups_out = ng_out;
+  if (nout > (int64_t)INT32_MAX) { set_error("the slice selects more than INT32_MAX rows"); return DTB_ENOTIMPL; }
+  if (nout > rows_capacity) { set_error("rows_out is too small: " + std::to_string(nout) + " rows selected"); return DTB_ENOSPACE; }
+  const int32_t h_end = (int32_t)nout;
+  DTB_CUDA_CHECK(cudaMemcpyAsync((int32_t*)d_oo.dptr + ng_out, &h_end, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  if (nout > 0) {
+    if (!rows_out) { set_error("rows_out is NULL"); return DTB_EINVAL; }
+    DevOut d_rows; DTB_TRY(d_rows.bind(rows_out, sizeof(int32_t) * (size_t)nout, s));
+    DevBuf gid; DTB_TRY(gid.alloc(sizeof(int32_t) * (size_t)nout, s));
+    DTB_TRY(launch_slice_groups_emit((const int32_t*)d_off.dptr, p, (const int32_t*)d_oo.dptr, gsel.as<int32_t>(), ng_out, nout,
+                                     gid.as<int32_t>(), (int32_t*)d_rows.dptr, s));
+    DTB_TRY(d_rows.finish(sizeof(int32_t) * (size_t)nout, s));
+  }
+  DTB_TRY(d_oo.finish(sizeof(int32_t) * (size_t)(ng_out + 1), s));
+  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  return DTB_OK;
+}
+
 int dtb_join(const dtb_col* xkeys, const dtb_col* jkeys, int nkeys, int64_t nrows_x, int64_t nrows_j,
              dtb_stream stream, void* index_out)
 {

@@ -226,6 +226,13 @@ int launch_widen_u32(const uint32_t* in, int64_t n, int64_t* out, cudaStream_t s
 int launch_firstlast(const void* v, int stype, int64_t nv, const int32_t* order, const int32_t* offsets,
                      int64_t ng, int last, void* out, cudaStream_t s);
 int launch_expand_gid(const int32_t* offsets, int64_t ng, int64_t n, int32_t* gid, cudaStream_t s);
+// integer slice applied inside every group (dtb_slice_groups)
+struct SliceParams { long long start, stop, step, nrows; int has_start, has_stop; };
+size_t slice_scratch_bytes(int64_t ng);
+int launch_slice_groups_plan(const int32_t* offsets, int64_t ng, const SliceParams& p, void* scratch, int32_t* offsets_out,
+                             int32_t* gsel, unsigned long long* totals, cudaStream_t s);
+int launch_slice_groups_emit(const int32_t* offsets, const SliceParams& p, const int32_t* offsets_out, const int32_t* gsel,
+                             int64_t ng_out, int64_t nout, int32_t* gid, int32_t* rows_out, cudaStream_t s);
 // sum/cnt: the MEAN accumulators of the same column; m2: double[ng], zeroed
 int launch_sd(const void* v, int stype, int64_t nv, const int32_t* order, const int32_t* offsets, int64_t ng, int64_t n,
               const unsigned long long* sum, const unsigned long long* cnt, double* m2, void* out, cudaStream_t s);

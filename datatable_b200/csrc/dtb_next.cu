@@ -494,4 +494,183 @@ int launch_lower_bound(const void* sorted, int stype, int64_t n, const void* val
   return DTB_OK;
 }
 
+// ===========================================================================
+// i = integer slice under by() / sort(): the slice applied inside every group
+// (FExpr_Literal_SliceInt::evaluate_iby, expr/fexpr_literal_sliceint.cc:82-170; an integer i is the
+// slice [i, i+1), fexpr_literal_int.cc:146-192).  The reference walks the groups one after the other and
+// appends; here: rows per group (one thread per group), a two-level scan that also drops the groups
+// which select nothing, and a row-parallel emit.
+// ===========================================================================
+// first position, signed step and number of selected rows of the group [off0, off1); restates
+// fexpr_literal_sliceint.cc:101-165 including its int32 casts
+__device__ __forceinline__ void slice_of_group(const SliceParams& p, int32_t off0, int32_t off1, int32_t& first,
+                                               int32_t& step, u32& count)
+{
+  const int32_t n = off1 - off0;
+  step = (int32_t)p.step; count = 0; first = off0;
+  if (step > 0) {
+    int32_t a = p.has_start ? (int32_t)p.start : 0;
+    int32_t b = p.has_stop ? (int32_t)p.stop : (int32_t)p.nrows;
+    if (a < 0) a += n;
+    if (a < 0) a = 0;
+    if (b < 0) b += n;
+    if (b > n) b = n;                                          // (stop > off1 -> off1, relative to the group)
+    if (a < b) { first = off0 + a; count = (u32)(((long long)b - a + step - 1) / step); }
+  } else if (step < 0) {
+    int32_t a = (!p.has_start || p.start >= (long long)n) ? n - 1 : (int32_t)p.start;
+    if (a < 0) a += n;
+    int32_t b;
+    if (!p.has_stop) b = -1;
+    else { b = (int32_t)p.stop; if (b < 0) b += n; if (b < 0) b = -1; }
+    if (a > b) { first = off0 + a; count = (u32)(((long long)a - b - (long long)step - 1) / -(long long)step); }
+  } else {                                                     // step 0: `stop` copies of row `start`
+    int32_t a = (int32_t)p.start;
+    if (a < 0) a += n;
+    if (a >= 0 && a < n) { first = off0 + a; count = (u32)p.stop; }
+  }
+}
+
+constexpr int SL_BLOCK = 1024;                                 // groups per scan block (256 threads x 4)
+
+__global__ void __launch_bounds__(256)
+slice_count_kernel(const int32_t* __restrict__ offsets, int64_t ng, SliceParams p, u32* __restrict__ cnt,
+                   u64* __restrict__ bsum /*[2 * nblocks]: rows, non-empty groups*/)
+{
+  __shared__ u64 wr[8], wg[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  u64 rows = 0, grp = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int64_t g = ((int64_t)blockIdx.x * 256 + t) * 4 + j;
+    u32 c = 0;
+    if (g < ng) { int32_t f, st; slice_of_group(p, offsets[g], offsets[g + 1], f, st, c); cnt[g] = c; }
+    rows += c; grp += c != 0;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { rows += __shfl_xor_sync(0xffffffffu, rows, d); grp += __shfl_xor_sync(0xffffffffu, grp, d); }
+  if (lane == 0) { wr[warp] = rows; wg[warp] = grp; }
+  __syncthreads();
+  if (t == 0) {
+    u64 r = 0, g = 0;
+    for (int w = 0; w < 8; w++) { r += wr[w]; g += wg[w]; }
+    bsum[2 * (size_t)blockIdx.x] = r; bsum[2 * (size_t)blockIdx.x + 1] = g;
+  }
+}
+
+// exclusive scan of the block sums in place (one CTA walks them); totals[0] = rows, totals[1] = groups
+__global__ void __launch_bounds__(1024)
+slice_scan_kernel(u64* __restrict__ bsum, int64_t nb, u64* __restrict__ totals)
+{
+  __shared__ u64 sr[32], sg[32];
+  __shared__ u64 carry_r, carry_g;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (t == 0) { carry_r = 0; carry_g = 0; }
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
+    const int64_t b = b0 + t;
+    const u64 r = b < nb ? bsum[2 * b] : 0, g = b < nb ? bsum[2 * b + 1] : 0;
+    u64 ir = r, ig = g;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const u64 a = __shfl_up_sync(0xffffffffu, ir, d), c = __shfl_up_sync(0xffffffffu, ig, d);
+      if (lane >= d) { ir += a; ig += c; }
+    }
+    if (lane == 31) { sr[warp] = ir; sg[warp] = ig; }
+    __syncthreads();
+    u64 pr = 0, pg = 0;
+    for (int w = 0; w < warp; w++) { pr += sr[w]; pg += sg[w]; }
+    const u64 cr = carry_r, cg = carry_g;
+    if (b < nb) { bsum[2 * b] = cr + pr + ir - r; bsum[2 * b + 1] = cg + pg + ig - g; }
+    __syncthreads();
+    if (t == 1023) { carry_r = cr + pr + ir; carry_g = cg + pg + ig; }
+    __syncthreads();
+  }
+  if (t == 0) { totals[0] = carry_r; totals[1] = carry_g; }
+}
+
+// offsets_out[k] = rows selected before the k-th non-empty group, gsel[k] = its index
+__global__ void __launch_bounds__(256)
+slice_compact_kernel(const u32* __restrict__ cnt, const u64* __restrict__ bsum, int64_t ng,
+                     int32_t* __restrict__ offsets_out, int32_t* __restrict__ gsel)
+{
+  __shared__ u64 wr[8], wg[8];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  u32 c[4]; u64 rows = 0, grp = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int64_t g = ((int64_t)blockIdx.x * 256 + t) * 4 + j;
+    c[j] = g < ng ? cnt[g] : 0;
+    rows += c[j]; grp += c[j] != 0;
+  }
+  u64 ir = rows, ig = grp;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const u64 a = __shfl_up_sync(0xffffffffu, ir, d), b = __shfl_up_sync(0xffffffffu, ig, d);
+    if (lane >= d) { ir += a; ig += b; }
+  }
+  if (lane == 31) { wr[warp] = ir; wg[warp] = ig; }
+  __syncthreads();
+  u64 pr = 0, pg = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) if (w < warp) { pr += wr[w]; pg += wg[w]; }
+  u64 r = bsum[2 * (size_t)blockIdx.x] + pr + ir - rows;
+  u64 k = bsum[2 * (size_t)blockIdx.x + 1] + pg + ig - grp;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (c[j]) {
+      offsets_out[k] = (int32_t)r;
+      gsel[k] = (int32_t)(((int64_t)blockIdx.x * 256 + t) * 4 + j);
+      k++; r += c[j];
+    }
+  }
+}
+
+// rows_out[j] = first(g) + (j - offsets_out[k]) * step for the k-th remaining group g = gsel[k]
+__global__ void slice_emit_kernel(const int32_t* __restrict__ offsets, SliceParams p, const int32_t* __restrict__ offsets_out,
+                                  const int32_t* __restrict__ gsel, const int32_t* __restrict__ gid, int64_t nout,
+                                  int32_t* __restrict__ rows_out)
+{
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nout; j += stride) {
+    const int32_t k = gid[j], g = gsel[k];
+    int32_t first, step; u32 c;
+    slice_of_group(p, offsets[g], offsets[g + 1], first, step, c);
+    rows_out[j] = first + (int32_t)(j - offsets_out[k]) * step;
+  }
+}
+
+size_t slice_scratch_bytes(int64_t ng) {
+  const size_t nb = (size_t)((ng + SL_BLOCK - 1) / SL_BLOCK);
+  return sizeof(u32) * (size_t)(ng + 4) + sizeof(u64) * (2 * nb + 4);
+}
+
+// phase 1: counts, scan, compaction.  totals (device u64[2]) receives {rows selected, groups left};
+// offsets_out needs ng + 1 entries, gsel ng.  The caller reads totals, terminates offsets_out and runs phase 2.
+int launch_slice_groups_plan(const int32_t* offsets, int64_t ng, const SliceParams& p, void* scratch, int32_t* offsets_out,
+                             int32_t* gsel, unsigned long long* totals, cudaStream_t s)
+{
+  if (ng == 0) { DTB_CUDA_CHECK(cudaMemsetAsync(totals, 0, 2 * sizeof(u64), s)); return DTB_OK; }
+  const int64_t nb = (ng + SL_BLOCK - 1) / SL_BLOCK;
+  u32* cnt = (u32*)scratch;
+  u64* bsum = (u64*)((char*)scratch + ((sizeof(u32) * (size_t)(ng + 4) + 7) / 8) * 8);
+  slice_count_kernel<<<(unsigned)nb, 256, 0, s>>>(offsets, ng, p, cnt, bsum);
+  slice_scan_kernel<<<1, 1024, 0, s>>>(bsum, nb, totals);
+  slice_compact_kernel<<<(unsigned)nb, 256, 0, s>>>(cnt, bsum, ng, offsets_out, gsel);
+  count_launch(3);
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
+// phase 2: gid scratch int32[nout]
+int launch_slice_groups_emit(const int32_t* offsets, const SliceParams& p, const int32_t* offsets_out, const int32_t* gsel,
+                             int64_t ng_out, int64_t nout, int32_t* gid, int32_t* rows_out, cudaStream_t s)
+{
+  if (nout == 0) return DTB_OK;
+  DTB_TRY(launch_expand_gid(offsets_out, ng_out, nout, gid, s));
+  slice_emit_kernel<<<grid_for(nout), 256, 0, s>>>(offsets, p, offsets_out, gsel, gid, nout, rows_out);
+  count_launch();
+  DTB_CUDA_CHECK(cudaGetLastError());
+  return DTB_OK;
+}
+
 }  // namespace dtb

@@ -390,6 +390,32 @@ def largest_group(offsets, skip=0):
     return idx.value, size.value
 
 
+SLICE_NA = -2**63
+
+
+def slice_groups(offsets, start=None, stop=None, step=None):
+    """An integer slice applied inside every group (the `i` node under by() / sort(), dtb_slice_groups;
+    expr/fexpr_literal_sliceint.cc:82-170).  Returns (positions into the RowIndex of group(), offsets of the
+    groups that remain); in HBM when `offsets` is."""
+    f = Col(offsets)
+    ng = f.nrows - 1
+    st, sp, se = [SLICE_NA if x is None else int(x) for x in (start, stop, step)]
+    if ng > 0:
+        last = offsets[-1]
+        nrows = int(last.item() if is_tensor(last) else last)
+    else:
+        nrows = 0
+    cap = nrows if se != 0 else ng * (sp if sp != SLICE_NA and sp > 0 else 0)
+    rows, rptr = _alloc(cap, INT32, f.on_device)
+    offs, optr = _alloc(ng + 1, INT32, f.on_device)
+    ngo, nro = ctypes.c_int64(0), ctypes.c_int64(0)
+    check(lib.dtb_slice_groups(ctypes.c_void_p(f.ptr), ng, st, sp, se, _stream(), ctypes.c_void_p(rptr), cap,
+                               ctypes.c_void_p(optr), ctypes.byref(ngo), ctypes.byref(nro)))
+    if ng == 0:
+        offs[:1] = 0
+    return rows[:nro.value], offs[:ngo.value + 1]
+
+
 def join_index(xcols, jcols):
     """natural_join (frame/join.cc:392-470): for every X row the row of J (sorted by its key columns) with
     equal key, or the NA index; int32, in HBM when every column is."""

@@ -328,13 +328,18 @@ class Frame:
                 join_ = m
             else:
                 raise TypeError(f"Unsupported modifier {m!r}")
+        isel = None
         if not (isinstance(i, slice) and i == slice(None)):
-            raise NotImplementedError("row filters are outside the GPU hot path (use i = :)")
+            ok = (isinstance(i, int) and not isinstance(i, bool)) or (
+                isinstance(i, slice) and all(x is None or (isinstance(x, int) and not isinstance(x, bool)) for x in (i.start, i.stop, i.step)))
+            if not ok:
+                raise NotImplementedError("row filters other than an integer or an integer slice are outside the GPU hot path")
+            isel = i
         if join_ is not None:
-            if by_ is not None or sort_ is not None:
-                raise NotImplementedError("join() together with by()/sort() is outside the GPU hot path")
+            if by_ is not None or sort_ is not None or isel is not None:
+                raise NotImplementedError("join() together with i / by() / sort() is outside the GPU hot path")
             return _evaluate_join(self, j, join_.frame)
-        return _evaluate(self, j, by_, sort_)
+        return _evaluate(self, j, by_, sort_, isel)
 
 
 def _from_list(lst):
@@ -365,8 +370,10 @@ def _copy_stream():
 _PIECE_BYTES = 1 << 30        # host value columns of >= 2 GB are uploaded (and reduced) in 1 GB pieces
 
 
-def _evaluate(DT, j, by_, sort_):
-    """EvalContext::evaluate (eval_context.cc:144-172) for the hot-path shapes."""
+def _evaluate(DT, j, by_, sort_, isel=None):
+    """EvalContext::evaluate (eval_context.cc:144-172) for the hot-path shapes.
+    isel: an integer or integer slice for `i` -- applied inside every group under by() / sort()
+    (iexpr_->evaluate_iby, eval_context.cc:154-158), to the rows otherwise (evaluate_i, :159-163)."""
     # Host columns are uploaded once (pinned memory -> DMA), the whole query then runs on
     # HBM-resident buffers, and only the result frame travels back.
     if torch is None or not torch.cuda.is_available():
@@ -449,7 +456,36 @@ def _evaluate(DT, j, by_, sort_):
     ngroups = None
     gb = None
     has_reducer = any(isinstance(e, Reducer) for e in exprs)
-    if keycols:
+    sliced = False
+    if keycols and isel is not None:
+        # i under by() / sort(): group() first, then the slice inside every group; its positions are composed with
+        # the RowIndex (apply_rowindex) and the Groupby is replaced (replace_groupby)
+        order, offsets, ngroups = engine.group(keycols, flags, na_pos)
+        if offsets is None:                                            # sort() alone: Groupby::single_group
+            offsets = torch.tensor([0, len(order)], dtype=torch.int32, device="cuda")
+        if isinstance(isel, int):
+            st_, sp_, se_ = isel, (isel + 1 if isel != -1 else None), 1     # fexpr_literal_int.cc:146-192 == the slice [i, i+1)
+            if not -2**31 <= isel < 2**31:
+                st_, sp_, se_ = 0, 0, 1
+        else:
+            st_, sp_, se_ = isel.start, isel.stop, isel.step
+        sel, offsets = engine.slice_groups(offsets, st_, sp_, se_)
+        order = engine.gather(order, sel)
+        ngroups = len(offsets) - 1
+        sliced = True
+    elif isel is not None:
+        # no by() / sort(): evaluate_i -- a plain row slice (python slice semantics; step 0 = repeat is not taken here)
+        n_ = DT.nrows
+        if isinstance(isel, int):
+            if not -n_ <= isel < n_:
+                raise ValueError(f"Row `{isel}` is invalid for a frame with {n_} row{'s' if n_ != 1 else ''}")
+            rng_ = range(isel % n_, isel % n_ + 1)
+        else:
+            if isel.step == 0:
+                raise NotImplementedError("repeat slices (step 0) without by() are outside the GPU hot path")
+            rng_ = range(*isel.indices(n_))
+        order = torch.arange(rng_.start, rng_.stop, rng_.step, dtype=torch.int32, device="cuda")
+    elif keycols:
         if by_ is not None and has_reducer:
             # RowIndex + Groupby stay in HBM behind a handle; reducers go through it
             # the reducers of j are known before group() runs: hand them over so that the engine can
@@ -507,6 +543,20 @@ def _evaluate(DT, j, by_, sort_):
         out._stypes[name] = st
 
     if by_ is not None:
+        if has_reducer and sliced:
+            first = engine.gather(order, offsets[:-1])
+            for ref in by_.cols:
+                c = dcol(ref.name)
+                add(ref.name, engine.gather(c, first), c.stype)
+            for name, e in zip(names, exprs):
+                if not isinstance(e, Reducer):
+                    raise NotImplementedError("mixing reducers and plain columns under by() is outside the hot path")
+                add(name, _reduce(dcol, e, order, offsets), _red_stype(dcol, e))
+            for n_ in out._cols:
+                if out._stypes[n_] is None:
+                    out._stypes[n_] = engine.Col(out._cols[n_]).stype
+            out._nrows = ngroups
+            return out
         if has_reducer:
             # group keys = first row of every group (get_group_rowindex, eval_context.cc:124-135)
             if early_keys is not None:

@@ -249,6 +249,23 @@ DTB_API int dtb_gather(dtb_col src, int64_t nrows_src,
                dtb_stream stream, void* out);
 
 /*
+ * dtb_slice_groups -- the `i` node of DT[i, j, by(), sort()] when i is an integer slice (or an integer: the
+ * slice [i, i+1)); replaces FExpr_Literal_SliceInt::evaluate_iby (expr/fexpr_literal_sliceint.cc:82-170) and
+ * FExpr_Literal_Int::evaluate_iby (expr/fexpr_literal_int.cc:146-192): the slice is applied inside every group
+ * of the grouped frame.  offsets: int32[ngroups+1] (the Groupby; one group [0, n] under sort() alone).
+ * start / stop / step: DTB_SLICE_NA for a missing member; step 0 = `stop` copies of row `start` (the reference's
+ * repeat slice).  rows_out: int32 positions INTO THE ROWINDEX of group() (the caller composes: RowIndex product =
+ * dtb_gather on the index buffer, eval_context.cc:154-163), at most rows_capacity of them (DTB_ENOSPACE with
+ * *nrows_out = the number needed otherwise; the grouped frame's row count always suffices for step != 0);
+ * offsets_out: int32[ngroups+1], the remaining groups -- groups that select nothing disappear.
+ * Host or device pointers.
+ */
+#define DTB_SLICE_NA INT64_MIN
+DTB_API int dtb_slice_groups(const void* offsets, int64_t ngroups, int64_t start, int64_t stop, int64_t step,
+                     dtb_stream stream, void* rows_out, int64_t rows_capacity, void* offsets_out,
+                     int64_t* ngroups_out, int64_t* nrows_out);
+
+/*
  * dtb_sort_grouped -- replaces Column::sort_grouped (sort.cc:1499-1530): reorders the rows INSIDE every
  * group of (order, offsets) by `value` ascending, NA first, stable; the groups themselves stay where
  * they are.  order_out: int32[offsets[ngroups]].  DTB_OP_MEDIAN / DTB_OP_NUNIQUE expect this order

@@ -255,3 +255,76 @@ def join_index(xcols, xst, jcols, jst):
         if found >= 0:
             out[r] = found
     return out
+
+
+SLICE_NA = -2**63          # a missing slice member (py::oslice::NA)
+
+
+def _i32(x):
+    """static_cast<int32_t>(int64) as the reference does it (two's-complement truncation)."""
+    x &= 0xFFFFFFFF
+    return x - (1 << 32) if x & 0x80000000 else x
+
+
+def slice_groups(offsets, start, stop, step):
+    """FExpr_Literal_SliceInt::evaluate_iby (expr/fexpr_literal_sliceint.cc:82-170): the slice applied inside
+    every group of the grouped frame.  Returns (positions into the RowIndex of group(), new offsets); groups
+    that select nothing disappear.  None / SLICE_NA = missing member; step 0 = repeat row `start` `stop` times."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    nrows = int(offsets[-1]) if len(offsets) else 0
+    NA = (None, SLICE_NA)
+    istart, istop, istep = [SLICE_NA if x in NA else int(x) for x in (start, stop, step)]
+    if istep == SLICE_NA:
+        istep = 1                                               # :86
+    rows, offs = [], [0]
+    step32 = _i32(istep)
+    for g in range(len(offsets) - 1):
+        off0, off1 = int(offsets[g]), int(offsets[g + 1])
+        n = off1 - off0
+        if step32 > 0:                                          # :102-125
+            s0 = 0 if istart == SLICE_NA else istart
+            s1 = nrows if istop == SLICE_NA else istop
+            a, b = _i32(s0), _i32(s1)
+            if a < 0: a += n
+            if a < 0: a = 0
+            a += off0
+            if b < 0: b += n
+            b += off0
+            if b > off1: b = off1
+            if a < b:
+                rows.extend(range(a, b, step32)); offs.append(len(rows))
+        elif step32 < 0:                                        # :126-148
+            a = n - 1 if (istart == SLICE_NA or istart >= n) else _i32(istart)
+            if a < 0: a += n
+            a += off0
+            if istop == SLICE_NA:
+                b = off0 - 1
+            else:
+                b = _i32(istop)
+                if b < 0: b += n
+                if b < 0: b = -1
+                b += off0
+            if a > b:
+                rows.extend(range(a, b, step32)); offs.append(len(rows))
+        else:                                                   # :149-165  step == 0: `stop` copies of row `start`
+            a = _i32(istart)
+            if a < 0: a += n
+            if a < 0 or a >= n:
+                continue
+            rows.extend([a + off0] * istop); offs.append(len(rows))
+    return np.array(rows, dtype=np.int32), np.array(offs, dtype=np.int32)
+
+
+def int_groups(offsets, i):
+    """FExpr_Literal_Int::evaluate_iby (expr/fexpr_literal_int.cc:146-192): the i-th row of every group (negative: from
+    its end); groups that are too short disappear, every remaining group has one row."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    if _i32(i) != i:
+        return np.zeros(0, np.int32), np.zeros(1, np.int32)
+    rows = []
+    for g in range(len(offsets) - 1):
+        a, b = int(offsets[g]), int(offsets[g + 1])
+        r = a + i if i >= 0 else b + i
+        if (i >= 0 and r < b) or (i < 0 and r >= a):
+            rows.append(r)
+    return np.array(rows, dtype=np.int32), np.arange(len(rows) + 1, dtype=np.int32)
