@@ -139,4 +139,19 @@ inline RowIndex natural_join(const std::vector<Column>& xkeys, const std::vector
   return RowIndex(std::move(out));
 }
 
+// The `i` node under by() / sort() for an integer slice (expr/fexpr_literal_sliceint.cc:82-170): the slice applied
+// inside every group; returns positions into the RowIndex of group() and the Groupby of the groups that remain.
+// Missing slice members: DTB_SLICE_NA.
+inline RiGb slice_groups(const Groupby& gby, int64_t start, int64_t stop, int64_t step, dtb_stream stream = nullptr)
+{
+  size_t i0 = 0, nrows = 0;
+  if (gby.size()) gby.get_group(gby.size() - 1, &i0, &nrows);
+  const int64_t cap = step == 0 ? int64_t(gby.size()) * (stop > 0 ? stop : 0) : int64_t(nrows);
+  std::vector<int32_t> rows(size_t(cap > 0 ? cap : 0)), offs(gby.size() + 1);
+  int64_t ngo = 0, nro = 0;
+  check(dtb_slice_groups(gby.offsets_r(), int64_t(gby.size()), start, stop, step, stream, rows.data(), cap, offs.data(), &ngo, &nro));
+  rows.resize(size_t(nro)); offs.resize(size_t(ngo) + 1);
+  return RiGb(RowIndex(std::move(rows)), Groupby(size_t(ngo), std::move(offs)));
+}
+
 }  // namespace dtb

@@ -61,6 +61,16 @@ int main() {
     dtb::RowIndex jr = dtb::natural_join({kc}, {jc});
     for (size_t i = 0; i < n; i += 1013)
       if (jr[i] < 0 || uniq[size_t(jr[i])] != k[i]) { printf("FAIL: join at row %zu\n", i); return 1; }
+    // DT[-2:, :, by(k)]: the last two rows of every group (expr/fexpr_literal_sliceint.cc:82-170)
+    dtb::RiGb sl = dtb::slice_groups(gb, -2, DTB_SLICE_NA, DTB_SLICE_NA);
+    if (sl.second.size() != gb.size()) { printf("FAIL: slice_groups dropped a group\n"); return 1; }
+    for (size_t gg = 0; gg < gb.size(); gg += 89) {
+      size_t i0, i1, j0, j1; gb.get_group(gg, &i0, &i1); sl.second.get_group(gg, &j0, &j1);
+      const size_t want_n = (i1 - i0) < 2 ? (i1 - i0) : 2;
+      if (j1 - j0 != want_n) { printf("FAIL: slice_groups size of group %zu\n", gg); return 1; }
+      for (size_t q = 0; q < want_n; q++)
+        if (size_t(sl.first[j0 + q]) != i1 - want_n + q) { printf("FAIL: slice_groups rows of group %zu\n", gg); return 1; }
+    }
     // unsupported stype -> NotImplError, like sort.cc:673
     bool threw = false;
     try { dtb::Column sc(k.data(), static_cast<dtb::SType>(11), n); dtb::group({sc}, {dtb::SortFlag::NONE}); }
