@@ -329,6 +329,8 @@ class Frame:
             else:
                 raise TypeError(f"Unsupported modifier {m!r}")
         isel = None
+        if i is None:                                    # FExpr_Literal_None: every row (fexpr_literal_none.cc:88-96)
+            i = slice(None)
         if not (isinstance(i, slice) and i == slice(None)):
             ok = (isinstance(i, int) and not isinstance(i, bool)) or (
                 isinstance(i, slice) and all(x is None or (isinstance(x, int) and not isinstance(x, bool)) for x in (i.start, i.stop, i.step)))

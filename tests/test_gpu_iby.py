@@ -97,5 +97,6 @@ def test_frame_plain_row_slices():
     assert DT[2:9:3, :].to_list() == [[2, 5, 8], [1.0, 2.5, 4.0]]
     assert DT[::-4, :].to_list() == [[9, 5, 1], [4.5, 2.5, 0.5]]
     assert DT[-1, :].to_list() == [[9], [4.5]]
+    assert DT[None, :].to_list() == DT[:, :].to_list()          # None selects every row (fexpr_literal_none.cc:88-96)
     with pytest.raises(ValueError):
         DT[10, :]
