@@ -238,6 +238,11 @@ class Frame:
             cols[name], sts[name] = np.ascontiguousarray(a), st
         return cls(cols, stypes=sts)
 
+    def to_jay(self, path):
+        """Frame -> Jay file the reference opens with dt.fread (src/core/jay/save_jay.cc); see datatable_b200/jay.py."""
+        from .jay import save_jay
+        save_jay(self, path)
+
     def to_arrow(self):
         """Frame -> pyarrow.Table with NA sentinels turned back into nulls."""
         import pyarrow as pa

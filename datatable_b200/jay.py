@@ -151,3 +151,99 @@ def open_jay(path, columns=None, device=True):
             mm.close()
         except BufferError:                                              # a numpy view is still alive: let the GC close it
             pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# writer (Frame.to_jay of the reference, src/core/jay/save_jay.cc): the result frame of a query, in the format the
+# reference opens with dt.fread / dt.open.  Fixed-width columns; the meta section is laid out front to back (every
+# FlatBuffers reference points forward) with the alignment the reference's flatbuffers::Verifier checks.
+# ---------------------------------------------------------------------------------------------------------------
+_TO_JAY_STYPE = {st: j for j, (st, _) in _JAY_STYPE.items()}
+
+
+class _Meta:
+    def __init__(self):
+        self.b = bytearray()
+        self.patches = []                                    # (position of a uoffset32, its target's name)
+        self.at = {}
+
+    def pad(self, align, plus=0):
+        while (len(self.b) + plus) % align:
+            self.b += b"\0"
+
+    def ref(self, target):                                   # placeholder for a forward uoffset32
+        self.patches.append((len(self.b), target))
+        self.b += b"\0\0\0\0"
+
+    def finish(self):
+        for pos, target in self.patches:
+            struct.pack_into("<I", self.b, pos, self.at[target] - pos)
+        self.pad(8)
+        return bytes(self.b)
+
+
+def save_jay(frame, path):
+    """Frame -> Jay file (fixed-width columns; the key, if any, must be the leading columns like the reference's)."""
+    names = list(frame.names)
+    nk = len(frame.key)
+    if tuple(names[:nk]) != tuple(frame.key):
+        raise JayError("a keyed frame is stored with its key columns first")
+    data = bytearray(b"JAY1\0\0\0\0")
+    cols = []
+    for nm in names:
+        st = frame._stypes[nm]
+        if st not in _TO_JAY_STYPE:
+            raise _lib.DtbNotImplError(f"column `{nm}` of stype {st} cannot be written to Jay by this engine")
+        a = np.ascontiguousarray(frame.to_numpy(nm))
+        raw = a.tobytes()
+        if a.dtype.kind == "f":
+            nulls = int(np.isnan(a).sum())
+        else:
+            nulls = int((a == np.iinfo(a.dtype).min).sum())
+        cols.append((nm, _TO_JAY_STYPE[st], len(data) - 8, len(raw), nulls))
+        data += raw
+        data += b"\0" * (-len(data) % 8)
+    m = _Meta()
+    m.ref("frame")                                           # root uoffset
+    # Frame: vtable [12, 28, nrows@8, ncols@16, nkeys@4, columns@24], table 8-aligned
+    m.pad(8, plus=12)
+    vt = len(m.b)
+    m.b += struct.pack("<6H", 12, 28, 8, 16, 4, 24)
+    m.at["frame"] = len(m.b)
+    m.b += struct.pack("<iiQQ", len(m.b) - vt, nk, frame.nrows, len(names))
+    m.ref("columns")
+    m.pad(4)
+    m.at["columns"] = len(m.b)
+    m.b += struct.pack("<I", len(cols))
+    for i in range(len(cols)):
+        m.ref(f"col{i}")
+    for i, (nm, jst, off, length, nulls) in enumerate(cols):
+        # Column: ids 3 name@4, 4 nullcount@8, 7 type@24, 8 nrows@16, 9 buffers@28; table size 32, 8-aligned
+        m.pad(8, plus=26 + 2)                                # vtable of 26 bytes + 2 bytes of padding before the table
+        vt = len(m.b)
+        m.b += struct.pack("<13H", 26, 32, 0, 0, 0, 4, 8, 0, 0, 24, 16, 28, 0)
+        m.b += b"\0\0"
+        m.at[f"col{i}"] = len(m.b)
+        m.b += struct.pack("<i", len(m.b) - vt)
+        m.ref(f"name{i}")
+        m.b += struct.pack("<QQ", nulls, frame.nrows)
+        m.ref(f"type{i}")
+        m.ref(f"bufs{i}")
+        # Type: id 0 stype@4
+        m.pad(4, plus=6 + 2)
+        vt = len(m.b)
+        m.b += struct.pack("<3H", 6, 8, 4) + b"\0\0"
+        m.at[f"type{i}"] = len(m.b)
+        m.b += struct.pack("<iB3x", len(m.b) - vt, jst)
+        # buffers: [validity (empty), data]; the structs are 8-aligned, their count sits right before them
+        m.pad(8, plus=4)
+        m.at[f"bufs{i}"] = len(m.b)
+        m.b += struct.pack("<IQQQQ", 2, 0, 0, off, length)
+        enc = nm.encode("utf-8")
+        m.pad(4)
+        m.at[f"name{i}"] = len(m.b)
+        m.b += struct.pack("<I", len(enc)) + enc + b"\0"
+        m.pad(4)
+    meta = m.finish()
+    with open(path, "wb") as fh:
+        fh.write(bytes(data) + meta + struct.pack("<q", len(meta)) + b"\0\0\0\0" + b"1JAY")

@@ -78,3 +78,39 @@ def test_jay_straight_to_hbm_and_grouped():
     S = DT[:, f.i16, dt.sort(f.i16)]
     so, _, _ = orc.group([EXP["i16"]], [4], 1, stypes=[INT16])
     assert np.array_equal(S.to_numpy("i16"), EXP["i16"][so])
+
+
+REF = os.path.join(os.path.dirname(HERE), "oracle", "_ref")
+
+
+def test_writer_round_trip_and_key(tmp_path):
+    from datatable_b200 import jay
+    F = jay.open_jay(J1, columns=FIXED, device=False)
+    p = str(tmp_path / "out.jay")
+    F.to_jay(p)
+    G = jay.open_jay(p, device=False)
+    assert G.names == F.names and list(G.stypes) == list(F.stypes)
+    for nm in FIXED:
+        assert same(G.to_numpy(nm), EXP[nm]), nm
+    K = jay.open_jay(JK, device=False)
+    pk = str(tmp_path / "keyed.jay")
+    K.to_jay(pk)
+    assert jay.read_meta(open(pk, "rb").read())["nkeys"] == 1 and jay.open_jay(pk, device=False).key == ("k",)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "datatable", "__init__.py")),
+                    reason="the staged reference build (oracle/build_ref.sh) is not present")
+def test_reference_opens_what_the_writer_wrote(tmp_path):
+    """The reference's own reader (flatbuffers::Verifier + open_jay.cc) accepts the file and sees the same frame."""
+    import subprocess
+    import sys
+    from datatable_b200 import jay
+    F = jay.open_jay(J1, columns=FIXED, device=False)
+    p = str(tmp_path / "out.jay")
+    F.to_jay(p)
+    code = ("import datatable as dt, sys\n"
+            "A = dt.fread(sys.argv[1]); B = dt.fread(sys.argv[2])[:, :8]\n"
+            "assert A.names == B.names and A.stypes == B.stypes and A.to_list() == B.to_list(), 'differs'\n"
+            "print('same')\n")
+    r = subprocess.run([sys.executable, "-c", code, p, J1], env=dict(os.environ, PYTHONPATH=REF), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "same" in r.stdout, r.stderr[-500:]
