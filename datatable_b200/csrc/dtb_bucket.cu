@@ -115,48 +115,51 @@ struct BucketCols {
   void* out[BK_MAXCOLS];
 };
 
-template <typename L>
-__device__ __forceinline__ void bucket_load_column(const void* v, u64 (&val)[BK_IPT], int64_t base, int tile_n) {
+template <typename L, int TH, int IP>
+__device__ __forceinline__ void bucket_load_column(const void* v, u64 (&val)[IP], int64_t base, int tile_n) {
 #pragma unroll
-  for (int i = 0; i < BK_IPT; i++) {
-    const int p = threadIdx.x + i * BK_THREADS;
+  for (int i = 0; i < IP; i++) {
+    const int p = threadIdx.x + i * TH;
     val[i] = p < tile_n ? (u64)reinterpret_cast<const L*>(v)[base + p] : 0ull;
   }
 }
-__device__ __forceinline__ void bucket_load_column(int esz, const void* v, u64 (&val)[BK_IPT], int64_t base, int tile_n) {
+template <int TH, int IP>
+__device__ __forceinline__ void bucket_load_column(int esz, const void* v, u64 (&val)[IP], int64_t base, int tile_n) {
   switch (esz) {
-    case 1:  bucket_load_column<uint8_t>(v, val, base, tile_n); break;
-    case 2:  bucket_load_column<uint16_t>(v, val, base, tile_n); break;
-    case 4:  bucket_load_column<u32>(v, val, base, tile_n); break;
-    default: bucket_load_column<u64>(v, val, base, tile_n); break;
+    case 1:  bucket_load_column<uint8_t, TH, IP>(v, val, base, tile_n); break;
+    case 2:  bucket_load_column<uint16_t, TH, IP>(v, val, base, tile_n); break;
+    case 4:  bucket_load_column<u32, TH, IP>(v, val, base, tile_n); break;
+    default: bucket_load_column<u64, TH, IP>(v, val, base, tile_n); break;
   }
 }
-template <typename L>
-__device__ __forceinline__ void bucket_stage_column(unsigned char* stage, const u64 (&val)[BK_IPT], const unsigned short (&slot)[BK_IPT], int tile_n) {
+template <typename L, int TH, int IP>
+__device__ __forceinline__ void bucket_stage_column(unsigned char* stage, const u64 (&val)[IP], const unsigned short (&slot)[IP], int tile_n) {
   L* sv = reinterpret_cast<L*>(stage);
 #pragma unroll
-  for (int i = 0; i < BK_IPT; i++) {
-    const int p = threadIdx.x + i * BK_THREADS;
+  for (int i = 0; i < IP; i++) {
+    const int p = threadIdx.x + i * TH;
     if (p < tile_n) sv[slot[i]] = (L)val[i];
   }
 }
-template <typename L>
+template <typename L, int TH>
 __device__ __forceinline__ void bucket_write_column(void* v_out, const unsigned char* stage, const u32* sx, const u32* gbase, int tile_n) {
   const L* sv = reinterpret_cast<const L*>(stage);
-  for (int p = threadIdx.x; p < tile_n; p += BK_THREADS) reinterpret_cast<L*>(v_out)[gbase[sx[p] >> BK_BITS] + (u32)p] = sv[p];
+  for (int p = threadIdx.x; p < tile_n; p += TH) reinterpret_cast<L*>(v_out)[gbase[sx[p] >> BK_BITS] + (u32)p] = sv[p];
 }
 
 // The next column's values are loaded into registers before the staged column is written out, and the
-// columns alternate between two staging buffers: one barrier per column (2 CTAs of 64 registers and 80 KB
-// per SM; 3 CTAs of 40 registers without the prefetch: 15.4 instead of 14.7 ms for C4's three columns).
-__global__ void __launch_bounds__(BK_THREADS, 2)
+// columns alternate between two staging buffers: one barrier per column (2 CTAs and 2 x 80 KB per SM;
+// 3 CTAs of 40 registers without the prefetch: 15.4 instead of 14.7 ms for C4's three columns).
+template <int TH, int IP>
+__global__ void __launch_bounds__(TH, 2048 / TH > 2 ? 2 : 2048 / TH)
 bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, int64_t n, int64_t slab_rows,
                       u32* __restrict__ cursors /*[nslabs][BK_MAXB]*/, unsigned short* __restrict__ xlow_out,
                       const __grid_constant__ BucketCols cols, int stage_bytes)
 {
   __shared__ u32 cnt[BK_MAXB];                 // rows of the bucket in this tile; then: tile slot of its first row
   __shared__ u32 gbase[BK_MAXB];               // (reserved global slot) - (tile slot) of the bucket
-  __shared__ u32 wsum[BK_THREADS / 32];
+  __shared__ u32 wsum[TH / 32];
+  static_assert(TH * IP == BK_TILE && TH >= BK_MAXB, "one tile, thread t owns bucket t in the scan");
   extern __shared__ __align__(16) unsigned char bk_stage[];      // group keys of the staged tile, then two value buffers
   u32* sx = reinterpret_cast<u32*>(bk_stage);
   unsigned char* stage0 = bk_stage + sizeof(u32) * BK_TILE;
@@ -164,23 +167,23 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, int64_t n, int6
   const int64_t base = (int64_t)blockIdx.x * BK_TILE;
   u32* cursor = cursors + (size_t)(base / slab_rows) * BK_MAXB;       // the slab's own reservation cursors
   const int tile_n = (int)((n - base) < (int64_t)BK_TILE ? (n - base) : (int64_t)BK_TILE);
-  for (int i = tid; i < BK_MAXB; i += BK_THREADS) cnt[i] = 0;
+  for (int i = tid; i < BK_MAXB; i += TH) cnt[i] = 0;
   __syncthreads();
 
-  u32 x[BK_IPT]; unsigned short slot[BK_IPT]; u64 val[BK_IPT];
+  u32 x[IP]; unsigned short slot[IP]; u64 val[IP];
 #pragma unroll
-  for (int i = 0; i < BK_IPT; i++) {
-    const int p = tid + i * BK_THREADS;
+  for (int i = 0; i < IP; i++) {
+    const int p = tid + i * TH;
     x[i] = p < tile_n ? (xkeys[base + p] >> gshift) : 0xffffffffu;
   }
-  bucket_load_column(cols.esz[0], cols.in[0], val, base, tile_n);
+  bucket_load_column<TH, IP>(cols.esz[0], cols.in[0], val, base, tile_n);
 #pragma unroll
-  for (int i = 0; i < BK_IPT; i++)
+  for (int i = 0; i < IP; i++)
     slot[i] = (x[i] != 0xffffffffu) ? (unsigned short)atomicAdd(&cnt[x[i] >> BK_BITS], 1u) : (unsigned short)0;
   __syncthreads();
 
   // exclusive scan of cnt[] over the buckets (one per thread), one global reservation per non-empty bucket
-  const u32 c0 = cnt[tid];
+  const u32 c0 = tid < BK_MAXB ? cnt[tid] : 0u;
   u32 incl = c0;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
@@ -188,22 +191,22 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, int64_t n, int6
   __syncthreads();
   u32 wpre = 0;
 #pragma unroll
-  for (int w = 0; w < BK_THREADS / 32; w++) if (w < warp) wpre += wsum[w];
+  for (int w = 0; w < TH / 32; w++) if (w < warp) wpre += wsum[w];
   const u32 e0 = wpre + incl - c0;
   __syncthreads();
-  cnt[tid] = e0;
+  if (tid < BK_MAXB) cnt[tid] = e0;
   if (c0) gbase[tid] = atomicAdd(&cursor[tid], c0) - e0;
   __syncthreads();
 
 #pragma unroll
-  for (int i = 0; i < BK_IPT; i++) {
+  for (int i = 0; i < IP; i++) {
     if (x[i] != 0xffffffffu) {
       slot[i] = (unsigned short)(cnt[x[i] >> BK_BITS] + slot[i]);
       sx[slot[i]] = x[i];
     }
   }
   __syncthreads();
-  for (int p = tid; p < tile_n; p += BK_THREADS) {
+  for (int p = tid; p < tile_n; p += TH) {
     const u32 xx = sx[p];
     xlow_out[gbase[xx >> BK_BITS] + (u32)p] = (unsigned short)(xx & (BK_KEYS - 1));
   }
@@ -211,18 +214,18 @@ bucket_scatter_kernel(const u32* __restrict__ xkeys, int gshift, int64_t n, int6
     const int esz = cols.esz[c];
     unsigned char* stage = stage0 + (size_t)(c & 1) * stage_bytes;
     switch (esz) {
-      case 1:  bucket_stage_column<uint8_t>(stage, val, slot, tile_n); break;
-      case 2:  bucket_stage_column<uint16_t>(stage, val, slot, tile_n); break;
-      case 4:  bucket_stage_column<u32>(stage, val, slot, tile_n); break;
-      default: bucket_stage_column<u64>(stage, val, slot, tile_n); break;
+      case 1:  bucket_stage_column<uint8_t, TH, IP>(stage, val, slot, tile_n); break;
+      case 2:  bucket_stage_column<uint16_t, TH, IP>(stage, val, slot, tile_n); break;
+      case 4:  bucket_stage_column<u32, TH, IP>(stage, val, slot, tile_n); break;
+      default: bucket_stage_column<u64, TH, IP>(stage, val, slot, tile_n); break;
     }
     __syncthreads();       // also: every thread is done reading the other buffer (column c - 1)
-    if (c + 1 < cols.ncols) bucket_load_column(cols.esz[c + 1], cols.in[c + 1], val, base, tile_n);
+    if (c + 1 < cols.ncols) bucket_load_column<TH, IP>(cols.esz[c + 1], cols.in[c + 1], val, base, tile_n);
     switch (esz) {
-      case 1:  bucket_write_column<uint8_t>(cols.out[c], stage, sx, gbase, tile_n); break;
-      case 2:  bucket_write_column<uint16_t>(cols.out[c], stage, sx, gbase, tile_n); break;
-      case 4:  bucket_write_column<u32>(cols.out[c], stage, sx, gbase, tile_n); break;
-      default: bucket_write_column<u64>(cols.out[c], stage, sx, gbase, tile_n); break;
+      case 1:  bucket_write_column<uint8_t, TH>(cols.out[c], stage, sx, gbase, tile_n); break;
+      case 2:  bucket_write_column<uint16_t, TH>(cols.out[c], stage, sx, gbase, tile_n); break;
+      case 4:  bucket_write_column<u32, TH>(cols.out[c], stage, sx, gbase, tile_n); break;
+      default: bucket_write_column<u64, TH>(cols.out[c], stage, sx, gbase, tile_n); break;
     }
   }
 }
@@ -395,9 +398,10 @@ int launch_bucketed_reduce(const u32* xkeys, int gshift, int dbits, int ncols, c
   const unsigned tiles = (unsigned)((n + BK_TILE - 1) / BK_TILE);
   const int stage_bytes = maxb * BK_TILE;
   const size_t sm_scatter = (size_t)4 * BK_TILE + (size_t)stage_bytes * (ncols > 1 ? 2 : 1);
-  DTB_CUDA_CHECK(cudaFuncSetAttribute(bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * BK_TILE));
+  // 1024 threads x 4 rows: 32 registers, two CTAs = every warp slot of the SM (512 x 8 at 64 registers: 14.6 instead of 14.1 ms)
+  DTB_CUDA_CHECK(cudaFuncSetAttribute(bucket_scatter_kernel<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 20 * BK_TILE));
   prof_begin("bucket_scatter", s);
-  bucket_scatter_kernel<<<tiles, BK_THREADS, sm_scatter, s>>>(xkeys, gshift, n, slab_rows, cursor, xlow, cols, stage_bytes);
+  bucket_scatter_kernel<1024, 4><<<tiles, 1024, sm_scatter, s>>>(xkeys, gshift, n, slab_rows, cursor, xlow, cols, stage_bytes);
   prof_end(s);
   count_launch();
   DTB_CUDA_CHECK(cudaGetLastError());
