@@ -416,8 +416,6 @@ def run_b200(args, rank, local_rank, world):
             le1 = torch.cuda.Event(enable_timing=True); le1.record()
             local_ev.append((le0, le1))
         launches[0] += _lib.last_call_stats()["kernels_launched"]
-        if profiling[0]:
-            main_prof.extend(_lib.profile_records(reset=True))
         sums = gb.reduced(0)
         ng = gb.ngroups
         if world > 1:
@@ -425,8 +423,6 @@ def run_b200(args, rank, local_rank, world):
             launches[0] += 2
             gkeys, sums = ddist.merge_partials_dense(gkeys, sums, _lib.OP_SUM, key_range=(0, G - 1))   # dictionary-coded keys
             launches[0] += ddist.LAST_MERGE_LAUNCHES
-            if profiling[0]:
-                _lib.profile_records(reset=True)
         gb.close()
         return None, None, ng, sums
 
@@ -457,7 +453,10 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     engine.set_option("profile", 0)
     profiling[0] = False
-    _lib.profile_records(reset=True)
+    # the engine recorded CUDA events around its kernels during the timed steps; they are read only now, so
+    # that no step waited for them (the dense merge at N > 1 launches none of these families)
+    own = ("col_stats", "radix_count", "radix_scatter", "group_offsets_from_counts", "group_offsets", "reduce_direct", "reduce")
+    main_prof.extend(r for r in _lib.profile_records(reset=True) if r[0] in own)
     per_rank = None
     if world > 1:
         # every rank's own time in group()+reduce, so that the line shows how much of a step is the merge and

@@ -68,11 +68,13 @@ void prof_end(cudaStream_t s) {
   t_prof_cur_on = false;
 }
 
-// call after the stream has been synchronised
+// Lazy: the calls only record events; the first query (dtb_profile_count / _reset) waits for them.  (A sync at the
+// end of every profiled call kept the host from running ahead and cost ~0.4 ms per C2 step in bench.py's timed region.)
 static void prof_collect() {
   for (auto& r : t_prof_open) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) t_prof_done.emplace_back(r.name, (double)ms);
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess)
+      t_prof_done.emplace_back(r.name, (double)ms);
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   t_prof_open.clear();
@@ -88,6 +90,15 @@ static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 #define DTB_TL(label) do { if (opt_verbose >= 2) fprintf(stderr, "[dtb200]   t=%9.3f ms  %s\n", now_ms() - tl0, label); } while (0)
+
+// Waits for the stream by polling.  cudaStreamSynchronize parks the thread (the context is usually created by the
+// host framework with the default scheduling policy) and wakes it 50-100 us after the stream drained; group() has
+// two such waits on its critical path (the statistics, the number of groups) with the GPU idle behind them.
+static cudaError_t stream_wait(cudaStream_t s) {
+  cudaError_t e;
+  while ((e = cudaStreamQuery(s)) == cudaErrorNotReady) {}
+  return e;
+}
 
 static int ensure_context() {
   int dev = 0;
@@ -500,7 +511,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
   }
   ColStats h_stats[MAX_KEYS];
   DTB_CUDA_CHECK(cudaMemcpyAsync(h_stats, d_stats.p, sizeof(ColStats) * nkeys, cudaMemcpyDeviceToHost, s));
-  DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+  DTB_CUDA_CHECK(stream_wait(s));
 
   DTB_TL("stats synced");
   KeyPlan kp; memset(&kp, 0, sizeof(kp));
@@ -752,7 +763,7 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
     }
     u64 h_ng[2] = {0, 0};                    // {groups, rows of the largest group (count-table path only)}
     DTB_CUDA_CHECK(cudaMemcpyAsync(h_ng, d_ng, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
-    DTB_CUDA_CHECK(cudaStreamSynchronize(s));
+    DTB_CUDA_CHECK(stream_wait(s));
     res.ngroups = (int64_t)h_ng[0];
     // group key of every group, for the direct-address reducers
     bool staged = false;
@@ -912,7 +923,6 @@ static int group_core(const dtb_col* keys, int nkeys, const int* flags, int na_p
       fr->out[i] = ob.detach();
     }
   }
-  if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   return DTB_OK;
 }
 
@@ -999,7 +1009,7 @@ int dtb_set_option(const char* name, int64_t value) {
   return DTB_EINVAL;
 }
 
-int dtb_profile_count(void) { return (int)t_prof_done.size(); }
+int dtb_profile_count(void) { prof_collect(); return (int)t_prof_done.size(); }
 
 int dtb_profile_get(int i, char* name, int cap, double* ms) {
   if (i < 0 || i >= (int)t_prof_done.size() || !name || cap < 1 || !ms) { set_error("bad dtb_profile_get arguments"); return DTB_EINVAL; }
@@ -1009,7 +1019,7 @@ int dtb_profile_get(int i, char* name, int cap, double* ms) {
   return DTB_OK;
 }
 
-int dtb_profile_reset(void) { t_prof_done.clear(); return DTB_OK; }
+int dtb_profile_reset(void) { prof_collect(); t_prof_done.clear(); return DTB_OK; }
 
 int dtb_get_option(const char* name, int64_t* value) {
   if (!name || !value) { set_error("NULL argument"); return DTB_EINVAL; }
@@ -1193,7 +1203,6 @@ int dtb_reduce(int op, dtb_col value, int64_t nrows_value, const void* order, in
                                (const int32_t*)d_off.dptr, ngroups, n, acc.as<u64>(),
                                acc.as<u64>() + ngroups, d_out.dptr, s, xb ? extra.p : nullptr));
   }
-  if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   if (d_out.staged()) {
     DTB_TRY(d_out.finish((size_t)ngroups * stype_bytes(out_st), s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -1235,7 +1244,6 @@ int dtb_groupby_reduce(dtb_groupby* g, int op, dtb_col value, int64_t nrows_valu
                                  (const uint32_t*)g->gkeys, g->ngroups, acc.as<u64>(),
                                  acc.as<u64>() + g->table, d_out.dptr, s));
   }
-  if (opt_profile) { DTB_CUDA_CHECK(cudaStreamSynchronize(s)); prof_collect(); }
   if (d_out.staged()) {
     DTB_TRY(d_out.finish((size_t)g->ngroups * stype_bytes(out_st), s));
     DTB_CUDA_CHECK(cudaStreamSynchronize(s));

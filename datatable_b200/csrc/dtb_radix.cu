@@ -194,15 +194,20 @@ fold_counts_kernel(const unsigned short* __restrict__ tile_hist, const unsigned 
 __global__ void __launch_bounds__(256)
 chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, int nbins, u32* __restrict__ total)
 {
+  // one CTA per digit walks the chunks, 1024 per round: every thread owns four consecutive chunks (four strided
+  // loads in flight; one chunk per thread and round took 60 dependent rounds for 1e9 rows: 0.08 ms per pass)
   __shared__ u32 wsum[8];
   __shared__ u32 s_carry;
   const int d = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   if (t == 0) s_carry = 0;
   __syncthreads();
-  for (int64_t c0 = 0; c0 < nchunks; c0 += 256) {
-    const int64_t c = c0 + t;
-    const u32 v = (c < nchunks) ? counts[(size_t)c * nbins + d] : 0;
-    u32 incl = v;
+  for (int64_t c0 = 0; c0 < nchunks; c0 += 1024) {
+    const int64_t c = c0 + (int64_t)t * 4;
+    u32 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = (c + j < nchunks) ? counts[(size_t)(c + j) * nbins + d] : 0;
+    const u32 tsum = v[0] + v[1] + v[2] + v[3];
+    u32 incl = tsum;
 #pragma unroll
     for (int k = 1; k < 32; k <<= 1) { const u32 o = __shfl_up_sync(0xffffffffu, incl, k); if (lane >= k) incl += o; }
     if (lane == 31) wsum[warp] = incl;
@@ -211,7 +216,9 @@ chunk_scan_kernel(u32* __restrict__ counts, int64_t nchunks, int nbins, u32* __r
 #pragma unroll
     for (int w = 0; w < 8; w++) if (w < warp) wpre += wsum[w];
     const u32 carry = s_carry;
-    if (c < nchunks) counts[(size_t)c * nbins + d] = carry + wpre + incl - v;
+    u32 e = carry + wpre + incl - tsum;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { if (c + j < nchunks) counts[(size_t)(c + j) * nbins + d] = e; e += v[j]; }
     __syncthreads();
     if (t == 255) s_carry = carry + wpre + incl;
     __syncthreads();
