@@ -349,13 +349,17 @@ DTB_API int dtb_memcpy(void* dst, const void* src, int64_t nbytes, dtb_stream st
  *   "radix_bits"   largest digit width of the LSD passes: 4..8, or 0 (default) = 8 bits (wider digits were
  *                  built and measured slower twice)
  *   "verbose"      1 = print the pass plan to stderr
- *   "profile"      1 = bracket every kernel with CUDA events on the call's stream
+ *   "profile"      1 = bracket every kernel with CUDA events on the call's stream (the calls do not wait for
+ *                  them; dtb_profile_count / dtb_profile_reset do)
  *   "overlap_reducers" 1 = dtb_groupby_create_reduce runs the direct-address reducers on a side stream
  *                  concurrently with the sort passes (default 0: same stream, measured equally fast)
  *   "stage_keys"   0 (default) = the first count and scatter kernels of a single raw key column normalise it on
  *                  the fly (no normalised-key array is written); 1 = the first count kernel materialises the
  *                  normalised keys and the first scatter reads those (round-1 behaviour; measured at 1e9 rows:
  *                  +0.5 ms and +8 GB of DRAM traffic for int32 keys, +0.9 ms for float64)
+ *   "fuse_stats_hist" 1 (default) = single-column keys: the statistics kernel also counts the low 8 bits of every
+ *                  tile and the first radix pass folds that into its digit counts instead of reading the column
+ *                  again; 0 = separate statistics and count kernels
  *   "bucketed_reducers" 1 (default) = value columns that would cost two or more L2 atomics per row (mean, or
  *                  several reducers of one column) take the bucketed multi-reducer (dtb_bucket.cu); 0 = always
  *                  one streaming pass per reducer
@@ -365,7 +369,8 @@ DTB_API int dtb_set_option(const char* name, int64_t value);
 DTB_API int dtb_get_option(const char* name, int64_t* value);
 
 /* Kernel timings collected while option "profile" is on (accumulated on the calling
- * thread until dtb_profile_reset): record i = (kernel family name, milliseconds). */
+ * thread until dtb_profile_reset): record i = (kernel family name, milliseconds).
+ * dtb_profile_count waits for the recorded events of earlier calls before it answers. */
 DTB_API int dtb_profile_count(void);
 DTB_API int dtb_profile_get(int i, char* name, int cap, double* ms);
 DTB_API int dtb_profile_reset(void);
