@@ -1,0 +1,32 @@
+"""Experiment: scatter kernel with 512 threads x 8 rows (option scatter_threads = 512) against 256 x 16:
+identical RowIndex / offsets, per-kernel times on C2 at 1e9 rows; then the single-key parity tests with the option on."""
+import sys, torch
+sys.path.insert(0, ".")
+from datatable_b200 import engine, _lib
+n = 1_000_000_000
+g = torch.Generator(device="cuda"); g.manual_seed(42)
+k = torch.randint(0, 1_000_000, (n,), generator=g, device="cuda", dtype=torch.int32)
+v = torch.rand(n, generator=g, device="cuda", dtype=torch.float64)
+
+def fam(fn):
+    for _ in range(2): fn()
+    engine.set_option("profile", 1); _lib.lib.dtb_profile_reset(); fn()
+    out = {}
+    for nm, ms in _lib.profile_records(): out.setdefault(nm, []).append(round(ms, 3))
+    engine.set_option("profile", 0)
+    return out
+
+res = {}
+for th in (256, 512):
+    engine.set_option("scatter_threads", th)          # (option removed with the variant: this script documents the experiment)
+    c2 = lambda: engine.Groupby([k], [0], 1, reducers=[(_lib.OP_SUM, v)]).close()
+    print("threads", th, fam(c2), flush=True)
+    o, f, ng = engine.group([k[:200_000_000]], [0], 1)
+    res[th] = (o, f)
+print("identical RowIndex / offsets:", bool(torch.equal(res[256][0], res[512][0])), bool(torch.equal(res[256][1], res[512][1])), flush=True)
+del res, k, v
+torch.cuda.empty_cache()
+engine.set_option("scatter_threads", 512)
+import pytest
+rc = pytest.main(["tests/test_gpu_random.py", "tests/test_gpu_fuzz.py", "-q", "-x", "-m", "gpu", "-k", "single_key or groupby_reducers or multikey or fuzz or fused_stats", "-p", "no:cacheprovider"])
+print("pytest with scatter_threads=512 rc =", rc)
