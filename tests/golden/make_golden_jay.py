@@ -47,5 +47,9 @@ K.key = "k"
 K.to_jay(os.path.join(HERE, "jay_keyed.jay"))
 exp["keyed.k"] = np.arange(0, 600, 3, dtype=np.int32)
 exp["keyed.v"] = np.arange(200, dtype=np.float64) * 0.5
+# a 0-row frame and a time64 column (expected values are written in tests/test_jay.py)
+dt.Frame(a=[], b=[], stypes={"a": dt.int32, "b": dt.float64}).to_jay(os.path.join(HERE, "jay_empty.jay"))
+dt.Frame(t=[datetime.datetime(2020, 1, 1, 12, 0, 0), None, datetime.datetime(1969, 12, 31, 23, 59, 59)],
+         x=[1, 2, 3]).to_jay(os.path.join(HERE, "jay_time.jay"))
 np.savez_compressed(os.path.join(HERE, "jay_expected.npz"), **exp)
 print("wrote", os.path.getsize(os.path.join(HERE, "jay_v1.jay")), os.path.getsize(os.path.join(HERE, "jay_keyed.jay")), "bytes;", DT.stypes)

@@ -114,3 +114,14 @@ def test_reference_opens_what_the_writer_wrote(tmp_path):
             "print('same')\n")
     r = subprocess.run([sys.executable, "-c", code, p, J1], env=dict(os.environ, PYTHONPATH=REF), capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "same" in r.stdout, r.stderr[-500:]
+
+
+def test_time64_and_empty_frames():
+    """Files written by the reference: a 0-row frame, and a time64 column (int64 nanoseconds, NA = INT64_MIN)."""
+    from datatable_b200 import jay, _lib
+    E = jay.open_jay(os.path.join(HERE, "golden", "jay_empty.jay"), device=False)
+    assert E.names == ("a", "b") and E.nrows == 0 and list(E.stypes) == [_lib.INT32, _lib.FLOAT64]
+    T = jay.open_jay(os.path.join(HERE, "golden", "jay_time.jay"), device=False)
+    assert list(T.stypes) == [_lib.TIME64, _lib.INT32]
+    assert np.array_equal(T.to_numpy("t"), np.array([1577880000000000000, -2**63, -1000000000], dtype=np.int64))
+    assert np.array_equal(T.to_numpy("x"), np.array([1, 2, 3], dtype=np.int32))
